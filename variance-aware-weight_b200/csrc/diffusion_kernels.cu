@@ -1,0 +1,339 @@
+// diffusion_kernels.cu — K1 (fused q_sample + target) and K2 (fused weighted-MSE forward + backward).
+//
+// Replaces, on the hot path of GaussianDiffusion.training_losses (reference
+// tools/gaussian_diffusion.py:834-930):
+//   K1: q_sample (:234-252) + compute_target (:818-832) + the four _extract_into_tensor gathers (:1059-1072)
+//   K2: (target - out)**2 -> mean_flat (tools/nn.py:86-90) -> w * raw_mse (:911-913) and its autograd backward
+//
+// Rounding contract (bit-exact with the reference's fp32 eager path):
+//   x_t    = fl( fl(a*x0) + fl(s*eps) )      two multiplies and one add, never contracted into an FMA
+//   v-tgt  = fl( fl(a*eps) - fl(s*x0) )
+// a = float(sqrt_alphas_cumprod[t]), s = float(sqrt_one_minus_alphas_cumprod[t]) (f64 table rounded once to f32).
+#include "vaw_common.cuh"
+
+namespace {
+
+// ModelMeanType codes follow the reference enum (enum.auto() starts at 1), gaussian_diffusion.py:21-32
+enum : int { MT_PREVIOUS_X = 1, MT_START_X = 2, MT_EPSILON = 3, MT_VELOCITY = 4, MT_VECTOR = 5, MT_SCORE = 6 };
+
+struct Coef {
+  float a, s;    // alpha_t, sigma_t
+  float c0, c1;  // posterior_mean_coef1/2 (PREVIOUS_X) or d_alpha/d_sigma (VECTOR)
+};
+
+__device__ __forceinline__ Coef load_coef(const long long* __restrict__ t, const float* __restrict__ tab_a,
+                                          const float* __restrict__ tab_s, const float* __restrict__ tab_c0,
+                                          const float* __restrict__ tab_c1, long long n) {
+  // t != null: tables are [T] and indexed by the integer timestep (diffusion mode)
+  // t == null: the "tables" are per-sample arrays [N] (flow-matching mode, continuous time)
+  long long i = t ? t[n] : n;
+  Coef c;
+  c.a = __ldg(tab_a + i);
+  c.s = __ldg(tab_s + i);
+  c.c0 = tab_c0 ? __ldg(tab_c0 + i) : 0.f;
+  c.c1 = tab_c1 ? __ldg(tab_c1 + i) : 0.f;
+  return c;
+}
+
+__device__ __forceinline__ float mix2(float p, float u, float q, float v) {
+  return __fadd_rn(__fmul_rn(p, u), __fmul_rn(q, v));
+}
+
+__device__ __forceinline__ float target_of(int mean_type, const Coef& c, float x0, float eps, float xt) {
+  switch (mean_type) {
+    case MT_START_X: return x0;
+    case MT_EPSILON: return eps;
+    case MT_VELOCITY: return __fsub_rn(__fmul_rn(c.a, eps), __fmul_rn(c.s, x0));
+    case MT_PREVIOUS_X: return mix2(c.c0, x0, c.c1, xt);
+    case MT_VECTOR: return mix2(c.c0, x0, c.c1, eps);
+    case MT_SCORE: return __fdiv_rn(-eps, c.s);
+    default: return eps;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: x_t (and optionally the regression target) from x0, eps, t.  12 B/element (eps/x0 target need
+// no extra write), 16 B/element when the target is materialised.
+// ------------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+qsample_target_kernel(const float* __restrict__ x0, const float* __restrict__ eps, const long long* __restrict__ t,
+                      const float* __restrict__ tab_a, const float* __restrict__ tab_s,
+                      const float* __restrict__ tab_c0, const float* __restrict__ tab_c1, float* __restrict__ x_t,
+                      float* __restrict__ target, int mean_type, long long N, long long chw) {
+  if (VEC) {
+    const long long chw4 = chw >> 2;
+    const long long total4 = N * chw4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+      const long long n = i / chw4;
+      const Coef c = load_coef(t, tab_a, tab_s, tab_c0, tab_c1, n);
+      const float4 x = ldg_stream_f4(reinterpret_cast<const float4*>(x0) + i);
+      const float4 e = ldg_stream_f4(reinterpret_cast<const float4*>(eps) + i);
+      float4 o;
+      o.x = mix2(c.a, x.x, c.s, e.x);
+      o.y = mix2(c.a, x.y, c.s, e.y);
+      o.z = mix2(c.a, x.z, c.s, e.z);
+      o.w = mix2(c.a, x.w, c.s, e.w);
+      stg_stream_f4(reinterpret_cast<float4*>(x_t) + i, o);
+      if (target) {
+        float4 g;
+        g.x = target_of(mean_type, c, x.x, e.x, o.x);
+        g.y = target_of(mean_type, c, x.y, e.y, o.y);
+        g.z = target_of(mean_type, c, x.z, e.z, o.z);
+        g.w = target_of(mean_type, c, x.w, e.w, o.w);
+        stg_stream_f4(reinterpret_cast<float4*>(target) + i, g);
+      }
+    }
+  } else {
+    const long long total = N * chw;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+      const long long n = i / chw;
+      const Coef c = load_coef(t, tab_a, tab_s, tab_c0, tab_c1, n);
+      const float x = x0[i], e = eps[i];
+      const float o = mix2(c.a, x, c.s, e);
+      x_t[i] = o;
+      if (target) target[i] = target_of(mean_type, c, x, e, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: one CTA per sample.  Reads the model output (fp32 or bf16), rebuilds the target on the fly from
+// x0/eps (no target tensor in HBM), accumulates sum((target-out)^2) with a fixed reduction tree
+// (thread-serial -> warp shuffle -> 8-warp shared reduce), and writes
+//   mse[n]  = w_n * sum / chw          (terms["mse"], reference :913)
+//   grad[n,i] = g_n * w_n * 2 (out - target) / chw     (d loss_n / d out, times the upstream per-sample factor)
+// in the same pass.  12 B/element fp32, 8 B/element bf16 (+ x0/eps re-read when the target needs both).
+// ------------------------------------------------------------------------------------------------
+template <typename OutT>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  static __device__ __forceinline__ float4 load(const float* p, long long i4) {
+    return ldg_stream_f4(reinterpret_cast<const float4*>(p) + i4);
+  }
+  static __device__ __forceinline__ void store(float* p, long long i4, float4 v) {
+    stg_stream_f4(reinterpret_cast<float4*>(p) + i4, v);
+  }
+};
+template <>
+struct Vec4<bf16> {
+  static __device__ __forceinline__ float4 load(const bf16* p, long long i4) {
+    uint2 u = ldg_stream_u2(reinterpret_cast<const uint2*>(p) + i4);
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ void store(bf16* p, long long i4, float4 v) {
+    uint2 u;
+    u.x = pack_bf16(v.x, v.y);
+    u.y = pack_bf16(v.z, v.w);
+    stg_stream_u2(reinterpret_cast<uint2*>(p) + i4, u);
+  }
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+wmse_fwd_bwd_kernel(const OutT* __restrict__ out, const float* __restrict__ x0, const float* __restrict__ eps,
+                    const long long* __restrict__ t, const float* __restrict__ tab_a, const float* __restrict__ tab_s,
+                    const float* __restrict__ tab_c0, const float* __restrict__ tab_c1,
+                    const float* __restrict__ w_tab, float* __restrict__ mse, float* __restrict__ raw_mse,
+                    OutT* __restrict__ grad, const float* __restrict__ gscale_n, float gscale, int mean_type,
+                    long long chw) {
+  const long long n = blockIdx.x;
+  const Coef c = load_coef(t, tab_a, tab_s, tab_c0, tab_c1, n);
+  const float w = w_tab ? __ldg(w_tab + (t ? t[n] : n)) : 1.f;
+  const float inv = 1.0f / (float)chw;
+  const float g = (gscale_n ? __ldg(gscale_n + n) : 1.f) * gscale * w * 2.f * inv;
+  const bool need_x0 = (mean_type != MT_EPSILON && mean_type != MT_SCORE);
+  const bool need_eps = (mean_type != MT_START_X);
+  const long long base = n * chw;
+  float acc = 0.f;
+  if ((chw & 3) == 0) {
+    const long long chw4 = chw >> 2, base4 = base >> 2;
+    for (long long i = threadIdx.x; i < chw4; i += blockDim.x) {
+      const float4 o = Vec4<OutT>::load(out, base4 + i);
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f), e = x;
+      if (need_x0) x = ldg_stream_f4(reinterpret_cast<const float4*>(x0) + base4 + i);
+      if (need_eps) e = ldg_stream_f4(reinterpret_cast<const float4*>(eps) + base4 + i);
+      float4 tg;
+      tg.x = target_of(mean_type, c, x.x, e.x, mix2(c.a, x.x, c.s, e.x));
+      tg.y = target_of(mean_type, c, x.y, e.y, mix2(c.a, x.y, c.s, e.y));
+      tg.z = target_of(mean_type, c, x.z, e.z, mix2(c.a, x.z, c.s, e.z));
+      tg.w = target_of(mean_type, c, x.w, e.w, mix2(c.a, x.w, c.s, e.w));
+      const float dx = tg.x - o.x, dy = tg.y - o.y, dz = tg.z - o.z, dw = tg.w - o.w;
+      acc += dx * dx;
+      acc += dy * dy;
+      acc += dz * dz;
+      acc += dw * dw;
+      if (grad) Vec4<OutT>::store(grad, base4 + i, make_float4(-g * dx, -g * dy, -g * dz, -g * dw));
+    }
+  } else {
+    for (long long i = threadIdx.x; i < chw; i += blockDim.x) {
+      const float o = (float)out[base + i];
+      const float x = need_x0 ? x0[base + i] : 0.f, e = need_eps ? eps[base + i] : 0.f;
+      const float tg = target_of(mean_type, c, x, e, mix2(c.a, x, c.s, e));
+      const float d = tg - o;
+      acc += d * d;
+      if (grad) grad[base + i] = (OutT)(-g * d);
+    }
+  }
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i];
+    const float m = s * inv;
+    if (raw_mse) raw_mse[n] = m;
+    mse[n] = w * m;
+  }
+}
+
+// per-sample row scale: y[n, :] = x[n, :] * s[n] (backward of K2 when the upstream grad arrives late)
+template <typename T>
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(const T* __restrict__ x, const float* __restrict__ s, T* __restrict__ y, long long N,
+                  long long chw) {
+  const long long total = N * chw;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    y[i] = (T)((float)x[i] * s[i / chw]);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int vaw_qsample_target(const float* x0, const float* noise, const long long* t, const float* tab_alpha,
+                                  const float* tab_sigma, const float* tab_c0, const float* tab_c1, float* x_t,
+                                  float* target, int mean_type, long long N, long long chw, cudaStream_t stream) {
+  VAW_CHECK_ARG(x0 && noise && tab_alpha && tab_sigma && x_t, "vaw_qsample_target: null pointer");
+  VAW_CHECK_ARG(N >= 0 && chw > 0, "vaw_qsample_target: bad shape N=%lld chw=%lld", N, chw);
+  VAW_CHECK_ARG(mean_type >= MT_PREVIOUS_X && mean_type <= MT_SCORE, "vaw_qsample_target: bad mean_type %d",
+                mean_type);
+  if (N == 0) return VAW_OK;
+  const bool vec = (chw % 4 == 0) && ((((uintptr_t)x0 | (uintptr_t)noise | (uintptr_t)x_t | (uintptr_t)target) & 15) == 0);
+  const long long work = vec ? N * (chw / 4) : N * chw;
+  long long blocks = (work + 255) / 256;
+  const long long cap = (long long)vaw_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (vec)
+    qsample_target_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(x0, noise, t, tab_alpha, tab_sigma, tab_c0,
+                                                                      tab_c1, x_t, target, mean_type, N, chw);
+  else
+    qsample_target_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(x0, noise, t, tab_alpha, tab_sigma, tab_c0,
+                                                                       tab_c1, x_t, target, mean_type, N, chw);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+extern "C" int vaw_wmse_fwd_bwd(const void* out, int out_dtype, const float* x0, const float* noise,
+                                const long long* t, const float* tab_alpha, const float* tab_sigma,
+                                const float* tab_c0, const float* tab_c1, const float* w_tab, float* mse,
+                                float* raw_mse, void* grad_out, const float* gscale_n, float gscale, int mean_type,
+                                long long N, long long chw, cudaStream_t stream) {
+  VAW_CHECK_ARG(out && x0 && noise && tab_alpha && tab_sigma && mse, "vaw_wmse_fwd_bwd: null pointer");
+  VAW_CHECK_ARG(out_dtype == 0 || out_dtype == 1, "vaw_wmse_fwd_bwd: out_dtype must be 0 (f32) or 1 (bf16)");
+  VAW_CHECK_ARG(N >= 0 && chw > 0, "vaw_wmse_fwd_bwd: bad shape N=%lld chw=%lld", N, chw);
+  VAW_CHECK_ARG(mean_type >= MT_PREVIOUS_X && mean_type <= MT_SCORE, "vaw_wmse_fwd_bwd: bad mean_type %d", mean_type);
+  if (N == 0) return VAW_OK;
+  if (out_dtype == 0)
+    wmse_fwd_bwd_kernel<float><<<(unsigned)N, 256, 0, stream>>>(
+        (const float*)out, x0, noise, t, tab_alpha, tab_sigma, tab_c0, tab_c1, w_tab, mse, raw_mse, (float*)grad_out,
+        gscale_n, gscale, mean_type, chw);
+  else
+    wmse_fwd_bwd_kernel<bf16><<<(unsigned)N, 256, 0, stream>>>(
+        (const bf16*)out, x0, noise, t, tab_alpha, tab_sigma, tab_c0, tab_c1, w_tab, mse, raw_mse, (bf16*)grad_out,
+        gscale_n, gscale, mean_type, chw);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+extern "C" int vaw_scale_rows(const void* x, const float* s, void* y, int dtype, long long N, long long chw,
+                              cudaStream_t stream) {
+  VAW_CHECK_ARG(x && s && y, "vaw_scale_rows: null pointer");
+  VAW_CHECK_ARG(dtype == 0 || dtype == 1, "vaw_scale_rows: dtype must be 0 (f32) or 1 (bf16)");
+  if (N * chw == 0) return VAW_OK;
+  long long blocks = (N * chw + 255) / 256;
+  const long long cap = (long long)vaw_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (dtype == 0)
+    scale_rows_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>((const float*)x, s, (float*)y, N, chw);
+  else
+    scale_rows_kernel<bf16><<<(unsigned)blocks, 256, 0, stream>>>((const bf16*)x, s, (bf16*)y, N, chw);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host: per-timestep loss-weight LUT.  compute_mse_loss_weight (reference :1092-1148) depends on t only,
+// so w[t] is evaluated once per diffusion object with the reference's fp32 operation order:
+//   alpha = float(sqrt_ac[t]); sigma = float(sqrt_1mac[t]); snr = (alpha/sigma)^2 (fp32) ...
+// kind codes: see include/vaw_b200.h (VAW_W_*).  Returns VAW_ERR_INVALID for combinations the reference
+// rejects with ValueError (:1144-1145).
+// ------------------------------------------------------------------------------------------------
+extern "C" int vaw_loss_weight_lut(const double* sqrt_ac, const double* sqrt_1mac, int T, int mean_type,
+                                   int weight_kind, double k, double p2_k, double p2_gamma, float* lut) {
+  VAW_CHECK_ARG(sqrt_ac && sqrt_1mac && lut && T > 0, "vaw_loss_weight_lut: bad arguments");
+  enum { W_CONSTANT = 0, W_LAMBDA, W_MIN_SNR, W_MAX_SNR, W_DEBIAS, W_MIN_DEBIAS, W_MAX_DEBIAS, W_P2, W_TRUNC_SNR,
+         W_SNR, W_INV_SNR };
+  for (int i = 0; i < T; ++i) {
+    volatile float alpha = (float)sqrt_ac[i];
+    volatile float sigma = (float)sqrt_1mac[i];
+    volatile float q = alpha / sigma;
+    volatile float snr = q * q;
+    const float kf = (float)k;
+    float w = 0.f;
+    bool ok = false;
+    if (weight_kind == W_CONSTANT) {
+      lut[i] = 1.f;  // early return in the reference: no snr==0 fix-up
+      continue;
+    }
+    if (mean_type == MT_EPSILON) {
+      ok = true;
+      switch (weight_kind) {
+        case W_MIN_SNR: { volatile float m = fminf(snr, kf); w = m / snr; } break;
+        case W_MAX_SNR: { volatile float m = fmaxf(snr, kf); w = m / snr; } break;
+        case W_LAMBDA: w = sigma; break;
+        case W_DEBIAS: w = sigma / alpha; break;
+        case W_P2: { volatile float b = (float)p2_k + snr; volatile float p = powf(b, (float)p2_gamma); w = 1.f / p; } break;
+        case W_MIN_DEBIAS: { volatile float r = sigma / alpha; w = fminf(r, 1.f); } break;
+        case W_MAX_DEBIAS: { volatile float r = sigma / alpha; w = fmaxf(r, 1.f); } break;
+        default: ok = false;
+      }
+    } else if (mean_type == MT_START_X) {
+      ok = true;
+      switch (weight_kind) {
+        case W_TRUNC_SNR: w = fmaxf(snr, 1.f); break;
+        case W_SNR: w = snr; break;
+        case W_INV_SNR: w = 1.f / snr; break;
+        case W_MIN_SNR: w = fminf(snr, kf); break;
+        case W_MAX_SNR: w = fmaxf(snr, kf); break;
+        case W_LAMBDA: w = alpha; break;
+        default: ok = false;
+      }
+    } else if (mean_type == MT_VECTOR) {
+      if (weight_kind == W_LAMBDA) { ok = true; w = 1.f; }
+    } else if (mean_type == MT_VELOCITY) {
+      ok = true;
+      switch (weight_kind) {
+        case W_MIN_SNR: { volatile float m = fminf(snr, kf); volatile float d = snr + 1.f; w = m / d; } break;
+        case W_LAMBDA: w = alpha * sigma; break;
+        default: ok = false;
+      }
+    }
+    if (!ok) {
+      vaw_set_error("Invalid mse_loss_weight_type: kind=%d for mean_type=%d", weight_kind, mean_type);
+      return VAW_ERR_INVALID;
+    }
+    if (snr == 0.f) w = 1.f;  // reference :1147
+    lut[i] = w;
+  }
+  return VAW_OK;
+}
