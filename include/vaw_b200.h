@@ -138,7 +138,10 @@ typedef struct vaw_gemm_args {
   long long ldo, ldg; /* 0 = N */
   int rows_per_sample;
   int accumulate;
-  int tile_n; /* 0 = auto; 128 / 192 / 256 */
+  int tile_n;    /* 0 = auto; 128 / 192 / 256 */
+  int resid_mod; /* > 0: resid is a [resid_mod, N] table indexed by row % resid_mod (pos_embed) */
+  int k_splits;  /* > 1 (VAW_EPI_F32 only): split-K over k_splits work items per tile (deterministic reduce) */
+  float* split_ws; /* fp32 scratch, k_splits * M * ldo elements */
 } vaw_gemm_args;
 
 int vaw_gemm_bf16(const vaw_gemm_args* args, vaw_stream_t stream);

@@ -1,0 +1,446 @@
+// attention.cu — flash-style multi-head self-attention forward and backward for the DiT / U-ViT blocks.
+//
+// Replaces F.scaled_dot_product_attention inside timm Attention (models/dit.py:126 via timm 0.9.2) and
+// models/uvit.py:72-75, forward and autograd backward.  Input is the packed qkv activation [B*T, 3*H*hd] with
+// feature order (3, H, hd) — the order both references produce — so no q/k/v split or head transpose is ever
+// materialised.  head_dim 64 (DiT-S/B/L, U-ViT) and 72 (DiT-XL) are supported; T is arbitrary (258 for U-ViT).
+//
+// Round-1 implementation: warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate), whole K/V (and for the
+// backward Q/dO) of one (batch, head) resident in shared memory.  Attention is 3.6 % of DiT-XL's FLOPs; the
+// tcgen05 version is scheduled after the GEMM path.
+//
+// Softmax statistics are kept in the log2 domain: L2[q] = max_k(s*c) + log2(sum_k 2^(s*c - max)), c = scale*log2(e),
+// so that P = exp2(s*c - L2) in the backward pass.
+#include "vaw_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <int HD>
+struct Geo {
+  static constexpr int HDP = (HD + 15) / 16 * 16;  // K-dim of Q K^T, zero padded (64 / 80)
+  static constexpr int SROW = HDP + 8;             // smem row stride in elements: an odd number of 16-byte chunks
+  static constexpr int NCH = HD / 8;               // 16-byte chunks of real data per row
+  static constexpr int PCH = HDP / 8;              // chunks per row including the zero pad
+  static constexpr int KS = HDP / 16;              // k-steps over the head dimension
+  static constexpr int NT = HD / 8;                // n-tiles over the head dimension (8 or 9)
+};
+
+// Load `rows_total` rows of one head slice into smem (row stride SROW); rows >= rows_valid and the pad chunks are
+// zero filled.  g points at (row 0, first element of the head slice); g_stride is the global row stride.
+template <int HD>
+__device__ __forceinline__ void load_head_rows(bf16* s, const bf16* g, long long g_stride, int rows_valid,
+                                               int rows_total, int tid, int nthreads) {
+  using G = Geo<HD>;
+  const int total = rows_total * G::PCH;
+  for (int i = tid; i < total; i += nthreads) {
+    const int r = i / G::PCH, c = i % G::PCH;
+    bf16* dst = s + r * G::SROW + c * 8;
+    if (r < rows_valid && c < G::NCH) cp_async16(smem_u32(dst), g + (long long)r * g_stride + c * 8);
+    else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// A fragment (16 x 16) of a row-major smem tile at (r0, c0)
+template <int SROW>
+__device__ __forceinline__ void load_a_frag(uint32_t (&a)[4], const bf16* s, int r0, int c0, int lane) {
+  const int r = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int c = c0 + (lane >> 4) * 8;
+  ldsm_x4(a, smem_u32(s + r * SROW + c));
+}
+// B fragments for two n-tiles (n0..n0+15) x k16 from an [n][k] row-major tile: r[0],r[1] -> tile 0; r[2],r[3] -> tile 1
+template <int SROW>
+__device__ __forceinline__ void load_b_nk(uint32_t (&b)[4], const bf16* s, int n0, int k0, int lane) {
+  const int r = n0 + (lane & 7) + (lane >> 4) * 8;
+  const int c = k0 + ((lane >> 3) & 1) * 8;
+  ldsm_x4(b, smem_u32(s + r * SROW + c));
+}
+// B fragments for two n-tiles x k16 from a [k][n] row-major tile (transposed load)
+template <int SROW>
+__device__ __forceinline__ void load_b_kn(uint32_t (&b)[4], const bf16* s, int k0, int n0, int lane) {
+  const int r = k0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int c = n0 + (lane >> 4) * 8;
+  ldsm_x4_t(b, smem_u32(s + r * SROW + c));
+}
+template <int SROW>
+__device__ __forceinline__ void load_b_kn_single(uint32_t (&b)[2], const bf16* s, int k0, int n0, int lane) {
+  const int l = lane & 15;
+  const int r = k0 + (l & 7) + ((l >> 3) & 1) * 8;
+  ldsm_x2_t(b, smem_u32(s + r * SROW + n0));
+}
+
+// acc[NT][4] += A(16 x 16*KSTEPS, register fragments) * B, where B is a [k][n] row-major smem tile (k rows from k0)
+template <int HD, int KSTEPS>
+__device__ __forceinline__ void mma_a_regs_b_kn(float (&acc)[Geo<HD>::NT][4], const uint32_t (&a)[KSTEPS][4],
+                                               const bf16* sB, int k0, int lane) {
+  using G = Geo<HD>;
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+    for (int nt = 0; nt + 1 < G::NT; nt += 2) {
+      uint32_t b[4];
+      load_b_kn<G::SROW>(b, sB, k0 + ks * 16, nt * 8, lane);
+      mma16816(acc[nt], a[ks], b[0], b[1]);
+      mma16816(acc[nt + 1], a[ks], b[2], b[3]);
+    }
+    if (G::NT & 1) {
+      uint32_t b[2];
+      load_b_kn_single<G::SROW>(b, sB, k0 + ks * 16, (G::NT - 1) * 8, lane);
+      mma16816(acc[G::NT - 1], a[ks], b[0], b[1]);
+    }
+  }
+}
+
+// s[NTILES][4] = A(16 x HDP, register fragments) * B^T with B an [n][k] row-major smem tile (n rows from n0)
+template <int HD, int NTILES>
+__device__ __forceinline__ void mma_a_regs_b_nk(float (&s)[NTILES][4], const uint32_t (&a)[Geo<HD>::KS][4],
+                                               const bf16* sB, int n0, int lane) {
+  using G = Geo<HD>;
+#pragma unroll
+  for (int nt = 0; nt < NTILES; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < G::KS; ++ks) {
+#pragma unroll
+    for (int nt = 0; nt < NTILES; nt += 2) {
+      uint32_t b[4];
+      load_b_nk<G::SROW>(b, sB, n0 + nt * 8, ks * 16, lane);
+      mma16816(s[nt], a[ks], b[0], b[1]);
+      mma16816(s[nt + 1], a[ks], b[2], b[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward: grid (ceil(T/64), H, B), 128 threads; each warp owns 16 query rows
+// ---------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __restrict__ lse2, int T, int H,
+                float scale_log2e) {
+  using G = Geo<HD>;
+  constexpr int SROW = G::SROW;
+  const int D = H * HD;
+  const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const int Tpad = (T + 63) / 64 * 64;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
+  bf16* sK = sQ + 64 * SROW;
+  bf16* sV = sK + Tpad * SROW;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  const bf16* gq = qkv + ((long long)b * T) * 3 * D + h * HD;
+  const int q_valid = min(64, T - q0);
+  load_head_rows<HD>(sQ, gq + (long long)q0 * 3 * D, 3LL * D, q_valid, 64, tid, 128);
+  load_head_rows<HD>(sK, gq + D, 3LL * D, T, Tpad, tid, 128);
+  load_head_rows<HD>(sV, gq + 2 * D, 3LL * D, T, Tpad, tid, 128);
+  cp_async_wait_all();
+  __syncthreads();
+
+  uint32_t qa[G::KS][4];
+#pragma unroll
+  for (int ks = 0; ks < G::KS; ++ks) load_a_frag<SROW>(qa[ks], sQ, warp * 16, ks * 16, lane);
+
+  float oacc[G::NT][4];
+#pragma unroll
+  for (int nt = 0; nt < G::NT; ++nt) oacc[nt][0] = oacc[nt][1] = oacc[nt][2] = oacc[nt][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const int g = lane >> 2, t4 = lane & 3;
+
+  for (int kc = 0; kc < Tpad; kc += 64) {
+    float s[8][4];
+    mma_a_regs_b_nk<HD, 8>(s, qa, sK, kc, lane);
+    // scale, mask keys >= T, running max
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = kc + nt * 8 + 2 * t4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool valid = (key + (j & 1)) < T;
+        s[nt][j] = valid ? s[nt][j] * scale_log2e : -INFINITY;
+      }
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float corr0 = exp2f(m0 - mn0), corr1 = exp2f(m1 - mn1);
+    m0 = mn0;
+    m1 = mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f(s[nt][0] - mn0), p1 = exp2f(s[nt][1] - mn0);
+      const float p2 = exp2f(s[nt][2] - mn1), p3 = exp2f(s[nt][3] - mn1);
+      rs0 += p0 + p1;
+      rs1 += p2 + p3;
+      // C layout -> A layout: n-tiles (2ks, 2ks+1) form k-step ks
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
+    }
+    l0 = l0 * corr0 + rs0;
+    l1 = l1 * corr1 + rs1;
+#pragma unroll
+    for (int nt = 0; nt < G::NT; ++nt) {
+      oacc[nt][0] *= corr0;
+      oacc[nt][1] *= corr0;
+      oacc[nt][2] *= corr1;
+      oacc[nt][3] *= corr1;
+    }
+    mma_a_regs_b_kn<HD, 4>(oacc, pa, sV, kc, lane);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+  bf16* go = o + ((long long)b * T) * D + h * HD;
+#pragma unroll
+  for (int nt = 0; nt < G::NT; ++nt) {
+    const int c = nt * 8 + 2 * t4;
+    if (r0 < T) *reinterpret_cast<uint32_t*>(go + (long long)r0 * D + c) = pack_bf16(oacc[nt][0] * inv0, oacc[nt][1] * inv0);
+    if (r1 < T) *reinterpret_cast<uint32_t*>(go + (long long)r1 * D + c) = pack_bf16(oacc[nt][2] * inv1, oacc[nt][3] * inv1);
+  }
+  if (t4 == 0) {
+    float* gl = lse2 + ((long long)b * H + h) * T;
+    if (r0 < T) gl[r0] = m0 + log2f(l0);
+    if (r1 < T) gl[r1] = m1 + log2f(l1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward: grid (H, B), 256 threads; Q, K, V, dO of one (batch, head) live in shared memory.
+//   phase A: each warp owns 16-row K/V tiles, sweeps the queries  -> dK, dV   (no atomics)
+//   phase B: each warp owns 16-row Q tiles,   sweeps the keys     -> dQ
+// ---------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ d_o,
+                const float* __restrict__ lse2, bf16* __restrict__ dqkv, int T, int H, float scale,
+                float scale_log2e) {
+  using G = Geo<HD>;
+  constexpr int SROW = G::SROW;
+  const int D = H * HD;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int Tpad = (T + 31) / 32 * 32;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
+  bf16* sK = sQ + Tpad * SROW;
+  bf16* sV = sK + Tpad * SROW;
+  bf16* sdO = sV + Tpad * SROW;
+  float* sL = reinterpret_cast<float*>(sdO + Tpad * SROW);
+  float* sDl = sL + Tpad;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+
+  const bf16* gq = qkv + ((long long)b * T) * 3 * D + h * HD;
+  const bf16* gdo = d_o + ((long long)b * T) * D + h * HD;
+  const bf16* go = o + ((long long)b * T) * D + h * HD;
+  load_head_rows<HD>(sQ, gq, 3LL * D, T, Tpad, tid, 256);
+  load_head_rows<HD>(sK, gq + D, 3LL * D, T, Tpad, tid, 256);
+  load_head_rows<HD>(sV, gq + 2 * D, 3LL * D, T, Tpad, tid, 256);
+  load_head_rows<HD>(sdO, gdo, (long long)D, T, Tpad, tid, 256);
+  cp_async_wait_all();
+  __syncthreads();
+  // delta[q] = sum_d dO[q,d] * O[q,d]; padded queries get L2 = +inf (P = 0) and delta = 0
+  for (int r = tid; r < Tpad; r += 256) {
+    float dl = 0.f, L = INFINITY;
+    if (r < T) {
+      L = lse2[((long long)b * H + h) * T + r];
+#pragma unroll
+      for (int c = 0; c < G::NCH; ++c) {
+        const uint4 ov = __ldg(reinterpret_cast<const uint4*>(go + (long long)r * D + c * 8));
+        const uint4 dv = *reinterpret_cast<const uint4*>(sdO + r * SROW + c * 8);
+        const uint32_t ou[4] = {ov.x, ov.y, ov.z, ov.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = unpack_bf16(ou[j]), d2 = unpack_bf16(du[j]);
+          dl += a.x * d2.x + a.y * d2.y;
+        }
+      }
+    }
+    sL[r] = L;
+    sDl[r] = dl;
+  }
+  __syncthreads();
+
+  bf16* gdq = dqkv + ((long long)b * T) * 3 * D + h * HD;
+
+  // ---------------- phase A: dK, dV ----------------
+  for (int j0 = warp * 16; j0 < T; j0 += 8 * 16) {
+    uint32_t ka[G::KS][4], va[G::KS][4];
+#pragma unroll
+    for (int ks = 0; ks < G::KS; ++ks) {
+      load_a_frag<SROW>(ka[ks], sK, j0, ks * 16, lane);
+      load_a_frag<SROW>(va[ks], sV, j0, ks * 16, lane);
+    }
+    float dk[G::NT][4], dv[G::NT][4];
+#pragma unroll
+    for (int nt = 0; nt < G::NT; ++nt) {
+      dk[nt][0] = dk[nt][1] = dk[nt][2] = dk[nt][3] = 0.f;
+      dv[nt][0] = dv[nt][1] = dv[nt][2] = dv[nt][3] = 0.f;
+    }
+    for (int i0 = 0; i0 < Tpad; i0 += 32) {
+      float st[4][4], dpt[4][4];
+      mma_a_regs_b_nk<HD, 4>(st, ka, sQ, i0, lane);     // S^T  = K_j Q_i^T   [16 kv x 32 q]
+      mma_a_regs_b_nk<HD, 4>(dpt, va, sdO, i0, lane);   // dP^T = V_j dO_i^T
+      uint32_t pa[2][4], dsa[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int qc = i0 + nt * 8 + 2 * t4;
+        const float2 L = *reinterpret_cast<const float2*>(sL + qc);
+        const float2 Dl = *reinterpret_cast<const float2*>(sDl + qc);
+        const float p0 = exp2f(st[nt][0] * scale_log2e - L.x), p1 = exp2f(st[nt][1] * scale_log2e - L.y);
+        const float p2 = exp2f(st[nt][2] * scale_log2e - L.x), p3 = exp2f(st[nt][3] * scale_log2e - L.y);
+        pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
+        dsa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0 * (dpt[nt][0] - Dl.x), p1 * (dpt[nt][1] - Dl.y));
+        dsa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2 * (dpt[nt][2] - Dl.x), p3 * (dpt[nt][3] - Dl.y));
+      }
+      mma_a_regs_b_kn<HD, 2>(dv, pa, sdO, i0, lane);   // dV_j += P^T dO_i
+      mma_a_regs_b_kn<HD, 2>(dk, dsa, sQ, i0, lane);   // dK_j += dS^T Q_i
+    }
+    const int r0 = j0 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int nt = 0; nt < G::NT; ++nt) {
+      const int c = nt * 8 + 2 * t4;
+      if (r0 < T) {
+        *reinterpret_cast<uint32_t*>(gdq + (long long)r0 * 3 * D + D + c) = pack_bf16(dk[nt][0] * scale, dk[nt][1] * scale);
+        *reinterpret_cast<uint32_t*>(gdq + (long long)r0 * 3 * D + 2 * D + c) = pack_bf16(dv[nt][0], dv[nt][1]);
+      }
+      if (r1 < T) {
+        *reinterpret_cast<uint32_t*>(gdq + (long long)r1 * 3 * D + D + c) = pack_bf16(dk[nt][2] * scale, dk[nt][3] * scale);
+        *reinterpret_cast<uint32_t*>(gdq + (long long)r1 * 3 * D + 2 * D + c) = pack_bf16(dv[nt][2], dv[nt][3]);
+      }
+    }
+  }
+
+  // ---------------- phase B: dQ ----------------
+  for (int i0 = warp * 16; i0 < T; i0 += 8 * 16) {
+    uint32_t qa[G::KS][4], doa[G::KS][4];
+#pragma unroll
+    for (int ks = 0; ks < G::KS; ++ks) {
+      load_a_frag<SROW>(qa[ks], sQ, i0, ks * 16, lane);
+      load_a_frag<SROW>(doa[ks], sdO, i0, ks * 16, lane);
+    }
+    const float L0 = sL[i0 + g], L1 = sL[i0 + g + 8];
+    const float D0 = sDl[i0 + g], D1 = sDl[i0 + g + 8];
+    float dq[G::NT][4];
+#pragma unroll
+    for (int nt = 0; nt < G::NT; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
+    for (int j0 = 0; j0 < Tpad; j0 += 32) {
+      float s[4][4], dp[4][4];
+      mma_a_regs_b_nk<HD, 4>(s, qa, sK, j0, lane);    // S  = Q_i K_j^T   [16 q x 32 kv]
+      mma_a_regs_b_nk<HD, 4>(dp, doa, sV, j0, lane);  // dP = dO_i V_j^T
+      uint32_t dsa[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int kc = j0 + nt * 8 + 2 * t4;
+        const bool v0 = kc < T, v1 = (kc + 1) < T;
+        const float p0 = v0 ? exp2f(s[nt][0] * scale_log2e - L0) : 0.f;
+        const float p1 = v1 ? exp2f(s[nt][1] * scale_log2e - L0) : 0.f;
+        const float p2 = v0 ? exp2f(s[nt][2] * scale_log2e - L1) : 0.f;
+        const float p3 = v1 ? exp2f(s[nt][3] * scale_log2e - L1) : 0.f;
+        dsa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0 * (dp[nt][0] - D0), p1 * (dp[nt][1] - D0));
+        dsa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2 * (dp[nt][2] - D1), p3 * (dp[nt][3] - D1));
+      }
+      mma_a_regs_b_kn<HD, 2>(dq, dsa, sK, j0, lane);  // dQ_i += dS K_j
+    }
+    const int r0 = i0 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int nt = 0; nt < G::NT; ++nt) {
+      const int c = nt * 8 + 2 * t4;
+      if (r0 < T) *reinterpret_cast<uint32_t*>(gdq + (long long)r0 * 3 * D + c) = pack_bf16(dq[nt][0] * scale, dq[nt][1] * scale);
+      if (r1 < T) *reinterpret_cast<uint32_t*>(gdq + (long long)r1 * 3 * D + c) = pack_bf16(dq[nt][2] * scale, dq[nt][3] * scale);
+    }
+  }
+}
+
+template <int HD>
+int launch_fwd(const bf16* qkv, bf16* o, float* lse2, int B, int T, int H, cudaStream_t stream) {
+  using G = Geo<HD>;
+  const int Tpad = (T + 63) / 64 * 64;
+  const int smem = (64 + 2 * Tpad) * G::SROW * 2;
+  VAW_CHECK_ARG(smem <= 227 * 1024, "vaw_attn_fwd: T=%d too long for the smem-resident K/V design", T);
+  static bool configured = false;
+  if (!configured) {
+    VAW_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const float scale = 1.0f / sqrtf((float)HD);
+  dim3 grid((T + 63) / 64, H, B);
+  attn_fwd_kernel<HD><<<grid, 128, smem, stream>>>(qkv, o, lse2, T, H, scale * 1.4426950408889634f);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+template <int HD>
+int launch_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, bf16* dqkv, int B, int T, int H,
+               cudaStream_t stream) {
+  using G = Geo<HD>;
+  const int Tpad = (T + 31) / 32 * 32;
+  const int smem = 4 * Tpad * G::SROW * 2 + 2 * Tpad * 4;
+  VAW_CHECK_ARG(smem <= 227 * 1024, "vaw_attn_bwd: T=%d head_dim=%d does not fit the smem-resident design", T, HD);
+  static bool configured = false;
+  if (!configured) {
+    VAW_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const float scale = 1.0f / sqrtf((float)HD);
+  dim3 grid(H, B);
+  attn_bwd_kernel<HD><<<grid, 256, smem, stream>>>(qkv, o, d_o, lse2, dqkv, T, H, scale, scale * 1.4426950408889634f);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+}  // namespace
+
+extern "C" int vaw_attn_fwd(const void* qkv, void* o, float* lse2, int B, int T, int H, int head_dim,
+                            cudaStream_t stream) {
+  VAW_CHECK_ARG(qkv && o && lse2 && B > 0 && T > 0 && H > 0, "vaw_attn_fwd: bad arguments");
+  if (head_dim == 64) return launch_fwd<64>((const bf16*)qkv, (bf16*)o, lse2, B, T, H, stream);
+  if (head_dim == 72) return launch_fwd<72>((const bf16*)qkv, (bf16*)o, lse2, B, T, H, stream);
+  vaw_set_error("vaw_attn_fwd: head_dim %d not supported (64, 72)", head_dim);
+  return VAW_ERR_UNSUPPORTED;
+}
+
+extern "C" int vaw_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int B,
+                            int T, int H, int head_dim, cudaStream_t stream) {
+  VAW_CHECK_ARG(qkv && o && d_o && lse2 && dqkv && B > 0 && T > 0 && H > 0, "vaw_attn_bwd: bad arguments");
+  if (head_dim == 64) return launch_bwd<64>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse2, (bf16*)dqkv, B, T, H, stream);
+  if (head_dim == 72) return launch_bwd<72>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse2, (bf16*)dqkv, B, T, H, stream);
+  vaw_set_error("vaw_attn_bwd: head_dim %d not supported (64, 72)", head_dim);
+  return VAW_ERR_UNSUPPORTED;
+}

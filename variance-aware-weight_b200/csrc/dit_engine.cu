@@ -1,0 +1,427 @@
+// dit_engine.cu — DiT forward / backward as one C call each: a fixed sequence of the library's kernels on one
+// stream, working on a flat fp32 parameter buffer (+ its bf16 shadow), a flat gradient buffer and one caller-owned
+// workspace.  Mirrors models/dit.py:258-280 (forward), with autograd replaced by the hand-derived backward.
+//
+// Data layout in HBM (per GPU):
+//   P   fp32 [n_params]      master weights, tensors at 64-element aligned offsets (vaw_dit_param_layout)
+//   Pb  bf16 [n_params]      shadow copy read by the GEMMs through TMA
+//   G   fp32 [n_params]      gradients (wgrad epilogues write / accumulate here directly)
+//   ws  workspace            saved activations (bf16 GEMM operands, fp32 residual stream x_0..x_2L) + backward temps
+// The residual stream stays fp32 (as it does under the reference's autocast: x + pos_embed promotes to fp32);
+// every GEMM operand is bf16, every reduction fp32.
+#include "vaw_common.cuh"
+#include "vaw_internal.h"
+
+namespace {
+
+constexpr int kMaxDepth = 64;
+constexpr float kLnEps = 1e-6f;  // dit.py:122,124,147
+
+// ---- parameter layout -------------------------------------------------------------------------------------
+enum ParamId : int {
+  P_XEMB_W = 0, P_XEMB_B, P_T0_W, P_T0_B, P_T2_W, P_T2_B, P_YTAB, P_POS, P_FADA_W, P_FADA_B, P_FLIN_W, P_FLIN_B,
+  P_PR0_W, P_PR0_B, P_PR2_W, P_PR2_B, P_PR4_W, P_PR4_B, P_ADA_W, P_ADA_B, P_BLOCK0
+};
+enum BlockParam : int { B_QKV_W = 0, B_QKV_B, B_PROJ_W, B_PROJ_B, B_FC1_W, B_FC1_B, B_FC2_W, B_FC2_B, B_COUNT };
+
+struct Layout {
+  long long off[P_BLOCK0 + kMaxDepth * B_COUNT];
+  long long numel[P_BLOCK0 + kMaxDepth * B_COUNT];
+  int n;
+  long long total;
+};
+
+long long align64(long long x) { return (x + 63) / 64 * 64; }
+
+void compute_layout(const vaw_dit_cfg& c, Layout& L) {
+  const long long D = c.D, Kp = (long long)c.C_in * c.P * c.P, PPC = (long long)c.P * c.P * c.C_out;
+  long long cur = 0;
+  int n = 0;
+  auto add = [&](long long numel) {
+    L.off[n] = cur;
+    L.numel[n] = numel;
+    cur = align64(cur + numel);
+    ++n;
+  };
+  add(D * Kp); add(D);                                   // x_embedder.proj
+  add(D * c.freq_dim); add(D); add(D * D); add(D);       // t_embedder.mlp.{0,2}
+  add((long long)c.table_rows * D);                      // y_embedder.embedding_table
+  add((long long)c.T * D);                               // pos_embed (no grad)
+  add(2 * D * D); add(2 * D);                            // final_layer.adaLN_modulation.1
+  add(PPC * D); add(PPC);                                // final_layer.linear
+  const long long pd = c.learn_align ? c.proj_dim : 0, zd = c.learn_align ? c.z_dim : 0;
+  add(pd * D); add(pd); add(pd * pd); add(pd); add(zd * pd); add(zd);  // projectors.{0,2,4}
+  add((long long)c.depth * 6 * D * D); add((long long)c.depth * 6 * D);  // all blocks' adaLN_modulation.1, stacked
+  for (int i = 0; i < c.depth; ++i) {
+    add(3 * D * D); add(3 * D);                          // attn.qkv
+    add(D * D); add(D);                                  // attn.proj
+    add((long long)c.hidden * D); add(c.hidden);         // mlp.fc1
+    add(D * (long long)c.hidden); add(D);                // mlp.fc2
+  }
+  L.n = n;
+  L.total = cur;
+}
+
+// ---- workspace ----------------------------------------------------------------------------------------------
+struct BlockWs {
+  float *mean1, *rstd1, *mean2, *rstd2, *lse;
+  bf16 *xn1, *qkv, *attn_o, *y_attn, *xn2, *h_pre, *h_act, *y_mlp;
+};
+struct Ws {
+  bf16 *patches, *freq, *t_h_pre, *t_h, *c_silu;
+  float *t_emb, *c, *mod_all, *mod_final;
+  float* x[2 * kMaxDepth + 1];
+  BlockWs blk[kMaxDepth];
+  float *meanf, *rstdf;
+  bf16 *xnf, *out_tok;
+  bf16 *xa, *z1_pre, *z1, *z2_pre, *z2;
+  // backward temporaries
+  float* dx;
+  bf16 *dy, *dh, *dqkv, *d_o, *dxn, *dtok, *dz, *dxa;
+  float *part, *cpart, *dmod_all, *dmod_final, *dcs, *dc;
+  bf16 *dmod_all_b, *dmod_final_b, *dc_b, *dth;
+  float* split_ws;
+  long long split_elems;
+  long long bytes;
+};
+
+struct Carver {
+  uint8_t* base;
+  long long cur = 0;
+  template <typename T>
+  T* take(long long n) {
+    T* p = base ? reinterpret_cast<T*>(base + cur) : nullptr;
+    cur += (n * (long long)sizeof(T) + 255) / 256 * 256;
+    return p;
+  }
+};
+
+int ln_chunks(const vaw_dit_cfg& c) {
+  int ch = (2 * vaw_num_sms() + c.B - 1) / c.B;
+  if (ch < 1) ch = 1;
+  while (ch > 1 && (c.T + ch - 1) / ch < 8) --ch;
+  return ch;
+}
+int colsum_rows(int M, int N) {
+  const int strips = (N + 63) / 64;
+  int chunks = (4 * vaw_num_sms() + strips - 1) / strips;
+  if (chunks < 1) chunks = 1;
+  int rows = (M + chunks - 1) / chunks;
+  rows = (rows + 7) / 8 * 8;
+  if (rows < 8) rows = 8;
+  return rows;
+}
+
+void carve(const vaw_dit_cfg& c, void* base, Ws& w) {
+  Carver k{reinterpret_cast<uint8_t*>(base)};
+  const long long B = c.B, D = c.D, M = (long long)c.B * c.T, Hd = c.hidden;
+  const long long Kp = (long long)c.C_in * c.P * c.P, PPC = (long long)c.P * c.P * c.C_out;
+  w.patches = k.take<bf16>(M * Kp);
+  w.freq = k.take<bf16>(B * c.freq_dim);
+  w.t_h_pre = k.take<bf16>(B * D);
+  w.t_h = k.take<bf16>(B * D);
+  w.c_silu = k.take<bf16>(B * D);
+  w.t_emb = k.take<float>(B * D);
+  w.c = k.take<float>(B * D);
+  w.mod_all = k.take<float>(B * c.depth * 6 * D);
+  w.mod_final = k.take<float>(B * 2 * D);
+  for (int i = 0; i <= 2 * c.depth; ++i) w.x[i] = k.take<float>(M * D);
+  for (int i = 0; i < c.depth; ++i) {
+    BlockWs& b = w.blk[i];
+    b.mean1 = k.take<float>(M); b.rstd1 = k.take<float>(M); b.mean2 = k.take<float>(M); b.rstd2 = k.take<float>(M);
+    b.lse = k.take<float>(B * c.H * c.T);
+    b.xn1 = k.take<bf16>(M * D); b.qkv = k.take<bf16>(M * 3 * D); b.attn_o = k.take<bf16>(M * D);
+    b.y_attn = k.take<bf16>(M * D); b.xn2 = k.take<bf16>(M * D); b.h_pre = k.take<bf16>(M * Hd);
+    b.h_act = k.take<bf16>(M * Hd); b.y_mlp = k.take<bf16>(M * D);
+  }
+  w.meanf = k.take<float>(M); w.rstdf = k.take<float>(M);
+  w.xnf = k.take<bf16>(M * D);
+  w.out_tok = k.take<bf16>(M * PPC);
+  const long long pd = c.learn_align ? c.proj_dim : 0;
+  w.xa = k.take<bf16>(c.learn_align ? M * D : 0);
+  w.z1_pre = k.take<bf16>(M * pd); w.z1 = k.take<bf16>(M * pd);
+  w.z2_pre = k.take<bf16>(M * pd); w.z2 = k.take<bf16>(M * pd);
+  // backward temporaries
+  w.dx = k.take<float>(M * D);
+  w.dy = k.take<bf16>(M * D);
+  w.dh = k.take<bf16>(M * Hd);
+  w.dqkv = k.take<bf16>(M * 3 * D);
+  w.d_o = k.take<bf16>(M * D);
+  w.dxn = k.take<bf16>(M * D);
+  w.dtok = k.take<bf16>(M * PPC);
+  w.dz = k.take<bf16>(2 * M * pd);
+  w.dxa = k.take<bf16>(c.learn_align ? M * D : 0);
+  w.part = k.take<float>(B * ln_chunks(c) * 2 * D);
+  long long maxN = 3 * D > Hd ? 3 * D : Hd;
+  if (pd > maxN) maxN = pd;
+  const long long cchunks = (M + colsum_rows((int)M, 64) - 1) / colsum_rows((int)M, 64) + 1;
+  w.cpart = k.take<float>(cchunks * maxN + 1024);
+  w.dmod_all = k.take<float>(B * c.depth * 6 * D);
+  w.dmod_final = k.take<float>(B * 2 * D);
+  w.dcs = k.take<float>(B * D);
+  w.dc = k.take<float>(B * D);
+  w.dmod_all_b = k.take<bf16>(B * c.depth * 6 * D);
+  w.dmod_final_b = k.take<bf16>(B * 2 * D);
+  w.dc_b = k.take<bf16>(B * D);
+  w.dth = k.take<bf16>(B * D);
+  w.split_elems = 4LL << 20;
+  w.split_ws = k.take<float>(w.split_elems);
+  w.bytes = k.cur;
+}
+
+int check_cfg(const vaw_dit_cfg* c) {
+  VAW_CHECK_ARG(c, "dit: null config");
+  VAW_CHECK_ARG(c->B > 0 && c->T > 0 && c->D > 0 && c->H > 0 && c->depth > 0 && c->depth <= kMaxDepth,
+                "dit: bad geometry B=%d T=%d D=%d H=%d depth=%d", c->B, c->T, c->D, c->H, c->depth);
+  VAW_CHECK_ARG(c->D % c->H == 0 && (c->D / c->H == 64 || c->D / c->H == 72), "dit: head_dim %d unsupported (64, 72)",
+                c->D / c->H);
+  VAW_CHECK_ARG(c->D % 8 == 0 && c->hidden % 8 == 0, "dit: D and hidden must be multiples of 8");
+  VAW_CHECK_ARG((c->img_h / c->P) * (c->img_w / c->P) == c->T, "dit: T does not match the patch grid");
+  VAW_CHECK_ARG((c->C_in * c->P * c->P) % 8 == 0 && (c->C_out * c->P * c->P) % 8 == 0,
+                "dit: patch feature counts must be multiples of 8");
+  VAW_CHECK_ARG(c->freq_dim % 8 == 0, "dit: freq_dim must be a multiple of 8");
+  VAW_CHECK_ARG(!c->learn_align || (c->encoder_depth > 0 && c->encoder_depth <= c->depth && c->proj_dim % 8 == 0 &&
+                                    c->z_dim % 8 == 0),
+                "dit: bad REPA projector config");
+  return VAW_OK;
+}
+
+struct G {  // small GEMM call builder
+  vaw_gemm_args a;
+  G(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M, int N, int K, int epi) {
+    memset(&a, 0, sizeof(a));
+    a.A = A; a.lda = lda; a.a_mn = a_mn; a.B = B; a.ldb = ldb; a.b_mn = b_mn;
+    a.M = M; a.N = N; a.K = K; a.epilogue = epi;
+  }
+  G& out(void* o, void* o2 = nullptr) { a.out = o; a.out2 = o2; return *this; }
+  G& bias(const float* b) { a.bias = b; return *this; }
+  G& resid(const float* r, int mod = 0) { a.resid = r; a.resid_mod = mod; return *this; }
+  G& gate(const float* g, long long ldg, int rps) { a.gate = g; a.ldg = ldg; a.rows_per_sample = rps; return *this; }
+  G& aux(const void* x) { a.aux = x; return *this; }
+  G& acc(int f) { a.accumulate = f; return *this; }
+  // skinny GEMMs (few output tiles, long K): split the K loop so that every SM gets work
+  G& autosplit(float* ws, long long ws_elems) {
+    const int bn = a.N % 192 == 0 ? 192 : (a.N % 256 == 0 ? 256 : (a.N % 128 == 0 ? 128 : (a.N > 128 ? 192 : 128)));
+    const long long tiles = (long long)((a.M + 127) / 128) * ((a.N + bn - 1) / bn);
+    const int num_kb = (a.K + 63) / 64;
+    long long sp = vaw_num_sms() / tiles;
+    if (sp > num_kb / 4) sp = num_kb / 4;  // keep at least 4 k-blocks per split
+    const long long per = (long long)a.M * (a.ldo ? a.ldo : a.N);
+    if (sp * per > ws_elems) sp = ws_elems / per;
+    if (sp > 1) { a.k_splits = (int)sp; a.split_ws = ws; }
+    return *this;
+  }
+  int run(cudaStream_t s) { return vaw_gemm_bf16(&a, s); }
+};
+
+#define TRY(expr)            \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc != VAW_OK) return _rc; \
+  } while (0)
+
+}  // namespace
+
+extern "C" int vaw_dit_param_layout(const vaw_dit_cfg* cfg, long long* offsets, long long* numels, int cap, int* n_out,
+                                    long long* total) {
+  TRY(check_cfg(cfg));
+  Layout L;
+  compute_layout(*cfg, L);
+  VAW_CHECK_ARG(cap >= L.n, "vaw_dit_param_layout: need room for %d entries", L.n);
+  for (int i = 0; i < L.n; ++i) {
+    if (offsets) offsets[i] = L.off[i];
+    if (numels) numels[i] = L.numel[i];
+  }
+  if (n_out) *n_out = L.n;
+  if (total) *total = L.total;
+  return VAW_OK;
+}
+
+extern "C" int vaw_dit_workspace_bytes(const vaw_dit_cfg* cfg, long long* bytes) {
+  TRY(check_cfg(cfg));
+  VAW_CHECK_ARG(bytes, "vaw_dit_workspace_bytes: null output");
+  Ws w;
+  carve(*cfg, nullptr, w);
+  *bytes = w.bytes;
+  return VAW_OK;
+}
+
+// x_t [B,C_in,H,W] fp32, t [B] fp32 (already scaled, gaussian_diffusion.py:417-420), y [B] int64 (may be null when
+// table_rows == 0) -> out [B,C_out,H,W] bf16 and, with learn_align, zs [B*T, z_dim] bf16.
+extern "C" int vaw_dit_forward(const vaw_dit_cfg* cfg, const float* P, const void* Pb_, void* ws_, const float* x_t,
+                               const float* t, const long long* y, void* out, void* zs, cudaStream_t s) {
+  TRY(check_cfg(cfg));
+  VAW_CHECK_ARG(P && Pb_ && ws_ && x_t && t && out, "vaw_dit_forward: null pointer");
+  const vaw_dit_cfg& c = *cfg;
+  VAW_CHECK_ARG(c.table_rows == 0 || y, "vaw_dit_forward: labels required");
+  VAW_CHECK_ARG(!c.learn_align || zs, "vaw_dit_forward: zs output required with learn_align");
+  Layout L;
+  compute_layout(c, L);
+  Ws w;
+  carve(c, ws_, w);
+  const bf16* Pb = reinterpret_cast<const bf16*>(Pb_);
+  const int B = c.B, T = c.T, D = c.D, M = B * T, Hd = c.hidden, hd = D / c.H;
+  const int Kp = c.C_in * c.P * c.P, PPC = c.P * c.P * c.C_out;
+  const long long ldm = (long long)c.depth * 6 * D;
+
+  // patch embedding + pos_embed -> x[0]
+  TRY(vaw_patchify_in(x_t, w.patches, B, c.C_in, c.img_h, c.img_w, c.P, s));
+  TRY(G(w.patches, Kp, 0, Pb + L.off[P_XEMB_W], Kp, 0, M, D, Kp, VAW_EPI_RES)
+          .out(nullptr, w.x[0]).bias(P + L.off[P_XEMB_B]).resid(P + L.off[P_POS], T).run(s));
+  // conditioning: c = t_mlp(freq(t)) + table[y]
+  TRY(vaw_timestep_embedding(t, w.freq, nullptr, B, c.freq_dim, s));
+  TRY(G(w.freq, c.freq_dim, 0, Pb + L.off[P_T0_W], c.freq_dim, 0, B, D, c.freq_dim, VAW_EPI_SILU)
+          .out(w.t_h_pre, w.t_h).bias(P + L.off[P_T0_B]).run(s));
+  TRY(G(w.t_h, D, 0, Pb + L.off[P_T2_W], D, 0, B, D, D, VAW_EPI_F32).out(w.t_emb).bias(P + L.off[P_T2_B]).run(s));
+  TRY(vaw_cond_combine(w.t_emb, c.table_rows ? P + L.off[P_YTAB] : nullptr, y, w.c, w.c_silu, B, D, s));
+  // adaLN modulation of every block (one GEMM) and of the final layer
+  TRY(G(w.c_silu, D, 0, Pb + L.off[P_ADA_W], D, 0, B, c.depth * 6 * D, D, VAW_EPI_F32)
+          .out(w.mod_all).bias(P + L.off[P_ADA_B]).run(s));
+  TRY(G(w.c_silu, D, 0, Pb + L.off[P_FADA_W], D, 0, B, 2 * D, D, VAW_EPI_F32)
+          .out(w.mod_final).bias(P + L.off[P_FADA_B]).run(s));
+
+  for (int i = 0; i < c.depth; ++i) {
+    BlockWs& b = w.blk[i];
+    const int pb = P_BLOCK0 + i * B_COUNT;
+    const float* mod = w.mod_all + (long long)i * 6 * D;  // [shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp]
+    float* x_in = w.x[2 * i];
+    float* x_mid = w.x[2 * i + 1];
+    float* x_out = w.x[2 * i + 2];
+    TRY(vaw_ln_fwd(x_in, mod, mod + D, ldm, T, nullptr, nullptr, b.xn1, b.mean1, b.rstd1, M, D, kLnEps, s));
+    TRY(G(b.xn1, D, 0, Pb + L.off[pb + B_QKV_W], D, 0, M, 3 * D, D, VAW_EPI_BF16)
+            .out(b.qkv).bias(P + L.off[pb + B_QKV_B]).run(s));
+    TRY(vaw_attn_fwd(b.qkv, b.attn_o, b.lse, B, T, c.H, hd, s));
+    TRY(G(b.attn_o, D, 0, Pb + L.off[pb + B_PROJ_W], D, 0, M, D, D, VAW_EPI_GATE_RES)
+            .out(b.y_attn, x_mid).bias(P + L.off[pb + B_PROJ_B]).resid(x_in).gate(mod + 2 * D, ldm, T).run(s));
+    TRY(vaw_ln_fwd(x_mid, mod + 3 * D, mod + 4 * D, ldm, T, nullptr, nullptr, b.xn2, b.mean2, b.rstd2, M, D, kLnEps, s));
+    TRY(G(b.xn2, D, 0, Pb + L.off[pb + B_FC1_W], D, 0, M, Hd, D, VAW_EPI_GELU_TANH)
+            .out(b.h_pre, b.h_act).bias(P + L.off[pb + B_FC1_B]).run(s));
+    TRY(G(b.h_act, Hd, 0, Pb + L.off[pb + B_FC2_W], Hd, 0, M, D, Hd, VAW_EPI_GATE_RES)
+            .out(b.y_mlp, x_out).bias(P + L.off[pb + B_FC2_B]).resid(x_mid).gate(mod + 5 * D, ldm, T).run(s));
+    if (c.learn_align && i + 1 == c.encoder_depth) {
+      const int pd = c.proj_dim, zd = c.z_dim;
+      TRY(vaw_cast_f32_bf16(x_out, w.xa, (long long)M * D, s));
+      TRY(G(w.xa, D, 0, Pb + L.off[P_PR0_W], D, 0, M, pd, D, VAW_EPI_SILU)
+              .out(w.z1_pre, w.z1).bias(P + L.off[P_PR0_B]).run(s));
+      TRY(G(w.z1, pd, 0, Pb + L.off[P_PR2_W], pd, 0, M, pd, pd, VAW_EPI_SILU)
+              .out(w.z2_pre, w.z2).bias(P + L.off[P_PR2_B]).run(s));
+      TRY(G(w.z2, pd, 0, Pb + L.off[P_PR4_W], pd, 0, M, zd, pd, VAW_EPI_BF16).out(zs).bias(P + L.off[P_PR4_B]).run(s));
+    }
+  }
+  // final layer: LN -> modulate -> linear -> unpatchify
+  float* x_last = w.x[2 * c.depth];
+  TRY(vaw_ln_fwd(x_last, w.mod_final, w.mod_final + D, 2LL * D, T, nullptr, nullptr, w.xnf, w.meanf, w.rstdf, M, D,
+                 kLnEps, s));
+  TRY(G(w.xnf, D, 0, Pb + L.off[P_FLIN_W], D, 0, M, PPC, D, VAW_EPI_BF16).out(w.out_tok).bias(P + L.off[P_FLIN_B]).run(s));
+  TRY(vaw_unpatchify(w.out_tok, out, 1, B, c.C_out, c.img_h, c.img_w, c.P, 1, s));
+  return VAW_OK;
+}
+
+// dout [B,C_out,H,W] bf16 (gradient of the model output), dzs [B*T, z_dim] bf16 or null.
+// accumulate = 0: G is overwritten for every trainable tensor; 1: gradients are added (grad accumulation).
+// events: optional array of depth + 1 cudaEvent_t; events[i] is recorded once block i's gradients are complete
+// (i = depth-1 .. 0), events[depth] after the remaining (embedder / adaLN / final-layer) gradients.
+extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const void* Pb_, float* Gd, void* ws_,
+                                const void* dout, const void* dzs, const long long* y, int accumulate, void** events,
+                                cudaStream_t s) {
+  TRY(check_cfg(cfg));
+  VAW_CHECK_ARG(P && Pb_ && Gd && ws_ && dout, "vaw_dit_backward: null pointer");
+  const vaw_dit_cfg& c = *cfg;
+  Layout L;
+  compute_layout(c, L);
+  Ws w;
+  carve(c, ws_, w);
+  const bf16* Pb = reinterpret_cast<const bf16*>(Pb_);
+  const int B = c.B, T = c.T, D = c.D, M = B * T, Hd = c.hidden, hd = D / c.H;
+  const int Kp = c.C_in * c.P * c.P, PPC = c.P * c.P * c.C_out;
+  const long long ldm = (long long)c.depth * 6 * D;
+  const int ch = ln_chunks(c);
+  const int acc = accumulate ? 1 : 0;
+
+  // ---- final layer ----
+  TRY(vaw_unpatchify(w.dtok, const_cast<void*>(dout), 1, B, c.C_out, c.img_h, c.img_w, c.P, 0, s));
+  TRY(vaw_colsum_bf16(w.dtok, PPC, M, PPC, w.cpart, colsum_rows(M, PPC), Gd + L.off[P_FLIN_B], acc, s));
+  TRY(G(w.dtok, PPC, 1, w.xnf, D, 1, PPC, D, M, VAW_EPI_F32).out(Gd + L.off[P_FLIN_W]).acc(acc)
+          .autosplit(w.split_ws, w.split_elems).run(s));
+  TRY(G(w.dtok, PPC, 0, Pb + L.off[P_FLIN_W], D, 1, M, D, PPC, VAW_EPI_BF16).out(w.dxn).run(s));
+  TRY(vaw_ln_bwd(w.dxn, w.x[2 * c.depth], w.meanf, w.rstdf, w.mod_final + D, 2LL * D, nullptr, w.dx, 0, w.part, T, B,
+                 ch, M, D, s));
+  TRY(vaw_finish_group(w.part, 0, B, ch, D, w.dmod_final, 2LL * D, 0, s));      // d shift
+  TRY(vaw_finish_group(w.part, 1, B, ch, D, w.dmod_final + D, 2LL * D, 0, s));  // d scale
+
+  for (int i = c.depth - 1; i >= 0; --i) {
+    BlockWs& b = w.blk[i];
+    const int pb = P_BLOCK0 + i * B_COUNT;
+    const float* mod = w.mod_all + (long long)i * 6 * D;
+    float* dmod = w.dmod_all + (long long)i * 6 * D;
+    if (c.learn_align && i + 1 == c.encoder_depth && dzs) {
+      // REPA projector backward: dzs -> grads of projectors.{4,2,0} and an extra gradient on x[2i+2]
+      const int pd = c.proj_dim, zd = c.z_dim;
+      bf16* dz2 = w.dz;
+      bf16* dz1 = w.dz + (long long)M * pd;
+      TRY(vaw_colsum_bf16(dzs, zd, M, zd, w.cpart, colsum_rows(M, zd), Gd + L.off[P_PR4_B], acc, s));
+      TRY(G(dzs, zd, 1, w.z2, pd, 1, zd, pd, M, VAW_EPI_F32).out(Gd + L.off[P_PR4_W]).acc(acc).run(s));
+      TRY(G(dzs, zd, 0, Pb + L.off[P_PR4_W], pd, 1, M, pd, zd, VAW_EPI_DSILU).out(dz2).aux(w.z2_pre).run(s));
+      TRY(vaw_colsum_bf16(dz2, pd, M, pd, w.cpart, colsum_rows(M, pd), Gd + L.off[P_PR2_B], acc, s));
+      TRY(G(dz2, pd, 1, w.z1, pd, 1, pd, pd, M, VAW_EPI_F32).out(Gd + L.off[P_PR2_W]).acc(acc).run(s));
+      TRY(G(dz2, pd, 0, Pb + L.off[P_PR2_W], pd, 1, M, pd, pd, VAW_EPI_DSILU).out(dz1).aux(w.z1_pre).run(s));
+      TRY(vaw_colsum_bf16(dz1, pd, M, pd, w.cpart, colsum_rows(M, pd), Gd + L.off[P_PR0_B], acc, s));
+      TRY(G(dz1, pd, 1, w.xa, D, 1, pd, D, M, VAW_EPI_F32).out(Gd + L.off[P_PR0_W]).acc(acc).run(s));
+      TRY(G(dz1, pd, 0, Pb + L.off[P_PR0_W], D, 1, M, D, pd, VAW_EPI_BF16).out(w.dxa).run(s));
+      TRY(vaw_add_bf16_into_f32(w.dxa, w.dx, (long long)M * D, s));
+    }
+    // ---- MLP branch: x_out = x_mid + gate_mlp * fc2(gelu(fc1(modulate(LN(x_mid))))) ----
+    TRY(vaw_gate_bwd(w.dx, b.y_mlp, mod + 5 * D, ldm, w.dy, w.part, T, B, ch, M, D, s));
+    TRY(vaw_finish_group(w.part, 1, B, ch, D, dmod + 5 * D, ldm, 0, s));                          // d gate_mlp
+    TRY(vaw_finish_all(w.part, 0, B, ch, D, mod + 5 * D, ldm, Gd + L.off[pb + B_FC2_B], acc, s));  // d fc2.bias
+    TRY(G(w.dy, D, 1, b.h_act, Hd, 1, D, Hd, M, VAW_EPI_F32).out(Gd + L.off[pb + B_FC2_W]).acc(acc).run(s));
+    TRY(G(w.dy, D, 0, Pb + L.off[pb + B_FC2_W], Hd, 1, M, Hd, D, VAW_EPI_DGELU_TANH).out(w.dh).aux(b.h_pre).run(s));
+    TRY(vaw_colsum_bf16(w.dh, Hd, M, Hd, w.cpart, colsum_rows(M, Hd), Gd + L.off[pb + B_FC1_B], acc, s));
+    TRY(G(w.dh, Hd, 1, b.xn2, D, 1, Hd, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_FC1_W]).acc(acc).run(s));
+    TRY(G(w.dh, Hd, 0, Pb + L.off[pb + B_FC1_W], D, 1, M, D, Hd, VAW_EPI_BF16).out(w.dxn).run(s));
+    TRY(vaw_ln_bwd(w.dxn, w.x[2 * i + 1], b.mean2, b.rstd2, mod + 4 * D, ldm, nullptr, w.dx, 1, w.part, T, B, ch, M, D, s));
+    TRY(vaw_finish_group(w.part, 0, B, ch, D, dmod + 3 * D, ldm, 0, s));  // d shift_mlp
+    TRY(vaw_finish_group(w.part, 1, B, ch, D, dmod + 4 * D, ldm, 0, s));  // d scale_mlp
+    // ---- attention branch: x_mid = x_in + gate_msa * proj(attn(qkv(modulate(LN(x_in))))) ----
+    TRY(vaw_gate_bwd(w.dx, b.y_attn, mod + 2 * D, ldm, w.dy, w.part, T, B, ch, M, D, s));
+    TRY(vaw_finish_group(w.part, 1, B, ch, D, dmod + 2 * D, ldm, 0, s));                            // d gate_msa
+    TRY(vaw_finish_all(w.part, 0, B, ch, D, mod + 2 * D, ldm, Gd + L.off[pb + B_PROJ_B], acc, s));  // d proj.bias
+    TRY(G(w.dy, D, 1, b.attn_o, D, 1, D, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_PROJ_W]).acc(acc).run(s));
+    TRY(G(w.dy, D, 0, Pb + L.off[pb + B_PROJ_W], D, 1, M, D, D, VAW_EPI_BF16).out(w.d_o).run(s));
+    TRY(vaw_attn_bwd(b.qkv, b.attn_o, w.d_o, b.lse, w.dqkv, B, T, c.H, hd, s));
+    TRY(vaw_colsum_bf16(w.dqkv, 3LL * D, M, 3 * D, w.cpart, colsum_rows(M, 3 * D), Gd + L.off[pb + B_QKV_B], acc, s));
+    TRY(G(w.dqkv, 3LL * D, 1, b.xn1, D, 1, 3 * D, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_QKV_W]).acc(acc).run(s));
+    TRY(G(w.dqkv, 3LL * D, 0, Pb + L.off[pb + B_QKV_W], D, 1, M, D, 3 * D, VAW_EPI_BF16).out(w.dxn).run(s));
+    TRY(vaw_ln_bwd(w.dxn, w.x[2 * i], b.mean1, b.rstd1, mod + D, ldm, nullptr, w.dx, 1, w.part, T, B, ch, M, D, s));
+    TRY(vaw_finish_group(w.part, 0, B, ch, D, dmod, ldm, 0, s));      // d shift_msa
+    TRY(vaw_finish_group(w.part, 1, B, ch, D, dmod + D, ldm, 0, s));  // d scale_msa
+    if (events && events[i]) VAW_CUDA_TRY(cudaEventRecord(reinterpret_cast<cudaEvent_t>(events[i]), s));
+  }
+
+  // ---- adaLN linears: mod = silu(c) W^T + b ----
+  const int NA = c.depth * 6 * D;
+  TRY(vaw_cast_f32_bf16(w.dmod_all, w.dmod_all_b, (long long)B * NA, s));
+  TRY(vaw_cast_f32_bf16(w.dmod_final, w.dmod_final_b, (long long)B * 2 * D, s));
+  TRY(vaw_colsum_f32_small(w.dmod_all, NA, B, NA, Gd + L.off[P_ADA_B], acc, s));
+  TRY(vaw_colsum_f32_small(w.dmod_final, 2LL * D, B, 2 * D, Gd + L.off[P_FADA_B], acc, s));
+  TRY(G(w.dmod_all_b, NA, 1, w.c_silu, D, 1, NA, D, B, VAW_EPI_F32).out(Gd + L.off[P_ADA_W]).acc(acc).run(s));
+  TRY(G(w.dmod_final_b, 2LL * D, 1, w.c_silu, D, 1, 2 * D, D, B, VAW_EPI_F32).out(Gd + L.off[P_FADA_W]).acc(acc).run(s));
+  TRY(G(w.dmod_all_b, NA, 0, Pb + L.off[P_ADA_W], D, 1, B, D, NA, VAW_EPI_F32).out(w.dcs)
+          .autosplit(w.split_ws, w.split_elems).run(s));
+  TRY(G(w.dmod_final_b, 2LL * D, 0, Pb + L.off[P_FADA_W], D, 1, B, D, 2 * D, VAW_EPI_F32).out(w.dcs).acc(1).run(s));
+  // ---- conditioning: c = t_emb + table[y] ----
+  TRY(vaw_cond_bwd(w.dcs, w.c, w.dc, w.dc_b, B * D, s));
+  if (c.table_rows) TRY(vaw_embedding_grad(w.dc, y, Gd + L.off[P_YTAB], c.table_rows, B, D, acc, s));
+  TRY(vaw_colsum_f32_small(w.dc, D, B, D, Gd + L.off[P_T2_B], acc, s));
+  TRY(G(w.dc_b, D, 1, w.t_h, D, 1, D, D, B, VAW_EPI_F32).out(Gd + L.off[P_T2_W]).acc(acc).run(s));
+  TRY(G(w.dc_b, D, 0, Pb + L.off[P_T2_W], D, 1, B, D, D, VAW_EPI_DSILU).out(w.dth).aux(w.t_h_pre).run(s));
+  TRY(vaw_colsum_bf16(w.dth, D, B, D, w.cpart, 8, Gd + L.off[P_T0_B], acc, s));
+  TRY(G(w.dth, D, 1, w.freq, c.freq_dim, 1, D, c.freq_dim, B, VAW_EPI_F32).out(Gd + L.off[P_T0_W]).acc(acc).run(s));
+  // ---- patch embedding: x[0] = patches W^T + b + pos ----
+  TRY(vaw_gate_bwd(w.dx, nullptr, nullptr, 0, w.dy, w.part, T, B, ch, M, D, s));
+  TRY(vaw_finish_all(w.part, 0, B, ch, D, nullptr, 0, Gd + L.off[P_XEMB_B], acc, s));
+  TRY(G(w.dy, D, 1, w.patches, Kp, 1, D, Kp, M, VAW_EPI_F32).out(Gd + L.off[P_XEMB_W]).acc(acc)
+          .autosplit(w.split_ws, w.split_elems).run(s));
+  if (events && events[c.depth]) VAW_CUDA_TRY(cudaEventRecord(reinterpret_cast<cudaEvent_t>(events[c.depth]), s));
+  return VAW_OK;
+}

@@ -15,6 +15,7 @@
 //   warps 2-5   epilogue       (tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global)
 // Two accumulator stages in TMEM (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "vaw_common.cuh"
+#include "vaw_internal.h"
 
 namespace {
 
@@ -48,9 +49,13 @@ struct EpiParams {
   long long ldo;    // leading dimension (elements) of out/out2/resid/aux
   long long ldg;    // leading dimension of gate
   int rows_per_sample;
+  int resid_mod;    // > 0: the residual is a [resid_mod, N] table indexed by row % resid_mod (pos_embed)
   int accumulate;
   int M, N, K;
   int a_mn, b_mn;   // operand majorness: 0 = K-major, 1 = MN-major
+  int k_splits;     // > 1: split-K; work item = (tile, split); raw fp32 partials go to out + split * split_stride
+  int kb_per_split;
+  long long split_stride;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -159,9 +164,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int mn_major) {
 // fused epilogue on one 32-column chunk of one row (also reused by the tail-split fix-up kernel)
 // ---------------------------------------------------------------------------------------------------
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int row, int col0, const uint32_t (&acc)[32]) {
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int row, int col0, const uint32_t (&acc)[32],
+                                               long long slab = 0) {
   if (row >= p.M) return;
   const long long ro = (long long)row * p.ldo;
+  const long long rr = (long long)(p.resid_mod > 0 ? row % p.resid_mod : row) * p.ldo;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns
     const int c = col0 + g * 8;
@@ -176,7 +183,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int row, int 
       v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
     }
     if constexpr (EPI == EPI_F32) {
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ro + c);
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + slab + ro + c);
       if (p.accumulate) {
         const float4 o0 = o[0], o1 = o[1];
         v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
@@ -185,7 +192,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int row, int 
       o[0] = make_float4(v[0], v[1], v[2], v[3]);
       o[1] = make_float4(v[4], v[5], v[6], v[7]);
     } else if constexpr (EPI == EPI_RES) {
-      const float4* r = reinterpret_cast<const float4*>(p.resid + ro + c);
+      const float4* r = reinterpret_cast<const float4*>(p.resid + rr + c);
       const float4 r0 = r[0], r1 = r[1];
       float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out2) + ro + c);
       // the linear output is a bf16 tensor in the reference's autocast path: round before the residual add
@@ -237,7 +244,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int row, int 
         const float* gp = p.gate + (long long)(row / p.rows_per_sample) * p.ldg + c;
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp) + 1);
-        const float4* r = reinterpret_cast<const float4*>(p.resid + ro + c);
+        const float4* r = reinterpret_cast<const float4*>(p.resid + rr + c);
         const float4 r0 = r[0], r1 = r[1];
         float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out2) + ro + c);
         o[0] = make_float4(fmaf(g0.x, y[0], r0.x), fmaf(g0.y, y[1], r0.y), fmaf(g0.z, y[2], r0.z), fmaf(g0.w, y[3], r0.w));
@@ -282,7 +289,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_kb_total = (p.K + BK - 1) / BK;
+  const int num_work = num_tiles * p.k_splits;  // work item w: tile = w % num_tiles, split = w / num_tiles
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -308,10 +316,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int tile = work % num_tiles, split = work / num_tiles;
         const int m0 = (tile / n_tiles) * BM;
         const int n0 = (tile % n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
           mbar_expect_tx(&full[stage], C::kStageBytes);
           uint8_t* a_dst = sA + stage * kABytes;
@@ -346,7 +357,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int split = work / num_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int num_kb = min(num_kb_total, kb0 + p.kb_per_split) - kb0;
         mbar_wait(&tempty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -374,9 +388,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const int tile = work % num_tiles, split = work / num_tiles;
       const int m0 = (tile / n_tiles) * BM;
       const int n0 = (tile % n_tiles) * BN;
+      const long long slab = (long long)split * p.split_stride;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
@@ -386,7 +402,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint32_t v[32];
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, row, n0 + c * 32, v);
+        epilogue_chunk<EPI>(p, row, n0 + c * 32, v, slab);
       }
       tc_fence_before();
       __syncwarp();
@@ -446,6 +462,32 @@ int make_tmap(CUtensorMap* map, const void* base, long long rows, long long cols
   return VAW_OK;
 }
 
+// split-K finish: out[r, c] = (accumulate ? out : 0) + bias[c] + sum_s ws[s][r, c]   (fixed order -> deterministic)
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long stride, float* __restrict__ out,
+                     const float* __restrict__ bias, int M, int N, long long ldo, int accumulate) {
+  const long long n4 = (long long)M * (N >> 2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (N >> 2)), c = (int)(i % (N >> 2)) * 4;
+    const long long o = (long long)r * ldo + c;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + (long long)s * stride + o);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    if (bias) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + c);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(out + o);
+    if (accumulate) {
+      const float4 d = *dst;
+      a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
+    }
+    *dst = a;
+  }
+}
+
 template <int BN, int EPI>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& p, cudaStream_t stream) {
   using C = Cfg<BN>;
@@ -456,7 +498,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams&
     configured = true;
   }
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
-  int grid = m_tiles * n_tiles;
+  int grid = m_tiles * n_tiles * (p.k_splits > 0 ? p.k_splits : 1);
   const int sms = vaw_num_sms();
   if (grid > sms) grid = sms;
   kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
@@ -483,26 +525,6 @@ int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 }
 
 }  // namespace
-
-// Public argument block of vaw_gemm_bf16 (declared in include/vaw_b200.h as vaw_gemm_args)
-struct vaw_gemm_args {
-  const void* A;       // bf16; K-major: [M,K] row-major (lda) ; MN-major: [K,M] row-major (lda)
-  const void* B;       // bf16; K-major: [N,K] row-major (ldb) ; MN-major: [K,N] row-major (ldb)
-  long long lda, ldb;
-  int a_mn, b_mn;
-  int M, N, K;
-  int epilogue;
-  void* out;           // primary output  [M,N] (ldo)
-  void* out2;          // secondary output [M,N] (ldo)
-  const float* bias;   // [N] or null
-  const float* resid;  // [M,N] fp32 (ldo)
-  const float* gate;   // [M / rows_per_sample, >=N] fp32 (ldg)
-  const void* aux;     // bf16 [M,N] (ldo): saved pre-activation for the d-activation epilogues
-  long long ldo, ldg;
-  int rows_per_sample;
-  int accumulate;      // EPI_F32: out += result
-  int tile_n;          // 0 = auto, else 128 / 192 / 256
-};
 
 extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
   VAW_CHECK_ARG(a && a->A && a->B, "vaw_gemm_bf16: null operand");
@@ -553,11 +575,42 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
   p.ldg = a->ldg ? a->ldg : a->N;
   p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : 1;
   p.accumulate = a->accumulate;
+  p.resid_mod = a->resid_mod;
   p.M = a->M;
   p.N = a->N;
   p.K = a->K;
   p.a_mn = a->a_mn ? 1 : 0;
   p.b_mn = a->b_mn ? 1 : 0;
+  // split-K (EPI_F32 only): partial slabs in split_ws, then a fixed-order reduction that applies bias / accumulate
+  const int num_kb = (a->K + BK - 1) / BK;
+  int splits = a->k_splits > 1 ? a->k_splits : 1;
+  if (splits > num_kb) splits = num_kb;
+  int kb_per = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kb_per - 1) / kb_per;
+  p.k_splits = splits;
+  p.kb_per_split = kb_per;
+  p.split_stride = (long long)a->M * ldo;
+  if (splits > 1) {
+    VAW_CHECK_ARG(epi == EPI_F32 && a->split_ws, "vaw_gemm_bf16: split-K needs the F32 epilogue and split_ws");
+    p.out = a->split_ws;
+    p.bias = nullptr;
+    p.accumulate = 0;
+    int rc2;
+    switch (bn) {
+      case 128: rc2 = dispatch_epi<128>(epi, tmA, tmB, p, stream); break;
+      case 192: rc2 = dispatch_epi<192>(epi, tmA, tmB, p, stream); break;
+      default: rc2 = dispatch_epi<256>(epi, tmA, tmB, p, stream); break;
+    }
+    if (rc2) return rc2;
+    const long long n4 = (long long)a->M * (a->N / 4);
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    VAW_CHECK_ARG(a->N % 4 == 0, "vaw_gemm_bf16: split-K needs N %% 4 == 0");
+    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a->split_ws, splits, p.split_stride, (float*)a->out,
+                                                              a->bias, a->M, a->N, ldo, a->accumulate);
+    VAW_LAUNCH_CHECK();
+    return VAW_OK;
+  }
 
   switch (bn) {
     case 128: return dispatch_epi<128>(epi, tmA, tmB, p, stream);

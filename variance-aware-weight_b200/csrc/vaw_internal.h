@@ -1,0 +1,73 @@
+// vaw_internal.h — declarations shared between the translation units of libvaw_b200.so.
+// The structs here are layout-identical to the public ones in include/vaw_b200.h (checked by tests/test_abi.py).
+#pragma once
+#include <cuda_runtime.h>
+
+struct vaw_gemm_args {
+  const void* A;       // bf16; K-major: [M,K] row-major (lda) ; MN-major: [K,M] row-major (lda)
+  const void* B;       // bf16; K-major: [N,K] row-major (ldb) ; MN-major: [K,N] row-major (ldb)
+  long long lda, ldb;
+  int a_mn, b_mn;
+  int M, N, K;
+  int epilogue;
+  void* out;           // primary output  [M,N] (ldo)
+  void* out2;          // secondary output [M,N] (ldo)
+  const float* bias;   // [N] or null
+  const float* resid;  // [M,N] fp32 (ldo)
+  const float* gate;   // [M / rows_per_sample, >=N] fp32 (ldg)
+  const void* aux;     // bf16 [M,N] (ldo): saved pre-activation for the d-activation epilogues
+  long long ldo, ldg;
+  int rows_per_sample;
+  int accumulate;      // EPI_F32: out += result
+  int tile_n;          // 0 = auto, else 128 / 192 / 256
+  int resid_mod;       // > 0: resid is [resid_mod, N], indexed by row % resid_mod
+  int k_splits;        // > 1 (EPI_F32 only): split the K loop over k_splits work items per tile
+  float* split_ws;     // fp32 scratch of k_splits * M * ldo elements
+};
+
+enum : int {
+  VAW_EPI_BF16 = 0, VAW_EPI_F32 = 1, VAW_EPI_GELU_TANH = 2, VAW_EPI_GELU_ERF = 3, VAW_EPI_GATE_RES = 4,
+  VAW_EPI_RES = 5, VAW_EPI_DGELU_TANH = 6, VAW_EPI_DGELU_ERF = 7, VAW_EPI_SILU = 8, VAW_EPI_DSILU = 9
+};
+
+// DiT geometry (models/dit.py:157-204)
+struct vaw_dit_cfg {
+  int B, T, D, H, depth, hidden;        // batch, tokens/sample, width, heads, blocks, mlp hidden
+  int C_in, C_out, P, img_h, img_w;     // channels, patch size, image size
+  int table_rows, freq_dim;             // label-embedding rows (0 = unconditional), sinusoid width (256)
+  int learn_align, encoder_depth, proj_dim, z_dim;  // REPA projector (dit.py:27-34,201,274-275)
+};
+
+extern "C" {
+int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream);
+int vaw_attn_fwd(const void* qkv, void* o, float* lse2, int B, int T, int H, int head_dim, cudaStream_t stream);
+int vaw_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int B, int T, int H,
+                 int head_dim, cudaStream_t stream);
+int vaw_ln_fwd(const float* x, const float* shift, const float* scale, long long ld_mod, int rows_per_sample,
+               const float* weight, const float* bias, void* y, float* mean, float* rstd, int M, int D, float eps,
+               cudaStream_t stream);
+int vaw_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
+               long long ld_mod, const float* weight, float* dx_io, int add_into, float* part, int rows_per_group,
+               int groups, int chunks, int M, int D, cudaStream_t stream);
+int vaw_gate_bwd(const float* dx, const void* y, const float* gate, long long ld_gate, void* dy, float* part,
+                 int rows_per_group, int groups, int chunks, int M, int D, cudaStream_t stream);
+int vaw_finish_group(const float* part, int which, int groups, int chunks, int D, float* out, long long ld_out,
+                     int accumulate, cudaStream_t stream);
+int vaw_finish_all(const float* part, int which, int groups, int chunks, int D, const float* w, long long ld_w,
+                   float* out, int accumulate, cudaStream_t stream);
+int vaw_colsum_bf16(const void* a, long long lda, int M, int N, float* part, int rows_per_chunk, float* out,
+                    int accumulate, cudaStream_t stream);
+int vaw_patchify_in(const float* x, void* patches, int B, int C, int H, int W, int P, cudaStream_t stream);
+int vaw_unpatchify(void* tokens, void* image, int dtype, int B, int C, int H, int W, int P, int to_image,
+                   cudaStream_t stream);
+int vaw_timestep_embedding(const float* t, void* out_bf16, float* out_f32, int B, int dim, cudaStream_t stream);
+int vaw_cond_combine(const float* t_emb, const float* table, const long long* labels, float* c, void* c_silu, int B,
+                     int D, cudaStream_t stream);
+int vaw_cond_bwd(const float* dc_silu, const float* c, float* dc, void* dc_bf16, int n, cudaStream_t stream);
+int vaw_embedding_grad(const float* dc, const long long* labels, float* dtable, int rows, int B, int D, int accumulate,
+                       cudaStream_t stream);
+int vaw_cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
+int vaw_add_bf16_into_f32(const void* src, float* dst, long long n, cudaStream_t stream);
+int vaw_colsum_f32_small(const float* a, long long lda, int rows, int N, float* out, int accumulate,
+                         cudaStream_t stream);
+}

@@ -36,7 +36,8 @@ class GemmArgs(C.Structure):
         ("out", C.c_void_p), ("out2", C.c_void_p),
         ("bias", C.c_void_p), ("resid", C.c_void_p), ("gate", C.c_void_p), ("aux", C.c_void_p),
         ("ldo", C.c_longlong), ("ldg", C.c_longlong),
-        ("rows_per_sample", C.c_int), ("accumulate", C.c_int), ("tile_n", C.c_int),
+        ("rows_per_sample", C.c_int), ("accumulate", C.c_int), ("tile_n", C.c_int), ("resid_mod", C.c_int),
+        ("k_splits", C.c_int), ("split_ws", C.c_void_p),
     ]
 
 

@@ -1,0 +1,382 @@
+"""DiT with the reference's constructor, parameter names and return convention, executed by libvaw_b200.so.
+
+Mirrors /root/reference/models/dit.py:157-280 (class DiT) and :361-382 (DiT_S/B/L/XL).  `forward(x, t, y)` returns
+the tuple `(x, zs)` like the reference (:258-280).  The nn.Module is only a *view* of the model: all parameters
+live in one flat fp32 buffer (plus a bf16 shadow for the tensor cores and a flat fp32 gradient buffer); forward
+and backward are one C call each (csrc/dit_engine.cu).  There is no PyTorch fallback: without a CUDA device and
+the built library, forward raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+
+
+class DiTCfg(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "B", "T", "D", "H", "depth", "hidden", "C_in", "C_out", "P", "img_h", "img_w", "table_rows", "freq_dim",
+        "learn_align", "encoder_depth", "proj_dim", "z_dim")]
+
+
+L.register("vaw_dit_param_layout", [C.POINTER(DiTCfg), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p])
+L.register("vaw_dit_workspace_bytes", [C.POINTER(DiTCfg), C.c_void_p])
+L.register("vaw_dit_forward", [C.POINTER(DiTCfg)] + [C.c_void_p] * 9)
+L.register("vaw_dit_backward", [C.POINTER(DiTCfg)] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_void_p])
+L.register("vaw_cast_f32_bf16", [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p])
+
+
+class _ParamHolder(nn.Module):
+    """Carries `weight` / `bias` so that state_dict keys match the reference; computes nothing itself."""
+
+    def __init__(self, weight_shape, bias_shape=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(weight_shape))
+        if bias_shape is not None:
+            self.bias = nn.Parameter(torch.empty(bias_shape))
+
+
+class _Slot(nn.Module):
+    """Placeholder for the parameter-free entries of the reference's nn.Sequential (SiLU) so indices line up."""
+
+
+class _Named(nn.Module):
+    pass
+
+
+def _sincos_1d(dim, pos):
+    omega = np.arange(dim // 2, dtype=np.float64) / (dim / 2.0)
+    omega = 1.0 / 10000 ** omega
+    out = np.einsum("m,d->md", pos.reshape(-1), omega)
+    return np.concatenate([np.sin(out), np.cos(out)], axis=1)
+
+
+def sincos_pos_embed_2d(dim, grid):
+    """Fixed 2-D sin/cos table, same construction as reference dit.py:307-354 (w axis first)."""
+    gh = np.arange(grid, dtype=np.float32)
+    gw = np.arange(grid, dtype=np.float32)
+    mesh = np.stack(np.meshgrid(gw, gh), axis=0).reshape(2, 1, grid, grid)
+    return np.concatenate([_sincos_1d(dim // 2, mesh[0]), _sincos_1d(dim // 2, mesh[1])], axis=1)
+
+
+class DiT(nn.Module):
+    def __init__(self, image_size=32, patch_size=2, in_channels=4, hidden_size=1152, depth=28, num_heads=16,
+                 mlp_ratio=4.0, class_dropout_prob=0.1, num_classes=1000, learn_sigma=False, learn_align=False,
+                 encoder_depth=8, z_dims=768, projector_dim=2048):
+        super().__init__()
+        self.learn_sigma = learn_sigma
+        self.learn_align = learn_align
+        self.in_channels = in_channels
+        self.out_channels = in_channels * 2 if learn_sigma else in_channels
+        self.patch_size = patch_size
+        self.num_heads = num_heads
+        self.encoder_depth = encoder_depth
+        self.hidden_size = hidden_size
+        self.depth = depth
+        self.image_size = image_size
+        self.num_classes = num_classes
+        self.class_dropout_prob = class_dropout_prob
+        self.mlp_hidden = int(hidden_size * mlp_ratio)
+        self.z_dims, self.projector_dim = z_dims, projector_dim
+        assert not learn_align or encoder_depth > 0, "encoder_depth must be > 0 when learn_align=True"  # dit.py:190
+        D, Hd = hidden_size, self.mlp_hidden
+        grid = image_size // patch_size
+        self.num_patches = grid * grid
+        ppc = patch_size * patch_size * self.out_channels
+        table_rows = num_classes + (1 if class_dropout_prob > 0 else 0)
+
+        # --- module tree with the reference's names (dit.py:192-202) ---
+        self.x_embedder = _Named()
+        self.x_embedder.proj = _ParamHolder((D, in_channels, patch_size, patch_size), (D,))
+        self.x_embedder.patch_size = (patch_size, patch_size)
+        self.x_embedder.num_patches = self.num_patches
+        self.t_embedder = _Named()
+        self.t_embedder.mlp = nn.ModuleList([_ParamHolder((D, 256), (D,)), _Slot(), _ParamHolder((D, D), (D,))])
+        self.y_embedder = _Named()
+        self.y_embedder.embedding_table = _ParamHolder((table_rows, D))
+        self.pos_embed = nn.Parameter(torch.zeros(1, self.num_patches, D), requires_grad=False)
+        blocks = []
+        for _ in range(depth):
+            b = _Named()
+            b.attn = _Named()
+            b.attn.qkv = _ParamHolder((3 * D, D), (3 * D,))
+            b.attn.proj = _ParamHolder((D, D), (D,))
+            b.mlp = _Named()
+            b.mlp.fc1 = _ParamHolder((Hd, D), (Hd,))
+            b.mlp.fc2 = _ParamHolder((D, Hd), (D,))
+            b.adaLN_modulation = nn.ModuleList([_Slot(), _ParamHolder((6 * D, D), (6 * D,))])
+            blocks.append(b)
+        self.blocks = nn.ModuleList(blocks)
+        if learn_align:
+            self.projectors = nn.ModuleList([
+                _ParamHolder((projector_dim, D), (projector_dim,)), _Slot(),
+                _ParamHolder((projector_dim, projector_dim), (projector_dim,)), _Slot(),
+                _ParamHolder((z_dims, projector_dim), (z_dims,))])
+        else:
+            self.projectors = None
+        self.final_layer = _Named()
+        self.final_layer.linear = _ParamHolder((ppc, D), (ppc,))
+        self.final_layer.adaLN_modulation = nn.ModuleList([_Slot(), _ParamHolder((2 * D, D), (2 * D,))])
+
+        self._cfg_static = dict(T=self.num_patches, D=D, H=num_heads, depth=depth, hidden=Hd, C_in=in_channels,
+                                C_out=self.out_channels, P=patch_size, img_h=image_size, img_w=image_size,
+                                table_rows=table_rows, freq_dim=256, learn_align=int(learn_align),
+                                encoder_depth=encoder_depth if learn_align else 0,
+                                proj_dim=projector_dim if learn_align else 0, z_dim=z_dims if learn_align else 0)
+        self._flat = None      # fp32 [n] leaf tensor holding every parameter
+        self._shadow = None    # bf16 [n]
+        self._gflat = None     # fp32 [n]
+        self._shadow_version = -1
+        self._ws = None
+        self._ws_batch = -1
+        self._fwd_serial = 0
+        self._events = None
+        self.initialize_weights()
+
+    # ------------------------------------------------------------------------------------------------
+    def _ordered_params(self):
+        """Parameters in the engine's layout order (csrc/dit_engine.cu ParamId).  The stacked adaLN slot is
+        expanded into the per-block tensors, which are contiguous slices of it."""
+        t = self.t_embedder.mlp
+        head = [self.x_embedder.proj.weight, self.x_embedder.proj.bias, t[0].weight, t[0].bias, t[2].weight,
+                t[2].bias, self.y_embedder.embedding_table.weight, self.pos_embed,
+                self.final_layer.adaLN_modulation[1].weight, self.final_layer.adaLN_modulation[1].bias,
+                self.final_layer.linear.weight, self.final_layer.linear.bias]
+        if self.learn_align:
+            pr = self.projectors
+            head += [pr[0].weight, pr[0].bias, pr[2].weight, pr[2].bias, pr[4].weight, pr[4].bias]
+        else:
+            head += [None] * 6
+        return head
+
+    def _cfg(self, batch):
+        return DiTCfg(B=batch, **self._cfg_static)
+
+    def _layout(self):
+        cfg = self._cfg(1)
+        cap = 20 + 8 * self.depth
+        off = (C.c_longlong * cap)()
+        num = (C.c_longlong * cap)()
+        n = C.c_int()
+        total = C.c_longlong()
+        L.call("vaw_dit_param_layout", C.byref(cfg), off, num, cap, C.byref(n), C.byref(total))
+        return list(off)[: n.value], list(num)[: n.value], total.value
+
+    def _slots(self):
+        """[(parameter, flat offset)] for every parameter tensor."""
+        off, num, total = self._layout()
+        D = self.hidden_size
+        slots = []
+        for i, p in enumerate(self._ordered_params()):
+            if p is not None and p.numel() > 0:
+                assert p.numel() == num[i], (i, p.shape, num[i])
+                slots.append((p, off[i]))
+        for i, b in enumerate(self.blocks):  # stacked adaLN: rows [i*6D, (i+1)*6D)
+            slots.append((b.adaLN_modulation[1].weight, off[18] + i * 6 * D * D))
+            slots.append((b.adaLN_modulation[1].bias, off[19] + i * 6 * D))
+            base = 20 + 8 * i
+            for j, p in enumerate((b.attn.qkv.weight, b.attn.qkv.bias, b.attn.proj.weight, b.attn.proj.bias,
+                                   b.mlp.fc1.weight, b.mlp.fc1.bias, b.mlp.fc2.weight, b.mlp.fc2.bias)):
+                slots.append((p, off[base + j]))
+        return slots, total
+
+    def _ensure_flat(self, device):
+        """(Re)pack the parameters into the flat buffer if they are not already views of it (after .to(), deepcopy,
+        load_state_dict(assign=True) ...)."""
+        slots, total = self._slots()
+        ok = (self._flat is not None and self._flat.device == device and all(
+            p.data_ptr() == self._flat.data_ptr() + 4 * o and p.device == device for p, o in slots))
+        if ok:
+            return
+        flat = torch.zeros(total, dtype=torch.float32, device=device)
+        gflat = torch.zeros(total, dtype=torch.float32, device=device)
+        with torch.no_grad():
+            for p, o in slots:
+                n = p.numel()
+                flat[o:o + n].copy_(p.detach().reshape(-1).to(device=device, dtype=torch.float32))
+                old_grad = p.grad
+                p.data = flat[o:o + n].view(p.shape)
+                if old_grad is not None:
+                    gflat[o:o + n].copy_(old_grad.reshape(-1).to(device=device, dtype=torch.float32))
+                    p.grad = gflat[o:o + n].view(p.shape)
+        flat.requires_grad_(True)
+        self._flat, self._gflat = flat, gflat
+        self._shadow = torch.empty(total, dtype=torch.bfloat16, device=device)
+        self._shadow_version = -1
+        self._slot_cache = slots
+
+    def _refresh_shadow(self):
+        # every in-place update of a parameter (optimizer step, load_state_dict, init) bumps its version counter
+        v = sum(p._version for p, _ in self._slot_cache)
+        if v != self._shadow_version:
+            L.call("vaw_cast_f32_bf16", self._flat.data_ptr(), self._shadow.data_ptr(), self._flat.numel(), L.stream_ptr())
+            self._shadow_version = v
+
+    def _ensure_workspace(self, batch, device):
+        if self._ws is None or self._ws_batch != batch or self._ws.device != device:
+            cfg = self._cfg(batch)
+            nbytes = C.c_longlong()
+            L.call("vaw_dit_workspace_bytes", C.byref(cfg), C.byref(nbytes))
+            self._ws = None
+            self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+            self._ws_batch = batch
+
+    def flat_parameters(self):
+        """(flat fp32 params, flat fp32 grads, bf16 shadow) — used by the fused optimizer and the DP all-reduce."""
+        return self._flat, self._gflat, self._shadow
+
+    def block_grad_ranges(self):
+        """Element ranges [(begin, end)] of the flat gradient buffer per transformer block, for bucketed all-reduce."""
+        off, num, total = self._layout()
+        ranges = []
+        for i in range(self.depth):
+            base = 20 + 8 * i
+            ranges.append((off[base], off[base + 7] + num[base + 7]))
+        return ranges, (0, off[20]), total
+
+    # ------------------------------------------------------------------------------------------------
+    def initialize_weights(self):
+        """Same initialisation scheme as the reference (dit.py:206-241)."""
+        D = self.hidden_size
+        with torch.no_grad():
+            for m in self.modules():
+                if isinstance(m, _ParamHolder) and m.weight.dim() == 2 and m is not self.y_embedder.embedding_table:
+                    nn.init.xavier_uniform_(m.weight)
+                    if hasattr(m, "bias"):
+                        nn.init.zeros_(m.bias)
+            grid = int(self.num_patches ** 0.5)
+            self.pos_embed.copy_(torch.from_numpy(sincos_pos_embed_2d(D, grid)).float().unsqueeze(0))
+            w = self.x_embedder.proj.weight
+            nn.init.xavier_uniform_(w.view(w.shape[0], -1))
+            nn.init.zeros_(self.x_embedder.proj.bias)
+            nn.init.normal_(self.y_embedder.embedding_table.weight, std=0.02)
+            nn.init.normal_(self.t_embedder.mlp[0].weight, std=0.02)
+            nn.init.normal_(self.t_embedder.mlp[2].weight, std=0.02)
+            for b in self.blocks:
+                nn.init.zeros_(b.adaLN_modulation[1].weight)
+                nn.init.zeros_(b.adaLN_modulation[1].bias)
+            nn.init.zeros_(self.final_layer.adaLN_modulation[1].weight)
+            nn.init.zeros_(self.final_layer.adaLN_modulation[1].bias)
+            nn.init.zeros_(self.final_layer.linear.weight)
+            nn.init.zeros_(self.final_layer.linear.bias)
+
+    def unpatchify(self, x):
+        """(N, T, p*p*C) -> (N, C, H, W); host-side helper kept for API parity (dit.py:243-256)."""
+        c, p = self.out_channels, self.patch_size
+        h = w = int(x.shape[1] ** 0.5)
+        x = x.reshape(x.shape[0], h, w, p, p, c)
+        return torch.einsum("nhwpqc->nchpwq", x).reshape(x.shape[0], c, h * p, w * p)
+
+    def token_drop(self, labels, force_drop_ids=None):
+        """Label dropout for classifier-free guidance (dit.py:94-103); the draw stays a torch.rand on the device so
+        the CUDA generator is consumed exactly like the reference."""
+        if force_drop_ids is None:
+            drop = torch.rand(labels.shape[0], device=labels.device) < self.class_dropout_prob
+        else:
+            drop = force_drop_ids == 1
+        return torch.where(drop, self.num_classes, labels)
+
+    def forward(self, x, t, y=None, force_drop_ids=None, **kwargs):
+        if not x.is_cuda:
+            raise L.VawError("vaw_b200.models.DiT runs on CUDA only (no CPU fallback)")
+        if x.shape[1:] != (self.in_channels, self.image_size, self.image_size):
+            raise AssertionError(f"expected input [N,{self.in_channels},{self.image_size},{self.image_size}], got {tuple(x.shape)}")
+        if self._cfg_static["table_rows"] > 0:
+            if y is None:
+                raise ValueError("class-conditional DiT needs labels y")
+            if (self.training and self.class_dropout_prob > 0) or force_drop_ids is not None:
+                y = self.token_drop(y, force_drop_ids)
+            y = y.to(torch.int64).contiguous()
+        else:
+            y = None
+        self._ensure_flat(x.device)
+        self._ensure_workspace(x.shape[0], x.device)
+        out, zs = _DiTFunction.apply(self, x.float().contiguous(), t.float().contiguous(), y, self._flat)
+        return out, zs
+
+    # grad bookkeeping used by _DiTFunction.backward
+    def _bind_grads(self):
+        fresh = any(p.grad is None for p, _ in self._slot_cache if p.requires_grad)
+        if fresh:
+            for p, o in self._slot_cache:
+                if p.requires_grad:
+                    p.grad = self._gflat[o:o + p.numel()].view(p.shape)
+        return fresh
+
+
+class _DiTFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, t, y, flat):
+        B = x.shape[0]
+        cfg = model._cfg(B)
+        model._refresh_shadow()
+        out = torch.empty(B, model.out_channels, model.image_size, model.image_size, dtype=torch.bfloat16, device=x.device)
+        zs = None
+        if model.learn_align:
+            zs = torch.empty(B, model.num_patches, model.z_dims, dtype=torch.bfloat16, device=x.device)
+        L.call("vaw_dit_forward", C.byref(cfg), flat.data_ptr(), model._shadow.data_ptr(), model._ws.data_ptr(),
+               x.data_ptr(), t.data_ptr(), L.ptr(y), out.data_ptr(), L.ptr(zs), L.stream_ptr())
+        model._fwd_serial += 1
+        ctx.model, ctx.serial, ctx.batch, ctx.y = model, model._fwd_serial, B, y
+        return out, zs
+
+    @staticmethod
+    def backward(ctx, dout, dzs):
+        model = ctx.model
+        if ctx.serial != model._fwd_serial:
+            raise L.VawError("DiT backward after a newer forward: the activation workspace was overwritten "
+                             "(run forward/backward pairs in order)")
+        cfg = model._cfg(ctx.batch)
+        if dout is None:
+            dout = torch.zeros(ctx.batch, model.out_channels, model.image_size, model.image_size,
+                               dtype=torch.bfloat16, device=model._flat.device)
+        dout = dout.to(torch.bfloat16).contiguous()
+        if dzs is not None:
+            dzs = dzs.to(torch.bfloat16).contiguous()
+        fresh = model._bind_grads()
+        if fresh and model.learn_align and dzs is None:
+            model._gflat.zero_()  # projector gradients are not produced without an alignment loss
+        ev = None
+        if model._events is not None:
+            ev = (C.c_void_p * len(model._events))(*[e.cuda_event for e in model._events])
+        L.call("vaw_dit_backward", C.byref(cfg), model._flat.data_ptr(), model._shadow.data_ptr(),
+               model._gflat.data_ptr(), model._ws.data_ptr(), dout.data_ptr(), L.ptr(dzs), L.ptr(ctx.y),
+               0 if fresh else 1, ev, L.stream_ptr())
+        if model._post_backward is not None:
+            model._post_backward()
+        return None, None, None, None, None
+
+
+DiT._post_backward = None
+
+
+def DiT_S(image_size, patch_size, in_channels, class_dropout_prob, num_classes, learn_sigma, **kwargs):
+    return DiT(image_size=image_size, patch_size=patch_size, in_channels=in_channels, hidden_size=384, depth=12,
+               num_heads=6, class_dropout_prob=class_dropout_prob, num_classes=num_classes, learn_sigma=learn_sigma,
+               **kwargs)
+
+
+def DiT_B(image_size, patch_size, in_channels, class_dropout_prob, num_classes, learn_sigma, **kwargs):
+    return DiT(image_size=image_size, patch_size=patch_size, in_channels=in_channels, hidden_size=768, depth=12,
+               num_heads=12, class_dropout_prob=class_dropout_prob, num_classes=num_classes, learn_sigma=learn_sigma,
+               **kwargs)
+
+
+def DiT_L(image_size, patch_size, in_channels, class_dropout_prob, num_classes, learn_sigma, **kwargs):
+    return DiT(image_size=image_size, patch_size=patch_size, in_channels=in_channels, hidden_size=1024, depth=24,
+               num_heads=16, class_dropout_prob=class_dropout_prob, num_classes=num_classes, learn_sigma=learn_sigma,
+               **kwargs)
+
+
+def DiT_XL(image_size, patch_size, in_channels, class_dropout_prob, num_classes, learn_sigma, **kwargs):
+    return DiT(image_size=image_size, patch_size=patch_size, in_channels=in_channels, hidden_size=1152, depth=28,
+               num_heads=16, class_dropout_prob=class_dropout_prob, num_classes=num_classes, learn_sigma=learn_sigma,
+               **kwargs)
+
+
+DiT_models = {"DiT-S": DiT_S, "DiT-B": DiT_B, "DiT-L": DiT_L, "DiT-XL": DiT_XL}
