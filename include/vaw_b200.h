@@ -140,11 +140,92 @@ typedef struct vaw_gemm_args {
   int accumulate;
   int tile_n;    /* 0 = auto; 128 / 192 / 256 */
   int resid_mod; /* > 0: resid is a [resid_mod, N] table indexed by row % resid_mod (pos_embed) */
-  int k_splits;  /* > 1 (VAW_EPI_F32 only): split-K over k_splits work items per tile (deterministic reduce) */
-  float* split_ws; /* fp32 scratch, k_splits * M * ldo elements */
+  int k_splits;  /* VAW_EPI_F32 only. > 1: split every tile's K loop; -1: split only the partial last wave
+                    ("tail split"); partials are folded in fixed order (deterministic) */
+  float* split_ws;          /* fp32 scratch for the partial slabs (128 x tile_n each) */
+  long long split_ws_elems; /* capacity of split_ws in floats (0 = unchecked) */
+  int cta_group; /* 0 = auto, 1 = one CTA per 128-row tile, 2 = SM pair per 256-row tile (tcgen05 cta_group::2) */
 } vaw_gemm_args;
 
 int vaw_gemm_bf16(const vaw_gemm_args* args, vaw_stream_t stream);
+
+/* ---- K4: flash-style attention ------------------------------------------------------------------------------------
+ * Replaces F.scaled_dot_product_attention inside timm Attention (models/dit.py:126) / models/uvit.py:72-75 and its
+ * backward.  qkv: bf16 [B*T, 3*H*hd], feature order (3, H, hd); o: bf16 [B*T, H*hd]; lse2: fp32 [B, H, T] (log2
+ * domain); head_dim 64 or 72.  dqkv has the layout of qkv.                                                          */
+int vaw_attn_fwd(const void* qkv, void* o, float* lse2, int B, int T, int H, int head_dim, vaw_stream_t stream);
+int vaw_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int B, int T, int H,
+                 int head_dim, vaw_stream_t stream);
+
+/* ---- K4: LayerNorm (+ adaLN modulate | affine) forward / backward, residual-branch backward, reductions ------------
+ * Replace nn.LayerNorm + modulate (models/dit.py:24-25,122-124,133-137,151-155) and nn.LayerNorm(affine)
+ * (models/uvit.py:103-110) with their autograd backward.  x fp32 [M, D]; y / dy bf16 [M, D]; shift/scale/gate are
+ * rows of the adaLN output (row = sample, leading dimension ld_mod); weight/bias fp32 [D].
+ * Backward kernels leave [groups, chunks, 2, D] fp32 partial sums in `part`; vaw_finish_* fold them in fixed order. */
+int vaw_ln_fwd(const float* x, const float* shift, const float* scale, long long ld_mod, int rows_per_sample,
+               const float* weight, const float* bias, void* y, float* mean, float* rstd, int M, int D, float eps,
+               vaw_stream_t stream);
+int vaw_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
+               long long ld_mod, const float* weight, float* dx_io, int add_into, float* part, int rows_per_group,
+               int groups, int chunks, int M, int D, vaw_stream_t stream);
+int vaw_gate_bwd(const float* dx, const void* y, const float* gate, long long ld_gate, void* dy, float* part,
+                 int rows_per_group, int groups, int chunks, int M, int D, vaw_stream_t stream);
+int vaw_finish_group(const float* part, int which, int groups, int chunks, int D, float* out, long long ld_out,
+                     int accumulate, vaw_stream_t stream);
+int vaw_finish_all(const float* part, int which, int groups, int chunks, int D, const float* w, long long ld_w,
+                   float* out, int accumulate, vaw_stream_t stream);
+int vaw_colsum_bf16(const void* a, long long lda, int M, int N, float* part, int rows_per_chunk, float* out,
+                    int accumulate, vaw_stream_t stream);
+int vaw_colsum_f32_small(const float* a, long long lda, int rows, int N, float* out, int accumulate,
+                         vaw_stream_t stream);
+
+/* ---- embedders, (un)patchify, casts (models/dit.py:41-110,243-256; timm PatchEmbed; models/uvit.py:21-52) ---------- */
+int vaw_patchify_in(const float* x, void* patches, int B, int C, int H, int W, int P, vaw_stream_t stream);
+int vaw_unpatchify(void* tokens, void* image, int dtype, int B, int C, int H, int W, int P, int to_image,
+                   vaw_stream_t stream);
+int vaw_timestep_embedding(const float* t, void* out_bf16, float* out_f32, int B, int dim, vaw_stream_t stream);
+int vaw_cond_combine(const float* t_emb, const float* table, const long long* labels, float* c, void* c_silu, int B,
+                     int D, vaw_stream_t stream);
+int vaw_cond_bwd(const float* dc_silu, const float* c, float* dc, void* dc_bf16, int n, vaw_stream_t stream);
+int vaw_embedding_grad(const float* dc, const long long* labels, float* dtable, int rows, int B, int D, int accumulate,
+                       vaw_stream_t stream);
+int vaw_cast_f32_bf16(const float* src, void* dst, long long n, vaw_stream_t stream);
+int vaw_add_bf16_into_f32(const void* src, float* dst, long long n, vaw_stream_t stream);
+
+/* ---- K5: REPA alignment loss, type 'mse' (tools/gaussian_diffusion.py:1011-1013) ------------------------------------
+ * loss = mean((zs - feat)^2) (scalar, deterministic two-stage reduction); dzs = gscale * 2 (zs - feat) / n (nullable).
+ * dtype codes VAW_F32 / VAW_BF16; part: fp32 scratch of >= 1024 elements.                                            */
+int vaw_align_mse(const void* zs, int zs_dtype, const void* feat, int feat_dtype, void* dzs, float gscale, long long n,
+                  float* part, float* loss, vaw_stream_t stream);
+
+/* ---- fused AdamW over the flat parameter buffer (main.py:354 optim.AdamW; trainer.py:12-18 EMA; §8f-1) ----------------
+ * One pass: p, m, v updated in place from g * grad_scale; p_bf16 (nullable) refreshed; ema (nullable) updated.        */
+int vaw_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, float* ema, long long n, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, long long step, double grad_scale,
+                   double ema_decay, vaw_stream_t stream);
+
+/* ---- DiT engine: forward / backward of the whole denoiser as one call each (models/dit.py:157-280) ----------------- */
+typedef struct vaw_dit_cfg {
+  int B, T, D, H, depth, hidden;
+  int C_in, C_out, P, img_h, img_w;
+  int table_rows, freq_dim;
+  int learn_align, encoder_depth, proj_dim, z_dim;
+} vaw_dit_cfg;
+
+/* Offsets / sizes (elements) of every parameter tensor in the flat buffers; order documented in csrc/dit_engine.cu. */
+int vaw_dit_param_layout(const vaw_dit_cfg* cfg, long long* offsets, long long* numels, int cap, int* n_out,
+                         long long* total);
+int vaw_dit_workspace_bytes(const vaw_dit_cfg* cfg, long long* bytes);
+/* P fp32 params, Pb their bf16 shadow, ws the workspace; x_t fp32 [B,C,H,W], t fp32 [B] (scaled like
+ * _scale_timesteps, tools/gaussian_diffusion.py:417-420), y int64 [B]; out bf16 [B,C_out,H,W]; zs bf16 [B*T,z_dim]. */
+int vaw_dit_forward(const vaw_dit_cfg* cfg, const float* P, const void* Pb, void* ws, const float* x_t, const float* t,
+                    const long long* y, void* out, void* zs, vaw_stream_t stream);
+/* G fp32 gradients (same layout as P); dout bf16 [B,C_out,H,W]; dzs bf16 or NULL; accumulate 0 = overwrite G.
+ * events: NULL or depth+1 cudaEvent_t recorded as each block's gradients (last block first) become final.          */
+int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const void* Pb, float* G, void* ws, const void* dout,
+                     const void* dzs, const long long* y, int accumulate, void** events, vaw_stream_t stream);
+
+unsigned long long vaw_launch_count(void); /* kernels launched by this library in this process */
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,161 @@
+"""Generate the golden fixtures in tests/golden/ by EXECUTING the reference (/root/reference, read-only) on CPU.
+
+Run in the build container only (the reference does not travel to the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference is imported with the small import stubs in oracle/ref_stubs (timm / diffusers / torchdiffeq are not
+installed; see oracle/ref_stubs/README.md).  Everything written here is an input/output pair of reference code:
+    diffusion_golden.npz   schedules, tables, compute_mse_loss_weight over all t, q_sample / compute_target,
+                           training_losses (+ autograd gradient w.r.t. the model output)
+    sampler_golden.npz     LossSecondMomentResampler.weights / sample / update_with_all_losses, UniformSampler.sample
+    dit_golden.npz         a tiny DiT (with REPA projector): weights, forward outputs, full training_losses + grads
+"""
+import os
+import sys
+from types import SimpleNamespace
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [os.path.join(ROOT, "oracle", "ref_stubs"), "/root/reference"]
+
+import numpy as np
+import torch
+
+import tools.gaussian_diffusion as rgd   # noqa: E402  (reference)
+import tools.resample as rrs             # noqa: E402  (reference)
+import models.dit as rdit                # noqa: E402  (reference)
+
+
+def ref_args(**kw):
+    d = dict(weight_type="lambda", gamma=0.5, learn_sigma=False, p2_gamma=1.0, p2_k=1.0, time_dist=["uniform"],
+             learn_align=False, align_type="mse", amp=False)
+    d.update(kw)
+    return SimpleNamespace(**d)
+
+
+def make_diffusion(schedule="linear", mean="EPSILON", **kw):
+    return rgd.GaussianDiffusion(args=ref_args(**kw), betas=rgd.get_named_beta_schedule(schedule, 1000),
+                                 model_mean_type=rgd.ModelMeanType[mean], model_var_type=rgd.ModelVarType.FIXED_LARGE,
+                                 loss_type=rgd.LossType.MSE, rescale_timesteps=True, device="cpu")
+
+
+WEIGHT_CASES = [
+    ("EPSILON", "constant"), ("EPSILON", "lambda"), ("EPSILON", "min_snr_5"), ("EPSILON", "max_snr_1"),
+    ("EPSILON", "debias"), ("EPSILON", "p2"), ("EPSILON", "min_debias"), ("EPSILON", "max_debias"),
+    ("START_X", "trunc_snr"), ("START_X", "snr"), ("START_X", "inv_snr"), ("START_X", "min_snr_5"),
+    ("START_X", "max_snr_2"), ("START_X", "lambda"), ("VELOCITY", "min_snr_5"), ("VELOCITY", "lambda"),
+]
+
+
+def diffusion_golden():
+    out = {}
+    for sched in ("linear", "cosine", "linear_logsnr"):
+        d = make_diffusion(sched)
+        out[f"betas_{sched}"] = d.betas
+        out[f"sqrt_ac_{sched}"] = d.sqrt_alphas_cumprod
+        out[f"sqrt_1mac_{sched}"] = d.sqrt_one_minus_alphas_cumprod
+        out[f"pmc1_{sched}"] = d.posterior_mean_coef1
+        out[f"pmc2_{sched}"] = d.posterior_mean_coef2
+    t_all = torch.arange(1000)
+    for sched in ("linear", "cosine"):
+        d = make_diffusion(sched)
+        alpha = rgd._extract_into_tensor(d.sqrt_alphas_cumprod, t_all, t_all.shape)
+        sigma = rgd._extract_into_tensor(d.sqrt_one_minus_alphas_cumprod, t_all, t_all.shape)
+        for mean, wt in WEIGHT_CASES:
+            w = rgd.compute_mse_loss_weight(rgd.ModelMeanType[mean], wt, t_all, alpha.clone(), sigma.clone(), 1.0, 1.0)
+            out[f"w_{sched}_{mean}_{wt}"] = w.float().numpy()
+    g = torch.Generator().manual_seed(7)
+    x0 = torch.randn(6, 3, 8, 8, generator=g).clamp(-1, 1)
+    eps = torch.randn(6, 3, 8, 8, generator=g)
+    t = torch.tensor([0, 1, 500, 998, 999, 37])
+    model_out = torch.randn(6, 3, 8, 8, generator=g)
+    out.update(x0=x0.numpy(), eps=eps.numpy(), t=t.numpy(), model_out=model_out.numpy())
+    for mean, wt in (("EPSILON", "lambda"), ("START_X", "lambda"), ("VELOCITY", "min_snr_5"), ("PREVIOUS_X", "constant"),
+                     ("EPSILON", "min_snr_5")):
+        d = make_diffusion("linear", mean, weight_type=wt)
+        out[f"xt_{mean}"] = d.q_sample(x0, t, eps).numpy()
+        out[f"target_{mean}"] = d.compute_target(x0, eps, t).numpy()
+        mo = model_out.clone().requires_grad_(True)
+        terms = d.training_losses(lambda x, ts, **k: mo, x0, None, t=t, noise=eps)
+        terms["loss"].mean().backward()
+        out[f"mse_{mean}_{wt}"] = terms["mse"].detach().float().numpy()
+        out[f"grad_{mean}_{wt}"] = mo.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "diffusion_golden.npz"), **out)
+    print("diffusion_golden.npz", len(out), "arrays")
+
+
+def sampler_golden():
+    out = {}
+    d = make_diffusion("linear")
+    rng = np.random.RandomState(11)
+    # warmed-up sampler
+    s = rrs.LossSecondMomentResampler(d)
+    hist = np.abs(rng.randn(1000, 10)) * (0.02 + rng.rand(1000, 1))
+    s._loss_history[:] = hist
+    s._loss_counts[:] = 10
+    out["hist"] = hist
+    out["weights"] = s.weights()
+    np.random.seed(2024)
+    idx, w = s.sample(48, "cpu")
+    out["sample_idx"], out["sample_w"] = idx.numpy(), w.numpy()
+    out["next_uniform_after_sample"] = np.array([np.random.random_sample()])
+    # cold sampler -> uniform branch
+    s2 = rrs.LossSecondMomentResampler(d)
+    out["weights_cold"] = s2.weights()
+    np.random.seed(77)
+    idx2, w2 = s2.sample(32, "cpu")
+    out["cold_idx"], out["cold_w"] = idx2.numpy(), w2.numpy()
+    # update sequence with duplicates, small T range so that rows wrap around
+    ts = rng.randint(0, 25, size=400)
+    losses = rng.rand(400).astype(np.float32)
+    s3 = rrs.LossSecondMomentResampler(d)
+    s3.update_with_all_losses(ts.tolist(), [float(x) for x in losses])
+    out["upd_ts"], out["upd_losses"] = ts, losses
+    out["upd_hist"], out["upd_counts"] = s3._loss_history.copy(), s3._loss_counts.copy()
+    # uniform sampler
+    u = rrs.UniformSampler(d)
+    np.random.seed(5)
+    ui, uw = u.sample(40, "cpu")
+    out["uni_idx"], out["uni_w"] = ui.numpy(), uw.numpy()
+    np.savez_compressed(os.path.join(HERE, "sampler_golden.npz"), **out)
+    print("sampler_golden.npz", len(out), "arrays")
+
+
+def dit_golden():
+    torch.manual_seed(3)
+    cfg = dict(image_size=8, patch_size=2, in_channels=4, hidden_size=64, depth=2, num_heads=1,
+               class_dropout_prob=0.0, num_classes=10, learn_sigma=False, learn_align=True, encoder_depth=1,
+               z_dims=16, projector_dim=32)
+    m = rdit.DiT(**cfg)
+    with torch.no_grad():
+        for p in m.parameters():   # de-zero the adaLN-Zero / final-layer tensors
+            if p.requires_grad and p.abs().sum() == 0:
+                p.normal_(0, 0.02)
+    m.train()
+    g = torch.Generator().manual_seed(9)
+    x0 = torch.randn(3, 4, 8, 8, generator=g)
+    eps = torch.randn(3, 4, 8, 8, generator=g)
+    t = torch.tensor([3, 500, 990])
+    y = torch.tensor([1, 7, 4])
+    feats = torch.randn(3, 16, 16, generator=g)
+    out = {f"param::{k}": v.detach().numpy() for k, v in m.state_dict().items()}
+    out.update(x0=x0.numpy(), eps=eps.numpy(), t=t.numpy(), y=y.numpy(), feats=feats.numpy())
+    d = make_diffusion("cosine", "EPSILON", weight_type="lambda", learn_align=True, gamma=0.5)
+    x_t = d.q_sample(x0, t, eps)
+    o, zs = m(x_t, d._scale_timesteps(t), y)
+    out["fwd_out"], out["fwd_zs"] = o.detach().numpy(), zs.detach().numpy()
+    terms = d.training_losses(m, x0, feats, t=t, model_kwargs={"y": y}, noise=eps)
+    terms["loss"].mean().backward()
+    out["mse"], out["align"], out["loss"] = (terms[k].detach().numpy() for k in ("mse", "align", "loss"))
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            out[f"grad::{k}"] = p.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "dit_golden.npz"), **out)
+    print("dit_golden.npz", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    diffusion_golden()
+    sampler_golden()
+    dit_golden()

@@ -1,0 +1,46 @@
+"""GPU tier: flash-style attention forward/backward through the C ABI vs torch SDPA in fp32 on the same bf16 inputs."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import relerr
+from vaw_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+L.register("vaw_attn_fwd", [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p])
+L.register("vaw_attn_bwd", [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p])
+
+
+@pytest.mark.parametrize("B,T,H,hd", [(2, 256, 3, 64), (2, 256, 2, 72), (3, 258, 2, 64), (2, 64, 2, 72), (1, 100, 1, 64),
+                                      (1, 1, 1, 64), (2, 17, 2, 72), (64, 256, 16, 72)])
+def test_forward_backward(B, T, H, hd):
+    torch.manual_seed(0)
+    qkv = (torch.randn(B, T, 3, H, hd, device=DEV) * 0.7).bfloat16()
+    o = torch.full((B, T, H, hd), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, T, device=DEV)
+    L.call("vaw_attn_fwd", qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, H, hd, L.stream_ptr())
+    q, k, v = [qkv[:, :, i].float().permute(0, 2, 1, 3).requires_grad_(True) for i in range(3)]
+    ref = F.scaled_dot_product_attention(q, k, v)
+    assert relerr(o.permute(0, 2, 1, 3), ref) < 6e-3
+    # log-sum-exp (log2 domain) against the definition
+    s = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
+    assert relerr(lse, torch.logsumexp(s, -1) * 1.4426950408889634) < 1e-3
+    do = torch.randn_like(o)
+    dqkv = torch.full_like(qkv, float("nan"))
+    L.call("vaw_attn_bwd", qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, T, H, hd,
+           L.stream_ptr())
+    ref.backward(do.float().permute(0, 2, 1, 3))
+    scale = max(g.abs().max().item() for g in (q.grad, k.grad, v.grad))
+    for i, g in enumerate((q.grad, k.grad, v.grad)):
+        got = dqkv[:, :, i].permute(0, 2, 1, 3).float()
+        # relative to the tensor's norm, with a floor for gradients that are analytically zero (e.g. dq, dk at T = 1)
+        assert (got - g).norm().item() <= 1.2e-2 * g.norm().item() + 1e-4 * scale * g.numel() ** 0.5
+
+
+def test_unsupported_head_dim_fails_loudly():
+    x = torch.zeros(1, 16, 3, 1, 48, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(L.VawError):
+        L.call("vaw_attn_fwd", x.data_ptr(), x.data_ptr(), x.data_ptr(), 1, 16, 1, 48, L.stream_ptr())

@@ -1,0 +1,136 @@
+"""GPU tier: K1 (q_sample + target) and K2 (weighted MSE fwd+bwd) through the C ABI vs the oracle and the golden
+fixtures of the executed reference.  fp32 integer-indexed arithmetic: bit-exact; reductions: 1e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import diffusion as odiff
+from vaw_b200.tools import gaussian_diffusion as gd
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("mean", ["EPSILON", "START_X", "VELOCITY", "PREVIOUS_X"])
+def test_k1_matches_reference_golden_bit_exact(mean):
+    g = np.load(os.path.join(G, "diffusion_golden.npz"))
+    d = gd.create_gaussian_diffusion(noise_schedule="linear", mean_type=mean.lower(),
+                                     weight_type="constant" if mean == "PREVIOUS_X" else "lambda")
+    x0, eps, t = (torch.from_numpy(g[k]).to(DEV) for k in ("x0", "eps", "t"))
+    assert np.array_equal(d.q_sample(x0, t, eps).cpu().numpy(), g[f"xt_{mean}"])
+    assert np.array_equal(d.compute_target(x0, eps, t).cpu().numpy(), g[f"target_{mean}"])
+
+
+@pytest.mark.parametrize("shape", [(16, 3, 32, 32), (64, 4, 32, 32), (5, 3, 64, 64), (3, 1, 7, 9), (1, 4, 32, 32)])
+@pytest.mark.parametrize("sched", ["linear", "cosine"])
+def test_k1_vs_oracle_bit_exact(shape, sched):
+    torch.manual_seed(0)
+    d = gd.create_gaussian_diffusion(noise_schedule=sched, mean_type="velocity")
+    tb = odiff.tables(odiff.named_beta_schedule(sched, 1000))
+    x0 = torch.randn(*shape, device=DEV).clamp(-1, 1)
+    eps = torch.randn_like(x0)
+    t = torch.randint(0, 1000, (shape[0],), device=DEV)
+    t[0] = 999
+    xt = d.q_sample(x0, t, eps)
+    tg = d.compute_target(x0, eps, t)
+    assert np.array_equal(xt.cpu().numpy(), odiff.q_sample(tb, x0.cpu().numpy(), t.cpu().numpy(), eps.cpu().numpy()))
+    assert np.array_equal(tg.cpu().numpy(), odiff.target(tb, "VELOCITY", x0.cpu().numpy(), t.cpu().numpy(), eps.cpu().numpy()))
+
+
+def test_k1_empty_batch():
+    d = gd.create_gaussian_diffusion()
+    x0 = torch.zeros(0, 3, 8, 8, device=DEV)
+    assert d.q_sample(x0, torch.zeros(0, dtype=torch.long, device=DEV), x0).shape == (0, 3, 8, 8)
+
+
+@pytest.mark.parametrize("mean,wt", [("EPSILON", "lambda"), ("START_X", "lambda"), ("VELOCITY", "min_snr_5"),
+                                     ("PREVIOUS_X", "constant"), ("EPSILON", "min_snr_5")])
+def test_k2_matches_reference_golden(mean, wt):
+    g = np.load(os.path.join(G, "diffusion_golden.npz"))
+    d = gd.create_gaussian_diffusion(noise_schedule="linear", mean_type=mean.lower(), weight_type=wt)
+    x0, eps, t = (torch.from_numpy(g[k]).to(DEV) for k in ("x0", "eps", "t"))
+    out = torch.from_numpy(g["model_out"]).to(DEV).requires_grad_(True)
+    terms = d.training_losses(lambda x, ts, **k: out, x0, None, t=t, noise=eps)
+    terms["loss"].mean().backward()   # what trainer.py:107-108 does
+    np.testing.assert_allclose(terms["mse"].detach().cpu().numpy(), g[f"mse_{mean}_{wt}"], rtol=1e-5)
+    np.testing.assert_allclose(out.grad.cpu().numpy(), g[f"grad_{mean}_{wt}"], rtol=1e-5, atol=1e-9)
+    assert terms["loss"].dtype == torch.float32 and terms["loss"].shape == (6,)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 8e-3), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("chw", [(4, 32, 32), (3, 32, 32), (3, 5, 7)])
+def test_k2_vs_oracle_with_sample_weights(dtype, tol, chw):
+    torch.manual_seed(1)
+    N = 32
+    d = gd.create_gaussian_diffusion(noise_schedule="cosine", mean_type="epsilon", weight_type="lambda")
+    tb = odiff.tables(odiff.named_beta_schedule("cosine", 1000))
+    x0 = torch.randn(N, *chw, device=DEV)
+    eps = torch.randn_like(x0)
+    t = torch.randint(0, 1000, (N,), device=DEV)
+    out = torch.randn_like(x0).to(dtype).requires_grad_(True)
+    w = torch.rand(N, device=DEV) + 0.5
+    terms = d.training_losses(lambda x, ts, **k: out, x0, None, t=t, noise=eps)
+    (terms["loss"] * w).mean().backward()
+    mse, grad = odiff.mse_terms(tb, "EPSILON", "lambda", x0.cpu().numpy(), t.cpu().numpy(), eps.cpu().numpy(),
+                                out.detach().float().cpu().numpy())
+    np.testing.assert_allclose(terms["mse"].cpu().detach().numpy(), mse, rtol=1e-5)
+    ref_grad = grad * (w.cpu().numpy().astype(np.float64) / N).reshape(-1, 1, 1, 1)
+    got = out.grad.float().cpu().numpy()
+    assert out.grad.dtype == dtype
+    assert np.linalg.norm(got - ref_grad) / np.linalg.norm(ref_grad) < tol
+
+
+def test_k2_linearity_at_scale():
+    """Size-independent property at the benchmark's saturating size: the gradient is linear in the upstream weights,
+    and mse is invariant under a permutation of the batch."""
+    torch.manual_seed(2)
+    N = 4096
+    d = gd.create_gaussian_diffusion(noise_schedule="cosine")
+    x0 = torch.randn(N, 4, 32, 32, device=DEV); eps = torch.randn_like(x0)
+    t = torch.randint(0, 1000, (N,), device=DEV)
+    out = torch.randn_like(x0).requires_grad_(True)
+    mse = d.training_losses(lambda x, ts, **k: out, x0, None, t=t, noise=eps)["mse"]
+    g1, = torch.autograd.grad(mse.sum(), out, retain_graph=True)
+    g2, = torch.autograd.grad((2.0 * mse).sum(), out)
+    assert torch.equal(g2, 2.0 * g1)
+    perm = torch.randperm(N, device=DEV)
+    mse_p = d.training_losses(lambda x, ts, **k: out[perm], x0[perm], None, t=t[perm], noise=eps[perm])["mse"]
+    assert torch.equal(mse_p, mse[perm])
+
+
+def test_flow_matching_objective_vs_torch():
+    torch.manual_seed(3)
+    for path in ("linear", "cosine", "linear_logsnr"):
+        for mean in ("vector", "velocity", "epsilon"):
+            fm = gd.FlowMatching(args=gd.default_args(path_type=path, weight_type="lambda"),
+                                 model_mean_type=gd.ModelMeanType[mean.upper()])
+            x0 = torch.randn(8, 3, 16, 16, device=DEV); eps = torch.randn_like(x0)
+            t = torch.rand(8, device=DEV) * 0.98 + 0.01
+            out = torch.randn_like(x0).requires_grad_(True)
+            terms = fm.training_losses(lambda x, ts, **k: out, x0, None, t=t, noise=eps)
+            a, s, da, ds = fm.interpolant(t)
+            e = lambda v: v.view(-1, 1, 1, 1)
+            tgt = {"vector": e(da) * x0 + e(ds) * eps, "velocity": e(a) * eps - e(s) * x0, "epsilon": eps}[mean]
+            w = gd.compute_mse_loss_weight(fm.model_mean_type, "lambda", t, a, s)
+            ref = w * ((tgt - out) ** 2).mean(dim=(1, 2, 3))
+            np.testing.assert_allclose(terms["mse"].detach().cpu().numpy(), ref.detach().cpu().numpy(), rtol=2e-5)
+            xt = fm.q_sample(x0, eps, t)
+            assert torch.equal(xt, e(a) * x0 + e(s) * eps)
+
+
+def test_align_loss_kernel_vs_torch():
+    torch.manual_seed(4)
+    zs = (torch.randn(4, 64, 48, device=DEV)).bfloat16().requires_grad_(True)
+    feat = torch.randn(4, 64, 48, device=DEV)
+    loss = gd.compute_align_loss(feat, zs, "mse")
+    (loss * 0.5).backward()
+    z2 = zs.detach().float().requires_grad_(True)
+    ref = torch.nn.functional.mse_loss(z2, feat)
+    (ref * 0.5).backward()
+    assert abs(loss.item() - ref.item()) / ref.item() < 1e-5
+    assert ((zs.grad.float() - z2.grad).norm() / z2.grad.norm()).item() < 5e-3
+    with pytest.raises(ValueError):
+        gd.compute_align_loss(feat, zs, "nope")

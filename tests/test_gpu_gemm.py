@@ -1,0 +1,128 @@
+"""GPU tier: the tcgen05 GEMM through the C ABI vs an fp32 torch reference on the same bf16-rounded operands:
+every operand layout (forward / dgrad / wgrad), every tile width, ragged shapes, every fused epilogue, split-K."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import relerr, run_gemm
+from vaw_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("shape", [(256, 384, 128), (512, 1152, 1152), (200, 136, 72), (64, 2304, 384), (16, 1152, 4096),
+                                   (1152, 16, 2048)])
+@pytest.mark.parametrize("tile_n", [128, 192, 256])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_layouts_and_tiles(shape, tile_n, a_mn, b_mn, cta_group):
+    M, N, K = shape
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("MN-major operands need the MN extent to be a multiple of 8")
+    torch.manual_seed(0)
+    A = torch.randn(M, K, device=DEV).bfloat16(); B = torch.randn(N, K, device=DEV).bfloat16()
+    ref = A.float() @ B.float().t()
+    out = torch.full((M, N), float("nan"), device=DEV)
+    run_gemm(A.t().contiguous() if a_mn else A, B.t().contiguous() if b_mn else B, a_mn, b_mn, M, N, K, L.EPI_F32,
+             out=out, tile_n=tile_n, cta_group=cta_group)
+    assert relerr(out, ref) < 1e-5
+
+
+def test_full_size_block_gemms_linearity():
+    """At the benchmark's full size (M = 64*256 tokens, DiT-XL widths): GEMM(A1 + A2) == GEMM(A1) + GEMM(A2) with the
+    fp32 accumulate epilogue, and the result equals torch within bf16-input rounding."""
+    torch.manual_seed(1)
+    M, N, K = 16384, 4608, 1152
+    A1 = torch.randn(M, K, device=DEV).bfloat16(); W = (torch.randn(N, K, device=DEV) * 0.03).bfloat16()
+    out = torch.zeros(M, N, device=DEV)
+    run_gemm(A1, W, 0, 0, M, N, K, L.EPI_F32, out=out)
+    run_gemm(A1, W, 0, 0, M, N, K, L.EPI_F32, out=out, accumulate=1)
+    ref = A1.float() @ W.float().t()
+    assert relerr(out, 2 * ref) < 1e-5
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_epilogues(cta_group):
+    import functools
+    global run_gemm
+    from gpu_util import run_gemm as _rg
+    run_gemm = functools.partial(_rg, cta_group=cta_group)
+    try:
+        _epilogues_body()
+    finally:
+        run_gemm = _rg
+
+
+def _epilogues_body():
+    torch.manual_seed(2)
+    M, N, K, rps = 1024, 1152, 384, 256
+    A = torch.randn(M, K, device=DEV).bfloat16(); B = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    acc = A.float() @ B.float().t() + bias
+    pre = acc.bfloat16().float()
+    o = torch.empty(M, N, device=DEV, dtype=torch.bfloat16); o2 = torch.empty_like(o)
+    run_gemm(A, B, 0, 0, M, N, K, L.EPI_BF16, out=o, bias=bias)
+    assert torch.equal(o, acc.bfloat16()) or relerr(o, acc) < 3e-3
+    for epi, fn in ((L.EPI_GELU_TANH, lambda x: F.gelu(x, approximate="tanh")), (L.EPI_GELU_ERF, F.gelu), (L.EPI_SILU, F.silu)):
+        run_gemm(A, B, 0, 0, M, N, K, epi, out=o, out2=o2, bias=bias)
+        assert relerr(o, acc) < 3e-3 and relerr(o2, fn(pre)) < 4e-3
+    resid = torch.randn(M, N, device=DEV); gate = torch.randn(M // rps, N, device=DEV); xo = torch.empty(M, N, device=DEV)
+    run_gemm(A, B, 0, 0, M, N, K, L.EPI_GATE_RES, out=o, out2=xo, bias=bias, resid=resid, gate=gate, rows_per_sample=rps)
+    assert relerr(xo, resid + gate.repeat_interleave(rps, 0) * pre) < 2e-3
+    run_gemm(A, B, 0, 0, M, N, K, L.EPI_RES, out2=xo, bias=bias, resid=resid)
+    assert relerr(xo, resid + pre) < 2e-3
+    pos = torch.randn(rps, N, device=DEV)
+    run_gemm(A, B, 0, 0, M, N, K, L.EPI_RES, out2=xo, bias=bias, resid=pos, resid_mod=rps)
+    assert relerr(xo, pos.repeat(M // rps, 1) + pre) < 2e-3
+    aux = torch.randn(M, N, device=DEV).bfloat16()
+    for epi, fn in ((L.EPI_DGELU_TANH, lambda x: F.gelu(x, approximate="tanh")), (L.EPI_DGELU_ERF, F.gelu), (L.EPI_DSILU, F.silu)):
+        h = aux.float().requires_grad_(True)
+        fn(h).sum().backward()
+        run_gemm(A, B, 0, 0, M, N, K, epi, out=o, aux=aux)
+        assert relerr(o, (acc - bias) * h.grad) < 4e-3
+
+
+def test_tail_split_wgrad_shapes():
+    """k_splits = -1: whole tiles for the full waves, the partial last wave split along K (wgrad of a DiT-XL block)."""
+    torch.manual_seed(4)
+    for (Mo, No, Kt) in [(3456, 1152, 4096), (1152, 1152, 4096), (4608, 1152, 2048), (1152, 4608, 2048)]:
+        A = torch.randn(Kt, Mo, device=DEV).bfloat16(); B = (torch.randn(Kt, No, device=DEV) * 0.05).bfloat16()
+        ref = A.float().t() @ B.float()
+        ws = torch.empty(148 * 128 * 256, device=DEV)
+        out = torch.full((Mo, No), 0.5, device=DEV)
+        run_gemm(A, B, 1, 1, Mo, No, Kt, L.EPI_F32, out=out, accumulate=1, k_splits=-1, split_ws=ws)
+        assert relerr(out, ref + 0.5) < 1e-5
+        for cg, bn in ((1, 192), (2, 256), (2, 192), (2, 128)):
+            o = torch.empty(Mo, No, device=DEV)
+            run_gemm(A, B, 1, 1, Mo, No, Kt, L.EPI_F32, out=o, k_splits=-1, split_ws=ws, cta_group=cg, tile_n=bn)
+            assert relerr(o, ref) < 1e-5, (cg, bn)
+        out2 = torch.empty(Mo, No, device=DEV)
+        run_gemm(A, B, 1, 1, Mo, No, Kt, L.EPI_F32, out=out2, k_splits=-1, split_ws=ws)
+        out3 = torch.empty(Mo, No, device=DEV)
+        run_gemm(A, B, 1, 1, Mo, No, Kt, L.EPI_F32, out=out3, k_splits=-1, split_ws=ws)
+        assert torch.equal(out2, out3) and relerr(out2, ref) < 1e-5
+
+
+@pytest.mark.parametrize("splits", [2, 7, 24])
+def test_split_k_deterministic_and_correct(splits):
+    torch.manual_seed(3)
+    M, N, K = 64, 1152, 193536 // 8
+    A = torch.randn(M, K, device=DEV).bfloat16(); B = (torch.randn(K, N, device=DEV) * 0.02).bfloat16()
+    ref = A.float() @ B.float()
+    ws = torch.empty(splits * 128 * 6 * 192, device=DEV)
+    bias = torch.randn(N, device=DEV)
+    out = torch.ones(M, N, device=DEV)
+    run_gemm(A, B, 0, 1, M, N, K, L.EPI_F32, out=out, bias=bias, accumulate=1, k_splits=splits, split_ws=ws)
+    assert relerr(out, ref + bias + 1) < 3e-5  # K = 24192 fp32 accumulation order
+    out2 = torch.ones(M, N, device=DEV)
+    run_gemm(A, B, 0, 1, M, N, K, L.EPI_F32, out=out2, bias=bias, accumulate=1, k_splits=splits, split_ws=ws)
+    assert torch.equal(out, out2)
+
+
+def test_rejects_bad_arguments():
+    A = torch.zeros(128, 64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(L.VawError):
+        run_gemm(A, A, 0, 0, 128, 100, 64, L.EPI_F32, out=torch.zeros(128, 100, device=DEV))  # N % 8
+    with pytest.raises(L.VawError):
+        run_gemm(A, A, 0, 0, 128, 128, 64, L.EPI_GATE_RES, out=A)  # missing out2/resid/gate

@@ -138,28 +138,30 @@ __device__ __forceinline__ void mma_a_regs_b_nk(float (&s)[NTILES][4], const uin
 }
 
 // ---------------------------------------------------------------------------------------------------
-// forward: grid (ceil(T/64), H, B), 128 threads; each warp owns 16 query rows
+// forward: grid (ceil(T/128), H, B), 256 threads; each warp owns 16 query rows, 8 warps share one K/V copy
 // ---------------------------------------------------------------------------------------------------
+constexpr int kFwdBQ = 128;  // query rows per CTA
+
 template <int HD>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256, 2)
 attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __restrict__ lse2, int T, int H,
                 float scale_log2e) {
   using G = Geo<HD>;
   constexpr int SROW = G::SROW;
   const int D = H * HD;
-  const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * kFwdBQ, h = blockIdx.y, b = blockIdx.z;
   const int Tpad = (T + 63) / 64 * 64;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
-  bf16* sK = sQ + 64 * SROW;
+  bf16* sK = sQ + kFwdBQ * SROW;
   bf16* sV = sK + Tpad * SROW;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   const bf16* gq = qkv + ((long long)b * T) * 3 * D + h * HD;
-  const int q_valid = min(64, T - q0);
-  load_head_rows<HD>(sQ, gq + (long long)q0 * 3 * D, 3LL * D, q_valid, 64, tid, 128);
-  load_head_rows<HD>(sK, gq + D, 3LL * D, T, Tpad, tid, 128);
-  load_head_rows<HD>(sV, gq + 2 * D, 3LL * D, T, Tpad, tid, 128);
+  const int q_valid = min(kFwdBQ, T - q0);
+  load_head_rows<HD>(sQ, gq + (long long)q0 * 3 * D, 3LL * D, q_valid, kFwdBQ, tid, 256);
+  load_head_rows<HD>(sK, gq + D, 3LL * D, T, Tpad, tid, 256);
+  load_head_rows<HD>(sV, gq + 2 * D, 3LL * D, T, Tpad, tid, 256);
   cp_async_wait_all();
   __syncthreads();
 
@@ -392,7 +394,7 @@ template <int HD>
 int launch_fwd(const bf16* qkv, bf16* o, float* lse2, int B, int T, int H, cudaStream_t stream) {
   using G = Geo<HD>;
   const int Tpad = (T + 63) / 64 * 64;
-  const int smem = (64 + 2 * Tpad) * G::SROW * 2;
+  const int smem = (kFwdBQ + 2 * Tpad) * G::SROW * 2;
   VAW_CHECK_ARG(smem <= 227 * 1024, "vaw_attn_fwd: T=%d too long for the smem-resident K/V design", T);
   static bool configured = false;
   if (!configured) {
@@ -400,8 +402,8 @@ int launch_fwd(const bf16* qkv, bf16* o, float* lse2, int B, int T, int H, cudaS
     configured = true;
   }
   const float scale = 1.0f / sqrtf((float)HD);
-  dim3 grid((T + 63) / 64, H, B);
-  attn_fwd_kernel<HD><<<grid, 128, smem, stream>>>(qkv, o, lse2, T, H, scale * 1.4426950408889634f);
+  dim3 grid((T + kFwdBQ - 1) / kFwdBQ, H, B);
+  attn_fwd_kernel<HD><<<grid, 256, smem, stream>>>(qkv, o, lse2, T, H, scale * 1.4426950408889634f);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }

@@ -242,18 +242,30 @@ finish_group_kernel(const float* __restrict__ part, int which, int groups, int c
   float* o = out + (long long)g * ld_out + col;
   *o = accumulate ? *o + s : s;
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 finish_all_kernel(const float* __restrict__ part, int which, int groups, int chunks, int D,
                   const float* __restrict__ w, long long ld_w, float* __restrict__ out, int accumulate) {
-  const int col = blockIdx.x * 256 + threadIdx.x;
-  if (col >= D) return;
+  // block = 32 columns x 32 group-lanes; each group-lane folds groups gy, gy+32, ... in order, then lane 0 folds
+  // the 32 partials in order: fixed summation tree -> deterministic
+  __shared__ float red[32][33];
+  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
   float tot = 0.f;
-  for (int g = 0; g < groups; ++g) {
-    float s = 0.f;
-    for (int c = 0; c < chunks; ++c) s += part[(((long long)g * chunks + c) * 2 + which) * D + col];
-    tot += w ? w[(long long)g * ld_w + col] * s : s;
+  if (col < D) {
+    for (int g = gy; g < groups; g += 32) {
+      float s = 0.f;
+      for (int c = 0; c < chunks; ++c) s += part[(((long long)g * chunks + c) * 2 + which) * D + col];
+      tot += w ? w[(long long)g * ld_w + col] * s : s;
+    }
   }
-  out[col] = accumulate ? out[col] + tot : tot;
+  red[gy][cx] = tot;
+  __syncthreads();
+  if (gy == 0 && col < D) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += red[i][cx];
+    out[col] = accumulate ? out[col] + s : s;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -384,7 +396,7 @@ extern "C" int vaw_finish_all(const float* part, int which, int groups, int chun
                               long long ld_w, float* out, int accumulate, cudaStream_t stream) {
   VAW_CHECK_ARG(part && out && (which == 0 || which == 1) && groups > 0 && chunks > 0 && D > 0,
                 "vaw_finish_all: bad arguments");
-  finish_all_kernel<<<(D + 255) / 256, 256, 0, stream>>>(part, which, groups, chunks, D, w, ld_w, out, accumulate);
+  finish_all_kernel<<<(D + 31) / 32, 1024, 0, stream>>>(part, which, groups, chunks, D, w, ld_w, out, accumulate);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }

@@ -97,9 +97,10 @@ struct Carver {
 };
 
 int ln_chunks(const vaw_dit_cfg& c) {
-  int ch = (2 * vaw_num_sms() + c.B - 1) / c.B;
+  // (chunks x B) CTAs of the LN / gate backward kernels; 2 CTAs are resident per SM: stay within one wave
+  int ch = (2 * vaw_num_sms()) / c.B;
   if (ch < 1) ch = 1;
-  while (ch > 1 && (c.T + ch - 1) / ch < 8) --ch;
+  while (ch > 1 && (c.T + ch - 1) / ch < 16) --ch;
   return ch;
 }
 int colsum_rows(int M, int N) {
@@ -164,7 +165,7 @@ void carve(const vaw_dit_cfg& c, void* base, Ws& w) {
   w.dmod_final_b = k.take<bf16>(B * 2 * D);
   w.dc_b = k.take<bf16>(B * D);
   w.dth = k.take<bf16>(B * D);
-  w.split_elems = 4LL << 20;
+  w.split_elems = (long long)vaw_num_sms() * 128 * 256;  // one 128x256 fp32 slab per SM
   w.split_ws = k.take<float>(w.split_elems);
   w.bytes = k.cur;
 }
@@ -199,16 +200,12 @@ struct G {  // small GEMM call builder
   G& gate(const float* g, long long ldg, int rps) { a.gate = g; a.ldg = ldg; a.rows_per_sample = rps; return *this; }
   G& aux(const void* x) { a.aux = x; return *this; }
   G& acc(int f) { a.accumulate = f; return *this; }
-  // skinny GEMMs (few output tiles, long K): split the K loop so that every SM gets work
+  // split-K policy ("tail split"): whole tiles for the full waves, the partial last wave (or, for skinny GEMMs, every
+  // tile) split along K so that all SMs stay busy; partials are folded in fixed order
   G& autosplit(float* ws, long long ws_elems) {
-    const int bn = a.N % 192 == 0 ? 192 : (a.N % 256 == 0 ? 256 : (a.N % 128 == 0 ? 128 : (a.N > 128 ? 192 : 128)));
-    const long long tiles = (long long)((a.M + 127) / 128) * ((a.N + bn - 1) / bn);
-    const int num_kb = (a.K + 63) / 64;
-    long long sp = vaw_num_sms() / tiles;
-    if (sp > num_kb / 4) sp = num_kb / 4;  // keep at least 4 k-blocks per split
-    const long long per = (long long)a.M * (a.ldo ? a.ldo : a.N);
-    if (sp * per > ws_elems) sp = ws_elems / per;
-    if (sp > 1) { a.k_splits = (int)sp; a.split_ws = ws; }
+    a.split_ws = ws;
+    a.split_ws_elems = ws_elems;
+    a.k_splits = -1;
     return *this;
   }
   int run(cudaStream_t s) { return vaw_gemm_bf16(&a, s); }
@@ -360,13 +357,16 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
       bf16* dz2 = w.dz;
       bf16* dz1 = w.dz + (long long)M * pd;
       TRY(vaw_colsum_bf16(dzs, zd, M, zd, w.cpart, colsum_rows(M, zd), Gd + L.off[P_PR4_B], acc, s));
-      TRY(G(dzs, zd, 1, w.z2, pd, 1, zd, pd, M, VAW_EPI_F32).out(Gd + L.off[P_PR4_W]).acc(acc).run(s));
+      TRY(G(dzs, zd, 1, w.z2, pd, 1, zd, pd, M, VAW_EPI_F32).out(Gd + L.off[P_PR4_W]).acc(acc)
+              .autosplit(w.split_ws, w.split_elems).run(s));
       TRY(G(dzs, zd, 0, Pb + L.off[P_PR4_W], pd, 1, M, pd, zd, VAW_EPI_DSILU).out(dz2).aux(w.z2_pre).run(s));
       TRY(vaw_colsum_bf16(dz2, pd, M, pd, w.cpart, colsum_rows(M, pd), Gd + L.off[P_PR2_B], acc, s));
-      TRY(G(dz2, pd, 1, w.z1, pd, 1, pd, pd, M, VAW_EPI_F32).out(Gd + L.off[P_PR2_W]).acc(acc).run(s));
+      TRY(G(dz2, pd, 1, w.z1, pd, 1, pd, pd, M, VAW_EPI_F32).out(Gd + L.off[P_PR2_W]).acc(acc)
+              .autosplit(w.split_ws, w.split_elems).run(s));
       TRY(G(dz2, pd, 0, Pb + L.off[P_PR2_W], pd, 1, M, pd, pd, VAW_EPI_DSILU).out(dz1).aux(w.z1_pre).run(s));
       TRY(vaw_colsum_bf16(dz1, pd, M, pd, w.cpart, colsum_rows(M, pd), Gd + L.off[P_PR0_B], acc, s));
-      TRY(G(dz1, pd, 1, w.xa, D, 1, pd, D, M, VAW_EPI_F32).out(Gd + L.off[P_PR0_W]).acc(acc).run(s));
+      TRY(G(dz1, pd, 1, w.xa, D, 1, pd, D, M, VAW_EPI_F32).out(Gd + L.off[P_PR0_W]).acc(acc)
+              .autosplit(w.split_ws, w.split_elems).run(s));
       TRY(G(dz1, pd, 0, Pb + L.off[P_PR0_W], D, 1, M, D, pd, VAW_EPI_BF16).out(w.dxa).run(s));
       TRY(vaw_add_bf16_into_f32(w.dxa, w.dx, (long long)M * D, s));
     }
@@ -374,10 +374,12 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
     TRY(vaw_gate_bwd(w.dx, b.y_mlp, mod + 5 * D, ldm, w.dy, w.part, T, B, ch, M, D, s));
     TRY(vaw_finish_group(w.part, 1, B, ch, D, dmod + 5 * D, ldm, 0, s));                          // d gate_mlp
     TRY(vaw_finish_all(w.part, 0, B, ch, D, mod + 5 * D, ldm, Gd + L.off[pb + B_FC2_B], acc, s));  // d fc2.bias
-    TRY(G(w.dy, D, 1, b.h_act, Hd, 1, D, Hd, M, VAW_EPI_F32).out(Gd + L.off[pb + B_FC2_W]).acc(acc).run(s));
+    TRY(G(w.dy, D, 1, b.h_act, Hd, 1, D, Hd, M, VAW_EPI_F32).out(Gd + L.off[pb + B_FC2_W]).acc(acc)
+            .autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dy, D, 0, Pb + L.off[pb + B_FC2_W], Hd, 1, M, Hd, D, VAW_EPI_DGELU_TANH).out(w.dh).aux(b.h_pre).run(s));
     TRY(vaw_colsum_bf16(w.dh, Hd, M, Hd, w.cpart, colsum_rows(M, Hd), Gd + L.off[pb + B_FC1_B], acc, s));
-    TRY(G(w.dh, Hd, 1, b.xn2, D, 1, Hd, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_FC1_W]).acc(acc).run(s));
+    TRY(G(w.dh, Hd, 1, b.xn2, D, 1, Hd, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_FC1_W]).acc(acc)
+            .autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dh, Hd, 0, Pb + L.off[pb + B_FC1_W], D, 1, M, D, Hd, VAW_EPI_BF16).out(w.dxn).run(s));
     TRY(vaw_ln_bwd(w.dxn, w.x[2 * i + 1], b.mean2, b.rstd2, mod + 4 * D, ldm, nullptr, w.dx, 1, w.part, T, B, ch, M, D, s));
     TRY(vaw_finish_group(w.part, 0, B, ch, D, dmod + 3 * D, ldm, 0, s));  // d shift_mlp
@@ -386,11 +388,13 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
     TRY(vaw_gate_bwd(w.dx, b.y_attn, mod + 2 * D, ldm, w.dy, w.part, T, B, ch, M, D, s));
     TRY(vaw_finish_group(w.part, 1, B, ch, D, dmod + 2 * D, ldm, 0, s));                            // d gate_msa
     TRY(vaw_finish_all(w.part, 0, B, ch, D, mod + 2 * D, ldm, Gd + L.off[pb + B_PROJ_B], acc, s));  // d proj.bias
-    TRY(G(w.dy, D, 1, b.attn_o, D, 1, D, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_PROJ_W]).acc(acc).run(s));
+    TRY(G(w.dy, D, 1, b.attn_o, D, 1, D, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_PROJ_W]).acc(acc)
+            .autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dy, D, 0, Pb + L.off[pb + B_PROJ_W], D, 1, M, D, D, VAW_EPI_BF16).out(w.d_o).run(s));
     TRY(vaw_attn_bwd(b.qkv, b.attn_o, w.d_o, b.lse, w.dqkv, B, T, c.H, hd, s));
     TRY(vaw_colsum_bf16(w.dqkv, 3LL * D, M, 3 * D, w.cpart, colsum_rows(M, 3 * D), Gd + L.off[pb + B_QKV_B], acc, s));
-    TRY(G(w.dqkv, 3LL * D, 1, b.xn1, D, 1, 3 * D, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_QKV_W]).acc(acc).run(s));
+    TRY(G(w.dqkv, 3LL * D, 1, b.xn1, D, 1, 3 * D, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_QKV_W]).acc(acc)
+            .autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dqkv, 3LL * D, 0, Pb + L.off[pb + B_QKV_W], D, 1, M, D, 3 * D, VAW_EPI_BF16).out(w.dxn).run(s));
     TRY(vaw_ln_bwd(w.dxn, w.x[2 * i], b.mean1, b.rstd1, mod + D, ldm, nullptr, w.dx, 1, w.part, T, B, ch, M, D, s));
     TRY(vaw_finish_group(w.part, 0, B, ch, D, dmod, ldm, 0, s));      // d shift_msa

@@ -9,20 +9,27 @@
 //   dgrad    dX = dY W            A = dY [M,Nout] K-major    B = W  [Nout,Kin] used as MN-major (no transposed copy)
 //   wgrad    dW = dY^T X          A = dY [tokens,Nout] MN-major,  B = X [tokens,Kin] MN-major
 //
-// Kernel shape (one persistent CTA per SM, 192 threads):
-//   warp 0      TMA producer   (cp.async.bulk.tensor -> STAGES x {A 128x64, B BNx64} ring, mbarrier full/empty)
-//   warp 1      MMA issuer     (one lane issues tcgen05.mma 128xBNx16, commits to the ring / to the epilogue)
-//   warps 2-5   epilogue       (tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global)
+// Kernel shape (persistent, 320 threads per CTA):
+//   warp 0      TMA producer   (cp.async.bulk.tensor -> STAGES x {A, B} ring, mbarrier full/empty)
+//   warp 1      MMA issuer     (one lane issues tcgen05.mma, commits to the ring / to the epilogue)
+//   warps 2-9   epilogue       (tcgen05.ld -> registers -> smem transpose -> fused epilogue, coalesced global I/O)
 // Two accumulator stages in TMEM (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// PAIR = true: two CTAs of one cluster (an SM pair) work on a 256 x BN tile with tcgen05.mma.cta_group::2:
+// each CTA stages its own 128 rows of A and HALF of the B tile, the leader CTA issues the MMAs for both, and the
+// accumulator rows are split over the two CTAs' TMEM.  Per SM this halves the B traffic through shared memory and
+// L2, which is what bounds the single-CTA kernel (128x256x16 per 128 cycles needs 96 B/cycle of operand reads plus
+// the same again of TMA writes against a 128 B/cycle shared-memory port).
 #include "vaw_common.cuh"
 #include "vaw_internal.h"
+#include <stdlib.h>
 
 namespace {
 
-constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
-constexpr int kABytes = BM * BK * 2;  // 16 KB per stage
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kABytes = 128 * BK * 2;          // 16 KB per stage per CTA
 
 // epilogue selectors (mirrored in include/vaw_b200.h)
 enum : int {
@@ -53,15 +60,17 @@ struct EpiParams {
   int accumulate;
   int M, N, K;
   int a_mn, b_mn;   // operand majorness: 0 = K-major, 1 = MN-major
-  int k_splits;     // > 1: split-K; work item = (tile, split); raw fp32 partials go to out + split * split_stride
-  int kb_per_split;
-  long long split_stride;
+  // work decomposition (see decode_work): full tiles, then the remaining tiles split along K
+  int num_work, full_tiles, tail_splits, kb_per_split;
+  float* split_ws;
+  int dbg;  // debug knobs (env VAW_DBG): 1 = ring of 2 stages, 2 = skip MMA issue, 4 = skip TMA issue
 };
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's leader CTA
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -71,6 +80,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -97,41 +115,89 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
 
+template <bool PAIR>
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
+  if constexpr (!PAIR) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    // data lands in this CTA's shared memory; the transaction bytes are credited to the leader CTA's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+template <bool PAIR>
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if constexpr (!PAIR) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
+template <bool PAIR>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  if constexpr (!PAIR)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// MMA completion -> mbarrier.  PAIR: the arrive is multicast to the barrier at this offset in both CTAs of the pair.
+template <bool PAIR>
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  if constexpr (!PAIR) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+  }
 }
+template <bool PAIR>
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (!PAIR) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -161,95 +227,85 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int mn_major) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// fused epilogue on one 32-column chunk of one row (also reused by the tail-split fix-up kernel)
+// fused epilogue on 4 consecutive columns of one row.  The kernel transposes each 32x32 accumulator chunk through
+// shared memory first, so a warp touches 4 rows x 128 contiguous bytes per instruction: every global load / store of
+// the epilogue (residual, gate, saved pre-activation, outputs) is fully coalesced.
 // ---------------------------------------------------------------------------------------------------
+struct EpiPre {  // global operands of the epilogue, fetched for a whole chunk before any dependent math / store
+  float4 r;      // residual (RES / GATE_RES) or the previous output (F32 accumulate)
+  float4 g;      // gate (GATE_RES)
+  uint2 a;       // saved pre-activation (D-activation epilogues)
+};
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int row, int col0, const uint32_t (&acc)[32],
-                                               long long slab = 0) {
-  if (row >= p.M) return;
-  const long long ro = (long long)row * p.ldo;
-  const long long rr = (long long)(p.resid_mod > 0 ? row % p.resid_mod : row) * p.ldo;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {  // 4 groups of 8 columns
-    const int c = col0 + g * 8;
-    if (c >= p.N) break;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
-    if (p.bias) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c) + 1);
-      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+__device__ __forceinline__ void epilogue_load(const EpiParams& p, int row, int col, long long gate_off, EpiPre& pre) {
+  if (row >= p.M || col >= p.N) return;
+  const long long o = (long long)row * p.ldo + col;
+  if constexpr (EPI == EPI_F32) {
+    if (p.accumulate) pre.r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + o);
+  }
+  if constexpr (EPI == EPI_RES || EPI == EPI_GATE_RES) {
+    const long long rr = (long long)(p.resid_mod > 0 ? row % p.resid_mod : row) * p.ldo + col;
+    pre.r = *reinterpret_cast<const float4*>(p.resid + rr);
+  }
+  if constexpr (EPI == EPI_GATE_RES) pre.g = __ldg(reinterpret_cast<const float4*>(p.gate + gate_off + col));
+  if constexpr (EPI == EPI_DGELU_TANH || EPI == EPI_DGELU_ERF || EPI == EPI_DSILU)
+    pre.a = __ldg(reinterpret_cast<const uint2*>(p.aux + o));
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_vec4(const EpiParams& p, int row, int col, float4 v, const EpiPre& pre) {
+  if (row >= p.M || col >= p.N) return;
+  const long long o = (long long)row * p.ldo + col;
+  if (p.bias) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  }
+  if constexpr (EPI == EPI_F32) {
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
+    if (p.accumulate) {
+      const float4 d = pre.r;
+      v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
     }
-    if constexpr (EPI == EPI_F32) {
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + slab + ro + c);
-      if (p.accumulate) {
-        const float4 o0 = o[0], o1 = o[1];
-        v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
-        v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+    *dst = v;
+  } else if constexpr (EPI == EPI_RES) {
+    const float4 r = pre.r;
+    // the linear output is a bf16 tensor in the reference's autocast path: round before the residual add
+    const float2 y0 = unpack_bf16(pack_bf16(v.x, v.y)), y1 = unpack_bf16(pack_bf16(v.z, v.w));
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out2) + o) = make_float4(r.x + y0.x, r.y + y0.y, r.z + y1.x, r.w + y1.y);
+  } else {
+    if constexpr (EPI == EPI_DGELU_TANH || EPI == EPI_DGELU_ERF || EPI == EPI_DSILU) {
+      const float2 h0 = unpack_bf16(pre.a.x), h1 = unpack_bf16(pre.a.y);
+      if constexpr (EPI == EPI_DGELU_TANH) {
+        v.x *= gelu_tanh_grad_f(h0.x); v.y *= gelu_tanh_grad_f(h0.y); v.z *= gelu_tanh_grad_f(h1.x); v.w *= gelu_tanh_grad_f(h1.y);
+      } else if constexpr (EPI == EPI_DGELU_ERF) {
+        v.x *= gelu_erf_grad_f(h0.x); v.y *= gelu_erf_grad_f(h0.y); v.z *= gelu_erf_grad_f(h1.x); v.w *= gelu_erf_grad_f(h1.y);
+      } else {
+        v.x *= silu_grad_f(h0.x); v.y *= silu_grad_f(h0.y); v.z *= silu_grad_f(h1.x); v.w *= silu_grad_f(h1.y);
       }
-      o[0] = make_float4(v[0], v[1], v[2], v[3]);
-      o[1] = make_float4(v[4], v[5], v[6], v[7]);
-    } else if constexpr (EPI == EPI_RES) {
-      const float4* r = reinterpret_cast<const float4*>(p.resid + rr + c);
-      const float4 r0 = r[0], r1 = r[1];
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out2) + ro + c);
-      // the linear output is a bf16 tensor in the reference's autocast path: round before the residual add
-      float y[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-      o[0] = make_float4(r0.x + y[0], r0.y + y[1], r0.z + y[2], r0.w + y[3]);
-      o[1] = make_float4(r1.x + y[4], r1.y + y[5], r1.z + y[6], r1.w + y[7]);
-    } else {
-      // every other epilogue writes a bf16 primary output
-      if constexpr (EPI == EPI_DGELU_TANH || EPI == EPI_DGELU_ERF || EPI == EPI_DSILU) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.aux + ro + c));
-        const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
-        const float h[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if constexpr (EPI == EPI_DGELU_TANH) v[j] *= gelu_tanh_grad_f(h[j]);
-          else if constexpr (EPI == EPI_DGELU_ERF) v[j] *= gelu_erf_grad_f(h[j]);
-          else v[j] *= silu_grad_f(h[j]);
-        }
+    }
+    uint2 pk;
+    pk.x = pack_bf16(v.x, v.y);
+    pk.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + o) = pk;
+    if constexpr (EPI == EPI_GELU_TANH || EPI == EPI_GELU_ERF || EPI == EPI_SILU) {
+      // activation of the bf16-rounded pre-activation (what the next Linear sees in the reference)
+      const float2 h0 = unpack_bf16(pk.x), h1 = unpack_bf16(pk.y);
+      uint2 ak;
+      if constexpr (EPI == EPI_GELU_TANH) {
+        ak.x = pack_bf16(gelu_tanh_f(h0.x), gelu_tanh_f(h0.y)); ak.y = pack_bf16(gelu_tanh_f(h1.x), gelu_tanh_f(h1.y));
+      } else if constexpr (EPI == EPI_GELU_ERF) {
+        ak.x = pack_bf16(gelu_erf_f(h0.x), gelu_erf_f(h0.y)); ak.y = pack_bf16(gelu_erf_f(h1.x), gelu_erf_f(h1.y));
+      } else {
+        ak.x = pack_bf16(silu_f(h0.x), silu_f(h0.y)); ak.y = pack_bf16(silu_f(h1.x), silu_f(h1.y));
       }
-      uint4 pk;
-      pk.x = pack_bf16(v[0], v[1]);
-      pk.y = pack_bf16(v[2], v[3]);
-      pk.z = pack_bf16(v[4], v[5]);
-      pk.w = pack_bf16(v[6], v[7]);
-      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + ro + c) = pk;
-      if constexpr (EPI == EPI_GELU_TANH || EPI == EPI_GELU_ERF || EPI == EPI_SILU) {
-        // activation of the bf16-rounded pre-activation (what the next Linear sees in the reference)
-        const float2 q0 = unpack_bf16(pk.x), q1 = unpack_bf16(pk.y), q2 = unpack_bf16(pk.z), q3 = unpack_bf16(pk.w);
-        const float h[8] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y};
-        float a[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if constexpr (EPI == EPI_GELU_TANH) a[j] = gelu_tanh_f(h[j]);
-          else if constexpr (EPI == EPI_GELU_ERF) a[j] = gelu_erf_f(h[j]);
-          else a[j] = silu_f(h[j]);
-        }
-        uint4 ak;
-        ak.x = pack_bf16(a[0], a[1]);
-        ak.y = pack_bf16(a[2], a[3]);
-        ak.z = pack_bf16(a[4], a[5]);
-        ak.w = pack_bf16(a[6], a[7]);
-        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + ro + c) = ak;
-      }
-      if constexpr (EPI == EPI_GATE_RES) {
-        const float2 q0 = unpack_bf16(pk.x), q1 = unpack_bf16(pk.y), q2 = unpack_bf16(pk.z), q3 = unpack_bf16(pk.w);
-        const float y[8] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y};
-        const float* gp = p.gate + (long long)(row / p.rows_per_sample) * p.ldg + c;
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp) + 1);
-        const float4* r = reinterpret_cast<const float4*>(p.resid + rr + c);
-        const float4 r0 = r[0], r1 = r[1];
-        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out2) + ro + c);
-        o[0] = make_float4(fmaf(g0.x, y[0], r0.x), fmaf(g0.y, y[1], r0.y), fmaf(g0.z, y[2], r0.z), fmaf(g0.w, y[3], r0.w));
-        o[1] = make_float4(fmaf(g1.x, y[4], r1.x), fmaf(g1.y, y[5], r1.y), fmaf(g1.z, y[6], r1.z), fmaf(g1.w, y[7], r1.w));
-      }
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + o) = ak;
+    }
+    if constexpr (EPI == EPI_GATE_RES) {
+      const float2 y0 = unpack_bf16(pk.x), y1 = unpack_bf16(pk.y);
+      const float4 g = pre.g;
+      const float4 r = pre.r;
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out2) + o) =
+          make_float4(fmaf(g.x, y0.x, r.x), fmaf(g.y, y0.y, r.y), fmaf(g.z, y1.x, r.z), fmaf(g.w, y1.y, r.w));
     }
   }
 }
@@ -257,21 +313,59 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int row, int 
 // ---------------------------------------------------------------------------------------------------
 // the GEMM kernel
 // ---------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool PAIR>
 struct Cfg {
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kTileM = PAIR ? 256 : 128;
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;       // rows (K-major) / columns (MN-major) of B staged per CTA
+  static constexpr int kBBoxes = (kBRows + 63) / 64;      // MN-major B: 64-wide TMA boxes per stage
+  static constexpr int kBBytes = kBBoxes * 8192;          // smem reserved per stage for B (>= kBRows * 128)
+  static constexpr int kBBytesKMajor = kBRows * BK * 2;   // bytes a K-major B load actually transfers
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int kStagingBytes = kEpiWarps * 4096;  // one 32x32 fp32 transpose tile per epilogue warp
+  static constexpr int kBudget = 232448 - 1024 - 256 - kStagingBytes;
+  static constexpr int kStagesRaw = kBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + kStagingBytes + 1024 /*alignment slack*/;
 };
 
-template <int BN, int EPI>
+// One unit of work of the persistent loop.  The first `full_tiles` items are whole output tiles; the remaining
+// tiles (the partial last wave) are each split into `tail_splits` K-ranges whose raw fp32 partial accumulators go
+// to a scratch slab and are folded by splitk_fixup_kernel in fixed order (deterministic).
+struct Work {
+  int m0, n0, kb0, kb1, partial, slab;
+};
+template <int TM, int BN>
+__device__ __forceinline__ Work decode_work(int w, const EpiParams& p, int n_tiles, int num_kb_total) {
+  Work k;
+  int tile;
+  if (w < p.full_tiles) {
+    tile = w;
+    k.kb0 = 0;
+    k.kb1 = num_kb_total;
+    k.partial = 0;
+    k.slab = 0;
+  } else {
+    const int r = w - p.full_tiles;
+    tile = p.full_tiles + r / p.tail_splits;
+    const int sp = r % p.tail_splits;
+    k.kb0 = sp * p.kb_per_split;
+    k.kb1 = min(num_kb_total, k.kb0 + p.kb_per_split);
+    k.partial = 1;
+    k.slab = r;
+  }
+  k.m0 = (tile / n_tiles) * TM;
+  k.n0 = (tile % n_tiles) * BN;
+  return k;
+}
+
+template <int BN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const EpiParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
   constexpr int STAGES = C::kStages;
+  constexpr int TM = C::kTileM;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -285,82 +379,90 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;      // 0 = leader of the CTA pair
+  const int unit = PAIR ? (blockIdx.x >> 1) : blockIdx.x;   // persistent work is dealt to CTAs / CTA pairs
+  const int num_units = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
-  const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
   const int num_kb_total = (p.K + BK - 1) / BK;
-  const int num_work = num_tiles * p.k_splits;  // work item w: tile = w % num_tiles, split = w / num_tiles
+  const int num_work = p.num_work;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
+      // one arrival: the (leader's) producer arrive.expect_tx.  In PAIR mode it expects the bytes of BOTH CTAs; the
+      // peer's TMA credits them to this barrier directly.  (A release-arrive from the peer after its TMA issue
+      // waited for those loads to land and serialised the ring to depth 1: 1 us per k-block, measured.)
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 4);
+      mbar_init(&tempty[s], PAIR ? 2 * kEpiWarps : kEpiWarps);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  if (warp == 1) tmem_alloc<PAIR>(tmem_slot, C::kTmemCols);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===================== TMA producer =====================
+      // ===================== TMA producer (every CTA stages its own rows of A and its share of B) ===============
       int stage = 0;
       uint32_t phase = 0;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-        const int tile = work % num_tiles, split = work / num_tiles;
-        const int m0 = (tile / n_tiles) * BM;
-        const int n0 = (tile % n_tiles) * BN;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
+      const int ring = (p.dbg & 1) ? 2 : STAGES;
+      const bool skip_tma = (p.dbg & 4) != 0;
+      const uint32_t bbytes = p.b_mn ? (uint32_t)C::kBBytes : (uint32_t)C::kBBytesKMajor;
+      for (int work = unit; work < num_work; work += num_units) {
+        const Work wk = decode_work<TM, BN>(work, p, n_tiles, num_kb_total);
+        const int am0 = wk.m0 + (int)rank * 128;
+        const int bn0 = wk.n0 + (int)rank * C::kBRows;
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
-          mbar_expect_tx(&full[stage], C::kStageBytes);
+          if (rank == 0) mbar_expect_tx(&full[stage], skip_tma ? 0u : (PAIR ? 2u : 1u) * (kABytes + bbytes));
           uint8_t* a_dst = sA + stage * kABytes;
           uint8_t* b_dst = sB + stage * C::kBBytes;
           const int k0 = kb * BK;
-          if (!p.a_mn) {
-            tma_load_2d(a_dst, &tmA, &full[stage], k0, m0);
+          if (skip_tma) {
+          } else if (!p.a_mn) {
+            tma_load_2d<PAIR>(a_dst, &tmA, &full[stage], k0, am0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmA, &full[stage], m0 + j * 64, k0);
+            for (int j = 0; j < 2; ++j) tma_load_2d<PAIR>(a_dst + j * 8192, &tmA, &full[stage], am0 + j * 64, k0);
           }
-          if (!p.b_mn) {
-            tma_load_2d(b_dst, &tmB, &full[stage], k0, n0);
+          if (skip_tma) {
+          } else if (!p.b_mn) {
+            tma_load_2d<PAIR>(b_dst, &tmB, &full[stage], k0, bn0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full[stage], n0 + j * 64, k0);
+            for (int j = 0; j < C::kBBoxes; ++j) tma_load_2d<PAIR>(b_dst + j * 8192, &tmB, &full[stage], bn0 + j * 64, k0);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == ring) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    if (lane == 0 && rank == 0) {
+      // ===================== MMA issuer (leader CTA only) =====================
       // instruction descriptor: D=f32, A=B=bf16, majorness bits, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
                              ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) |
-                             ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(TM >> 4) << 24);
       const uint32_t a_kstep = p.a_mn ? 2048u : 32u;  // bytes per UMMA_K=16 step
       const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-        const int split = work / num_tiles;
-        const int kb0 = split * p.kb_per_split;
-        const int num_kb = min(num_kb_total, kb0 + p.kb_per_split) - kb0;
+      const int ring = (p.dbg & 1) ? 2 : STAGES;
+      const bool skip_mma = (p.dbg & 2) != 0;
+      for (int work = unit; work < num_work; work += num_units) {
+        const Work wk = decode_work<TM, BN>(work, p, n_tiles, num_kb_total);
+        const int num_kb = wk.kb1 - wk.kb0;
         mbar_wait(&tempty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -373,50 +475,123 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ad = umma_desc(a_base + k * a_kstep, p.a_mn);
             const uint64_t bd = umma_desc(b_base + k * b_kstep, p.b_mn);
-            tc_mma_f16(d_tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            if (!skip_mma) tc_mma_f16<PAIR>(d_tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
           }
-          tc_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          tc_commit<PAIR>(&empty[stage]);  // frees the smem slot (in both CTAs) once these MMAs have read it
+          if (++stage == ring) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        tc_commit<PAIR>(&tfull[acc]);  // accumulator complete -> epilogue warps (of both CTAs)
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue warps (2..9) =====================
+    // two warps per TMEM lane quarter, each draining half of the tile's columns
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // 0: chunks [0, NCH/2), 1: chunks [NCH/2, NCH)
+    constexpr int NCH = BN / 32;
+    float4* stg = reinterpret_cast<float4*>(smem + STAGES * C::kStageBytes + 256) + (warp - 2) * 256;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-      const int tile = work % num_tiles, split = work / num_tiles;
-      const int m0 = (tile / n_tiles) * BM;
-      const int n0 = (tile % n_tiles) * BN;
-      const long long slab = (long long)split * p.split_stride;
+    for (int work = unit; work < num_work; work += num_units) {
+      const Work wk = decode_work<TM, BN>(work, p, n_tiles, num_kb_total);
+      const int row0 = wk.m0 + (int)rank * 128;  // first global row held by this CTA's TMEM lanes
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const int c_begin = half * (NCH / 2), c_end = c_begin + NCH / 2;
+      // after the transpose this lane owns rows {4i + lane/8} (i = 0..7) and column group lane%8 of every chunk
+      const int sub_r = lane >> 3, sub_c = lane & 7;
+      long long gate_off[8];
+      if constexpr (EPI == EPI_GATE_RES) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          gate_off[i] = (long long)((row0 + q * 32 + 4 * i + sub_r) / p.rows_per_sample) * p.ldg;
+      }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
+        // issue the chunk's global operand loads first: their latency overlaps the TMEM load and the transpose
+        EpiPre pre[8];
+        if (!wk.partial) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            epilogue_load<EPI>(p, row0 + q * 32 + 4 * i + sub_r, wk.n0 + c * 32 + sub_c * 4,
+                               EPI == EPI_GATE_RES ? gate_off[i] : 0, pre[i]);
+        }
         uint32_t v[32];
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, row, n0 + c * 32, v, slab);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + sub_r;
+          const float4 a4 = stg[r * 8 + (sub_c ^ (r & 7))];
+          const int lrow = q * 32 + r;
+          const int lcol = c * 32 + sub_c * 4;
+          if (!wk.partial) {
+            epilogue_vec4<EPI>(p, row0 + lrow, wk.n0 + lcol, a4, pre[i]);
+          } else {
+            *reinterpret_cast<float4*>(p.split_ws + ((long long)wk.slab * TM + (int)rank * 128 + lrow) * BN + lcol) = a4;
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (!PAIR || rank == 0) mbar_arrive(&tempty[acc]);
+        else mbar_arrive_remote(&tempty[acc], 0);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
   }
 
+  __syncwarp();  // reconverge the single-lane role warps before the block / cluster barrier
   tc_fence_before();
+  // Idle lanes / warps park in the hardware block barrier (bar.sync blocks without issuing).  The cluster barrier
+  // polls, so it is only entered once the whole CTA is done: waiting in it from the start stole issue slots from
+  // the single-lane TMA / MMA roles and serialised the pipeline (measured: 1 us per k-block).
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    tmem_dealloc<PAIR>(tmem_base, C::kTmemCols);
+  }
+}
+
+// Split-K fix-up (EPI_F32 only): one CTA per split tile sums its `splits` slabs in fixed order and applies
+// bias / accumulate:  out[r, c] = (accumulate ? out : 0) + bias[c] + sum_s slab[s][r, c]
+template <int TM, int BN>
+__global__ void __launch_bounds__(256)
+splitk_fixup_kernel(const float* __restrict__ ws, int first_tile, int splits, int n_tiles, float* __restrict__ out,
+                    const float* __restrict__ bias, int M, int N, long long ldo, int accumulate) {
+  const int tile = first_tile + blockIdx.x;
+  const int m0 = (tile / n_tiles) * TM, n0 = (tile % n_tiles) * BN;
+  const float* base = ws + (long long)blockIdx.x * splits * (TM * BN);
+  for (int i = threadIdx.x; i < TM * BN / 4; i += 256) {
+    const int r = i / (BN / 4), c = (i % (BN / 4)) * 4;
+    if (m0 + r >= M || n0 + c >= N) continue;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(base + (long long)s * (TM * BN) + r * BN + c);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    if (bias) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + n0 + c);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(out + (long long)(m0 + r) * ldo + n0 + c);
+    if (accumulate) {
+      const float4 d = *dst;
+      a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
+    }
+    *dst = a;
   }
 }
 
@@ -462,66 +637,71 @@ int make_tmap(CUtensorMap* map, const void* base, long long rows, long long cols
   return VAW_OK;
 }
 
-// split-K finish: out[r, c] = (accumulate ? out : 0) + bias[c] + sum_s ws[s][r, c]   (fixed order -> deterministic)
-__global__ void __launch_bounds__(256)
-splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long stride, float* __restrict__ out,
-                     const float* __restrict__ bias, int M, int N, long long ldo, int accumulate) {
-  const long long n4 = (long long)M * (N >> 2);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i / (N >> 2)), c = (int)(i % (N >> 2)) * 4;
-    const long long o = (long long)r * ldo + c;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < splits; ++s) {
-      const float4 v = *reinterpret_cast<const float4*>(ws + (long long)s * stride + o);
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-    }
-    if (bias) {
-      const float4 b = *reinterpret_cast<const float4*>(bias + c);
-      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-    }
-    float4* dst = reinterpret_cast<float4*>(out + o);
-    if (accumulate) {
-      const float4 d = *dst;
-      a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
-    }
-    *dst = a;
-  }
-}
-
-template <int BN, int EPI>
+template <int BN, int EPI, bool PAIR>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& p, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
   static bool configured = false;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, PAIR>;
   if (!configured) {
     VAW_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
-  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
-  int grid = m_tiles * n_tiles * (p.k_splits > 0 ? p.k_splits : 1);
   const int sms = vaw_num_sms();
-  if (grid > sms) grid = sms;
-  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
+  if constexpr (!PAIR) {
+    const int grid = p.num_work < sms ? p.num_work : sms;
+    kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
+  } else {
+    const int pairs = p.num_work < sms / 2 ? p.num_work : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VAW_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  }
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& p, cudaStream_t s) {
   switch (epi) {
-    case EPI_BF16: return launch_gemm<BN, EPI_BF16>(tmA, tmB, p, s);
-    case EPI_F32: return launch_gemm<BN, EPI_F32>(tmA, tmB, p, s);
-    case EPI_GELU_TANH: return launch_gemm<BN, EPI_GELU_TANH>(tmA, tmB, p, s);
-    case EPI_GELU_ERF: return launch_gemm<BN, EPI_GELU_ERF>(tmA, tmB, p, s);
-    case EPI_GATE_RES: return launch_gemm<BN, EPI_GATE_RES>(tmA, tmB, p, s);
-    case EPI_RES: return launch_gemm<BN, EPI_RES>(tmA, tmB, p, s);
-    case EPI_DGELU_TANH: return launch_gemm<BN, EPI_DGELU_TANH>(tmA, tmB, p, s);
-    case EPI_DGELU_ERF: return launch_gemm<BN, EPI_DGELU_ERF>(tmA, tmB, p, s);
-    case EPI_SILU: return launch_gemm<BN, EPI_SILU>(tmA, tmB, p, s);
-    case EPI_DSILU: return launch_gemm<BN, EPI_DSILU>(tmA, tmB, p, s);
+    case EPI_BF16: return launch_gemm<BN, EPI_BF16, PAIR>(tmA, tmB, p, s);
+    case EPI_F32: return launch_gemm<BN, EPI_F32, PAIR>(tmA, tmB, p, s);
+    case EPI_GELU_TANH: return launch_gemm<BN, EPI_GELU_TANH, PAIR>(tmA, tmB, p, s);
+    case EPI_GELU_ERF: return launch_gemm<BN, EPI_GELU_ERF, PAIR>(tmA, tmB, p, s);
+    case EPI_GATE_RES: return launch_gemm<BN, EPI_GATE_RES, PAIR>(tmA, tmB, p, s);
+    case EPI_RES: return launch_gemm<BN, EPI_RES, PAIR>(tmA, tmB, p, s);
+    case EPI_DGELU_TANH: return launch_gemm<BN, EPI_DGELU_TANH, PAIR>(tmA, tmB, p, s);
+    case EPI_DGELU_ERF: return launch_gemm<BN, EPI_DGELU_ERF, PAIR>(tmA, tmB, p, s);
+    case EPI_SILU: return launch_gemm<BN, EPI_SILU, PAIR>(tmA, tmB, p, s);
+    case EPI_DSILU: return launch_gemm<BN, EPI_DSILU, PAIR>(tmA, tmB, p, s);
   }
   vaw_set_error("vaw_gemm_bf16: unknown epilogue %d", epi);
   return VAW_ERR_INVALID;
+}
+
+int dispatch_tile(int bn, bool pair, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& p,
+                  cudaStream_t s) {
+  if (pair) {
+    switch (bn) {
+      case 128: return dispatch_epi<128, true>(epi, tmA, tmB, p, s);
+      case 192: return dispatch_epi<192, true>(epi, tmA, tmB, p, s);
+      default: return dispatch_epi<256, true>(epi, tmA, tmB, p, s);
+    }
+  }
+  switch (bn) {
+    case 128: return dispatch_epi<128, false>(epi, tmA, tmB, p, s);
+    case 192: return dispatch_epi<192, false>(epi, tmA, tmB, p, s);
+    default: return dispatch_epi<256, false>(epi, tmA, tmB, p, s);
+  }
 }
 
 }  // namespace
@@ -545,22 +725,55 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
   VAW_CHECK_ARG(epi != EPI_GATE_RES || (a->gate && a->rows_per_sample > 0), "vaw_gemm_bf16: missing gate");
   VAW_CHECK_ARG(!(epi == EPI_DGELU_TANH || epi == EPI_DGELU_ERF || epi == EPI_DSILU) || a->aux,
                 "vaw_gemm_bf16: missing aux");
+  VAW_CHECK_ARG(a->cta_group >= 0 && a->cta_group <= 2, "vaw_gemm_bf16: cta_group must be 0 (auto), 1 or 2");
 
+  // ---- tile selection -----------------------------------------------------------------------------------
+  // Explicit tile_n / cta_group are honoured.  Otherwise pick the (tile_n, cta_group) pair with the smallest
+  // modelled time: waves x (k-blocks x cost-per-k-block + per-tile overhead), with the per-k-block costs measured on
+  // B200 (profiles/r01_gemm_tile_costs.md): the main loop is bound by shared-memory traffic (TMA writes + UMMA
+  // operand reads), which is why an SM pair on a 256x256 tile (half the B traffic per SM) is the cheapest per FLOP.
+  bool pair = a->cta_group == 2;
   int bn = a->tile_n;
-  if (bn == 0) {
-    if (a->N % 192 == 0) bn = 192;
-    else if (a->N % 256 == 0) bn = 256;
+  if (bn == 0 && a->cta_group == 0) {
+    const int sms = vaw_num_sms();
+    const int nkb = (a->K + BK - 1) / BK;
+    const bool tail_ok = (a->k_splits == -1);
+    double best = 1e30;
+    const int cand_bn[4] = {192, 256, 128, 256};
+    const bool cand_pair[4] = {false, false, false, true};
+    const double cand_cost[4] = {0.43, 0.50, 0.355, 0.455};  // us per k-block per CTA (per CTA pair for the last)
+    for (int i = 0; i < 4; ++i) {
+      if (cand_pair[i] && a->M < 256) continue;
+      const int tm = cand_pair[i] ? 256 : 128;
+      const int units = cand_pair[i] ? sms / 2 : sms;
+      const long long tiles = (long long)((a->M + tm - 1) / tm) * ((a->N + cand_bn[i] - 1) / cand_bn[i]);
+      const long long fullw = tiles / units, rem = tiles % units;
+      double waves = (double)fullw;
+      if (rem) {
+        const long long sp = units / rem;
+        waves += (tail_ok && sp > 1) ? (1.0 / (double)(sp < nkb / 2 ? sp : (nkb / 2 > 0 ? nkb / 2 : 1)) + 0.15) : 1.0;
+      }
+      const double t = waves * (nkb * cand_cost[i] + 1.0);
+      if (t < best) { best = t; bn = cand_bn[i]; pair = cand_pair[i]; }
+    }
+  } else if (bn == 0) {
+    if (a->N % 192 == 0 && !pair) bn = 192;
+    else if (a->N % 256 == 0 || pair) bn = 256;
     else if (a->N % 128 == 0) bn = 128;
     else bn = (a->N > 128) ? 192 : 128;
+  } else if (a->cta_group == 0) {
+    pair = false;
   }
   VAW_CHECK_ARG(bn == 128 || bn == 192 || bn == 256, "vaw_gemm_bf16: tile_n must be 128, 192 or 256");
+  const int tile_m = pair ? 256 : 128;
+  const int b_rows = pair ? bn / 2 : bn;
 
   CUtensorMap tmA, tmB;
   int rc;
-  if (!a->a_mn) rc = make_tmap(&tmA, a->A, a->M, a->K, a->lda, BM);
+  if (!a->a_mn) rc = make_tmap(&tmA, a->A, a->M, a->K, a->lda, 128);
   else rc = make_tmap(&tmA, a->A, a->K, a->M, a->lda, BK);
   if (rc) return rc;
-  if (!a->b_mn) rc = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, bn);
+  if (!a->b_mn) rc = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, b_rows);
   else rc = make_tmap(&tmB, a->B, a->K, a->N, a->ldb, BK);
   if (rc) return rc;
 
@@ -581,40 +794,57 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
   p.K = a->K;
   p.a_mn = a->a_mn ? 1 : 0;
   p.b_mn = a->b_mn ? 1 : 0;
-  // split-K (EPI_F32 only): partial slabs in split_ws, then a fixed-order reduction that applies bias / accumulate
+
+  // ---- work decomposition -------------------------------------------------------------------------------
+  // k_splits > 1: every tile is split (skinny GEMMs).  k_splits == -1: "tail split" — whole tiles for the full
+  // waves, the partial last wave split along K so that all SMs stay busy (wgrad GEMMs, long K).
   const int num_kb = (a->K + BK - 1) / BK;
-  int splits = a->k_splits > 1 ? a->k_splits : 1;
-  if (splits > num_kb) splits = num_kb;
-  int kb_per = (num_kb + splits - 1) / splits;
-  splits = (num_kb + kb_per - 1) / kb_per;
-  p.k_splits = splits;
-  p.kb_per_split = kb_per;
-  p.split_stride = (long long)a->M * ldo;
-  if (splits > 1) {
+  const int m_tiles = (a->M + tile_m - 1) / tile_m, n_tiles = (a->N + bn - 1) / bn;
+  const int tiles = m_tiles * n_tiles;
+  const int G = pair ? vaw_num_sms() / 2 : vaw_num_sms();
+  int full = tiles, splits = 1, kb_per = num_kb;
+  if (a->k_splits != 0 && a->k_splits != 1) {
     VAW_CHECK_ARG(epi == EPI_F32 && a->split_ws, "vaw_gemm_bf16: split-K needs the F32 epilogue and split_ws");
-    p.out = a->split_ws;
-    p.bias = nullptr;
-    p.accumulate = 0;
-    int rc2;
-    switch (bn) {
-      case 128: rc2 = dispatch_epi<128>(epi, tmA, tmB, p, stream); break;
-      case 192: rc2 = dispatch_epi<192>(epi, tmA, tmB, p, stream); break;
-      default: rc2 = dispatch_epi<256>(epi, tmA, tmB, p, stream); break;
-    }
-    if (rc2) return rc2;
-    const long long n4 = (long long)a->M * (a->N / 4);
-    long long blocks = (n4 + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
     VAW_CHECK_ARG(a->N % 4 == 0, "vaw_gemm_bf16: split-K needs N %% 4 == 0");
-    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a->split_ws, splits, p.split_stride, (float*)a->out,
-                                                              a->bias, a->M, a->N, ldo, a->accumulate);
-    VAW_LAUNCH_CHECK();
-    return VAW_OK;
+    int want;
+    if (a->k_splits > 1) { full = 0; want = a->k_splits; }
+    else { full = (tiles / G) * G; want = (tiles - full) > 0 ? G / (tiles - full) : 1; }
+    const int rem = tiles - full;
+    if (want > num_kb / 2) want = num_kb / 2;  // at least two k-blocks per split
+    const long long slab = (long long)tile_m * bn;
+    if (a->split_ws_elems > 0 && (long long)rem * want * slab > a->split_ws_elems)
+      want = (int)(a->split_ws_elems / (slab * (rem > 0 ? rem : 1)));
+    if (rem > 0 && want > 1) {
+      kb_per = (num_kb + want - 1) / want;
+      splits = (num_kb + kb_per - 1) / kb_per;
+    }
+    if (splits <= 1) { full = tiles; splits = 1; kb_per = num_kb; }
+  }
+  p.full_tiles = full;
+  p.tail_splits = splits;
+  p.kb_per_split = kb_per;
+  p.num_work = full + (tiles - full) * splits;
+  p.split_ws = a->split_ws;
+  {
+    const char* e = getenv("VAW_DBG");
+    p.dbg = e ? atoi(e) : 0;
   }
 
-  switch (bn) {
-    case 128: return dispatch_epi<128>(epi, tmA, tmB, p, stream);
-    case 192: return dispatch_epi<192>(epi, tmA, tmB, p, stream);
-    default: return dispatch_epi<256>(epi, tmA, tmB, p, stream);
+  rc = dispatch_tile(bn, pair, epi, tmA, tmB, p, stream);
+  if (rc || splits == 1) return rc;
+  {
+    const int rem = tiles - full;
+    float* o = reinterpret_cast<float*>(a->out);
+#define VAW_FIXUP(TM_, BN_)                                                                                          \
+  splitk_fixup_kernel<TM_, BN_><<<rem, 256, 0, stream>>>(a->split_ws, full, splits, n_tiles, o, a->bias, a->M, a->N, \
+                                                         ldo, a->accumulate)
+    if (pair) {
+      if (bn == 128) VAW_FIXUP(256, 128); else if (bn == 192) VAW_FIXUP(256, 192); else VAW_FIXUP(256, 256);
+    } else {
+      if (bn == 128) VAW_FIXUP(128, 128); else if (bn == 192) VAW_FIXUP(128, 192); else VAW_FIXUP(128, 256);
+    }
+#undef VAW_FIXUP
+    VAW_LAUNCH_CHECK();
   }
+  return VAW_OK;
 }

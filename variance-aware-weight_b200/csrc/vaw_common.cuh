@@ -36,7 +36,12 @@ void vaw_set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
-#define VAW_LAUNCH_CHECK() VAW_CUDA_TRY(cudaGetLastError())
+void vaw_note_launch();  // bumps the library-wide kernel launch counter (vaw_launch_count)
+#define VAW_LAUNCH_CHECK()            \
+  do {                                \
+    vaw_note_launch();                \
+    VAW_CUDA_TRY(cudaGetLastError()); \
+  } while (0)
 
 int vaw_num_sms();  // cached SM count of the current device
 
@@ -102,29 +107,43 @@ __device__ __forceinline__ void stg_stream_u2(uint2* p, uint2 v) {
   asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
-// activation functions (forward value and derivative), all fp32
+// activation functions (forward value and derivative), fp32 with hardware-approximate transcendentals
+// (tanh.approx / ex2.approx / rcp.approx: relative error ~2^-11, below the bf16 resolution of every consumer).
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float u = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.f + tanhf(u));
+  const float u = k0 * x * fmaf(k1, x * x, 1.f);
+  return 0.5f * x * (1.f + tanh_fast(u));
 }
 __device__ __forceinline__ float gelu_tanh_grad_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float x2 = x * x;
-  float u = k0 * (x + k1 * x * x2);
-  float th = tanhf(u);
-  float du = k0 * (1.f + 3.f * k1 * x2);
+  const float x2 = x * x;
+  const float th = tanh_fast(k0 * x * fmaf(k1, x2, 1.f));
+  const float du = k0 * fmaf(3.f * k1, x2, 1.f);
   return 0.5f * (1.f + th) + 0.5f * x * (1.f - th * th) * du;
 }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
+// exact-GELU via erf(z) ~ 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p|z|)  (Abramowitz-Stegun 7.1.26, |err| < 1.5e-7)
+__device__ __forceinline__ float erf_fast(float z) {
+  const float az = fabsf(z);
+  const float t = __fdividef(1.f, fmaf(0.3275911f, az, 1.f));
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float r = 1.f - poly * __expf(-az * az);
+  return copysignf(r, z);
+}
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.7071067811865476f)); }
 __device__ __forceinline__ float gelu_erf_grad_f(float x) {
-  float cdf = 0.5f * (1.f + erff(x * 0.7071067811865476f));
-  float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  const float cdf = 0.5f * (1.f + erf_fast(x * 0.7071067811865476f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_fast(x); }
 __device__ __forceinline__ float silu_grad_f(float x) {
-  float s = 1.f / (1.f + __expf(-x));
+  const float s = sigmoid_fast(x);
   return s * (1.f + x * (1.f - s));
 }
 

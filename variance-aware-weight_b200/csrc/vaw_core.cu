@@ -2,9 +2,16 @@
 #include "vaw_common.cuh"
 #include <stdarg.h>
 
+#include <atomic>
 namespace {
 thread_local char g_err[1024] = "";
+std::atomic<unsigned long long> g_launches{0};
 }
+
+void vaw_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// number of kernels this library has launched in this process (all threads)
+extern "C" unsigned long long vaw_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void vaw_set_error(const char* fmt, ...) {
   va_list ap;

@@ -21,8 +21,10 @@ struct vaw_gemm_args {
   int accumulate;      // EPI_F32: out += result
   int tile_n;          // 0 = auto, else 128 / 192 / 256
   int resid_mod;       // > 0: resid is [resid_mod, N], indexed by row % resid_mod
-  int k_splits;        // > 1 (EPI_F32 only): split the K loop over k_splits work items per tile
-  float* split_ws;     // fp32 scratch of k_splits * M * ldo elements
+  int k_splits;        // EPI_F32 only.  > 1: split every tile's K loop; -1: split only the partial last wave
+  float* split_ws;     // fp32 scratch for the split partials (slabs of 128 x tile_n)
+  long long split_ws_elems;  // capacity of split_ws in floats (0 = unchecked)
+  int cta_group;       // 0 = auto, 1 = one CTA per 128-row tile, 2 = SM pair per 256-row tile (tcgen05 cta_group::2)
 };
 
 enum : int {

@@ -37,7 +37,7 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p), ("resid", C.c_void_p), ("gate", C.c_void_p), ("aux", C.c_void_p),
         ("ldo", C.c_longlong), ("ldg", C.c_longlong),
         ("rows_per_sample", C.c_int), ("accumulate", C.c_int), ("tile_n", C.c_int), ("resid_mod", C.c_int),
-        ("k_splits", C.c_int), ("split_ws", C.c_void_p),
+        ("k_splits", C.c_int), ("split_ws", C.c_void_p), ("split_ws_elems", C.c_longlong), ("cta_group", C.c_int),
     ]
 
 

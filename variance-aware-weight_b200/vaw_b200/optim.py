@@ -1,0 +1,128 @@
+"""Fused optimizer step over the engine's flat parameter buffer, and the data-parallel model wrapper.
+
+FusedAdamW replaces, for models that expose `flat_parameters()` (vaw_b200.models.DiT), the reference's
+`optim.AdamW(model.parameters(), lr, betas, weight_decay, eps)` (main.py:354) + GradScaler unscale (trainer.py:124-129)
++ rank-0 EMA (trainer.py:12-18) with ONE HBM-bound pass (vaw_adamw_step): read p, g, m, v; write p, m, v, the bf16
+shadow used by the tensor cores, and optionally the EMA copy.  torch.optim.AdamW over `model.parameters()` keeps
+working (the per-tensor Parameters are views of the flat buffer); this class is the fast path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from contextlib import nullcontext
+
+import torch
+
+from . import _lib as L
+from .parallel import FlatGradSync, dist_ready
+
+L.register("vaw_adamw_step", [C.c_void_p] * 6 + [C.c_longlong] + [C.c_double] * 5 + [C.c_longlong, C.c_double, C.c_double,
+                                                                                      C.c_void_p])
+
+
+class FusedAdamW:
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, ema_decay=None):
+        self.model = model
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.ema_decay = ema_decay
+        self.step_count = 0
+        self.m = self.v = self.ema = None
+        self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)]  # LambdaLR-style access
+
+    def _ensure_state(self):
+        flat, gflat, shadow = self.model.flat_parameters()
+        if flat is None:
+            raise L.VawError("FusedAdamW: run a forward pass (or model._ensure_flat(device)) before the first step")
+        if self.m is None or self.m.device != flat.device or self.m.numel() != flat.numel():
+            self.m = torch.zeros_like(flat, requires_grad=False)
+            self.v = torch.zeros_like(flat, requires_grad=False)
+            if self.ema_decay is not None:
+                self.ema = flat.detach().clone()
+        return flat, gflat, shadow
+
+    @torch.no_grad()
+    def step(self, grad_scale: float = 1.0):
+        flat, gflat, shadow = self._ensure_state()
+        self.step_count += 1
+        g = self.param_groups[0]
+        L.call("vaw_adamw_step", flat.data_ptr(), gflat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+               shadow.data_ptr(), L.ptr(self.ema), flat.numel(), float(g["lr"]), float(g["betas"][0]),
+               float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self.step_count, float(grad_scale),
+               float(self.ema_decay if self.ema_decay is not None else 0.0), L.stream_ptr())
+        # the kernel refreshed the bf16 shadow itself: mark it current so the next forward skips the cast pass
+        self.model._shadow_version = sum(p._version for p, _ in self.model._slot_cache)
+
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.model.parameters():
+            p.grad = None  # the next backward overwrites the flat gradient buffer (no memset pass needed)
+
+
+class DataParallel(torch.nn.Module):
+    """Drop-in for the reference's DDP wrapper (main.py:347): `.module`, `.no_sync()`, same forward.  Gradients are
+    averaged over ranks by FlatGradSync on the flat gradient buffer, bucketed per transformer block and overlapped
+    with backward through the engine's per-block events."""
+
+    def __init__(self, module, process_group=None):
+        super().__init__()
+        self.module = module
+        self._sync = None
+        self._group = process_group
+        self._events = None
+        first = next(module.parameters())
+        if dist_ready() and first.is_cuda:
+            self._setup()
+
+    def _setup(self):
+        m = self.module
+        m._ensure_flat(next(m.parameters()).device)
+        # every rank starts from rank 0's weights, like DDP's constructor broadcast (main.py:347)
+        import torch.distributed as dist
+        with torch.no_grad():
+            dist.broadcast(m._flat.data, 0, group=self._group)
+        m._shadow_version = -1
+        ranges, head, total = m.block_grad_ranges()
+        # gradients become final block L-1 first ... block 0, then everything before the blocks (embedders, adaLN, final)
+        buckets = list(reversed(ranges)) + [head]
+        self._sync = FlatGradSync(m._gflat, buckets, self._group)
+        ev = [torch.cuda.Event() for _ in range(m.depth + 1)]
+        for e in ev:
+            e.record()  # materialise the CUDA events so their handles can be passed through the C ABI
+        m._events = ev
+        self._events = list(reversed(ev[: m.depth])) + [ev[m.depth]]
+        m._post_backward = self._after_backward
+
+    def _after_backward(self):
+        # backward is fully enqueued at this point: the bucket all-reduces (gated by the per-block events) overlap
+        # with it on the side stream, and whatever the caller enqueues next (optimizer) is ordered after them.
+        self._sync.launch(self._events)
+        self._sync.wait()
+
+    def no_sync(self):
+        if self._sync is None:
+            return nullcontext()
+        return self._sync.no_sync()
+
+    def wait_grads(self):
+        if self._sync is not None:
+            self._sync.wait()
+
+    def forward(self, *a, **k):
+        out = self.module(*a, **k)
+        if self._sync is None and dist_ready():
+            self._setup()
+        return out
+
+    def flat_parameters(self):
+        return self.module.flat_parameters()
+
+    @property
+    def _slot_cache(self):
+        return self.module._slot_cache
+
+    @property
+    def _shadow_version(self):
+        return self.module._shadow_version
+
+    @_shadow_version.setter
+    def _shadow_version(self, v):
+        self.module._shadow_version = v

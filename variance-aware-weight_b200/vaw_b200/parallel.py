@@ -1,0 +1,110 @@
+"""Data-parallel plumbing: one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch) for the two natural
+collectives of the training step:
+
+  * gradient all-reduce (average) — the reference gets it from DDP's bucketed hooks (main.py:347, trainer.py:94-108).
+    Here the engine writes gradients straight into one flat buffer, so the all-reduce runs on contiguous per-block
+    slices of that buffer, launched on a side stream as soon as the engine's backward has recorded the block's event
+    (blocks finish in reverse order), overlapping with the rest of backward.
+  * all_gather of the per-sample (t, loss) pairs for LossAwareSampler.update_with_local_losses (resample.py:85-106):
+    one collective of packed int32 pairs instead of three collectives + 2*W*B host syncs.
+
+Everything in this file is backend-agnostic tensor plumbing (works with gloo on CPU tensors, which is how the
+world_size=2 CPU tests exercise it); the kernels it feeds are CUDA-only.
+"""
+from __future__ import annotations
+
+from contextlib import contextmanager
+
+import torch
+import torch.distributed as dist
+
+
+def dist_ready() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def gather_tloss(local_ts: torch.Tensor, local_losses: torch.Tensor, ragged: bool = False):
+    """All-gather (timestep, loss) pairs in rank order.  Returns (ts int32 [sum B], losses fp32 [sum B]); padding
+    entries (ragged batches only) carry t = -1 and are skipped by the update kernel.
+    Bit-exactness: the fp32 loss travels as its int32 bit pattern, so no value is rounded on the way."""
+    t32 = local_ts.to(torch.int32).reshape(-1)
+    l32 = local_losses.detach().to(torch.float32).reshape(-1)
+    if not dist_ready():
+        return t32.contiguous(), l32.contiguous()
+    W = dist.get_world_size()
+    B = t32.numel()
+    Bpad = B
+    if ragged:
+        bmax = torch.tensor([B], dtype=torch.int32, device=t32.device)
+        dist.all_reduce(bmax, op=dist.ReduceOp.MAX)
+        Bpad = int(bmax.item())
+    packed = torch.empty(2, Bpad, dtype=torch.int32, device=t32.device)
+    packed[0, :B] = t32
+    packed[1, :B] = l32.view(torch.int32)
+    if Bpad > B:
+        packed[0, B:] = -1
+        packed[1, B:] = 0
+    flat = torch.empty(W * 2 * Bpad, dtype=torch.int32, device=t32.device)
+    dist.all_gather_into_tensor(flat, packed.view(-1))
+    gathered = flat.view(W, 2, Bpad)
+    ts = gathered[:, 0, :].reshape(-1).contiguous()
+    losses = gathered[:, 1, :].reshape(-1).contiguous().view(torch.float32)
+    return ts, losses
+
+
+class FlatGradSync:
+    """Bucketed average all-reduce over a flat gradient buffer.
+
+    buckets: list of (begin, end) element ranges in the order their gradients become final during backward.
+    With CUDA tensors the collectives run on a dedicated stream gated by per-bucket events recorded by the engine;
+    call `launch(events)` right after backward was enqueued and `wait()` before the optimizer reads the gradients.
+    """
+
+    def __init__(self, gflat: torch.Tensor, buckets, process_group=None):
+        self.gflat = gflat
+        self.buckets = [(int(b), int(e)) for b, e in buckets if e > b]
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist_ready() else 1
+        self.stream = torch.cuda.Stream() if gflat.is_cuda else None
+        self.enabled = True
+        self._native_avg = dist_ready() and dist.get_backend(process_group) == "nccl"
+
+    @contextmanager
+    def no_sync(self):
+        """Gradient accumulation window (the reference uses DDP.no_sync, trainer.py:94-101)."""
+        old, self.enabled = self.enabled, False
+        try:
+            yield
+        finally:
+            self.enabled = old
+
+    def _reduce(self, view):
+        if self._native_avg:
+            dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+            view.div_(self.world)
+
+    def launch(self, events=None):
+        if not self.enabled or self.world == 1:
+            return
+        if self.stream is None:
+            for b, e in self.buckets:
+                self._reduce(self.gflat[b:e])
+            return
+        with torch.cuda.stream(self.stream):
+            for i, (b, e) in enumerate(self.buckets):
+                if events is not None and events[i] is not None:
+                    self.stream.wait_event(events[i])
+                else:
+                    self.stream.wait_stream(torch.cuda.default_stream())
+                self._reduce(self.gflat[b:e])
+
+    def wait(self):
+        if self.stream is not None and self.enabled and self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
+
+def shard_seed(base_seed: int, rank: int) -> int:
+    """Per-rank RNG seed rule of the reference (tools/utils.py:62-69): seed + rank."""
+    return int(base_seed) + int(rank)

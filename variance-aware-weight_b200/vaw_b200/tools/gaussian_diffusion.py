@@ -338,6 +338,8 @@ class GaussianDiffusion:
         x_t = th.empty_like(x0)
         target = th.empty_like(x0) if want_target else None
         N = x0.shape[0]
+        if x0.numel() == 0:
+            return x_t, target
         L.call("vaw_qsample_target", x0.data_ptr(), eps.data_ptr(), t64.data_ptr(), ta.data_ptr(), ts.data_ptr(),
                L.ptr(c0), L.ptr(c1), x_t.data_ptr(), L.ptr(target), self.model_mean_type.value, N,
                x0[0].numel() if N else 1, L.stream_ptr())

@@ -22,6 +22,7 @@ import torch as th
 import torch.distributed as dist
 
 from .. import _lib as L
+from ..parallel import gather_tloss
 
 
 def create_named_schedule_sampler(name: str, diffusion):
@@ -77,27 +78,7 @@ class LossAwareSampler(ScheduleSampler):
         """Gather (t, loss) from every rank in rank order and apply the identical update everywhere
         (reference :72-112)."""
         L.require_cuda(local_ts, local_losses)
-        B = int(local_ts.shape[0])
-        dev = local_ts.device
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            W = dist.get_world_size()
-            Bpad = B
-            if self.ragged_batches:
-                # per-rank batch sizes differ: pad to the maximum (one int all_reduce + host read); padding has t = -1
-                bmax = th.tensor([B], dtype=th.int32, device=dev)
-                dist.all_reduce(bmax, op=dist.ReduceOp.MAX)
-                Bpad = int(bmax.item())
-            packed = th.empty(2, Bpad, dtype=th.int32, device=dev)
-            L.call("vaw_pack_tloss", local_ts.to(th.int64).contiguous().data_ptr(),
-                   local_losses.detach().float().contiguous().data_ptr(), packed[0].data_ptr(),
-                   packed[1].data_ptr(), B, Bpad, L.stream_ptr())
-            gathered = th.empty(W, 2, Bpad, dtype=th.int32, device=dev)
-            dist.all_gather_into_tensor(gathered, packed)
-            ts = gathered[:, 0, :].contiguous().view(-1)
-            losses = gathered[:, 1, :].contiguous().view(-1).view(th.float32)
-        else:
-            ts = local_ts.to(th.int32).contiguous()
-            losses = local_losses.detach().float().contiguous()
+        ts, losses = gather_tloss(local_ts, local_losses, ragged=self.ragged_batches)
         self._device_update(ts, losses)
 
     # Set True when ranks may pass different batch sizes (the reference pads to the max, :96-100).  Equal sizes —
