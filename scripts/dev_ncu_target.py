@@ -32,10 +32,10 @@ for _ in range(reps):
     x = torch.randn(M, D, device=dev); mod = torch.randn(B, 6 * D, device=dev) * 0.1
     yn = torch.empty(M, D, device=dev, dtype=torch.bfloat16); mean = torch.empty(M, device=dev); rstd = torch.empty(M, device=dev)
     L.call("vaw_ln_fwd", x.data_ptr(), mod.data_ptr(), mod[:, D:].data_ptr(), 6 * D, T, None, None, yn.data_ptr(), mean.data_ptr(), rstd.data_ptr(), M, D, 1e-6, st())
-    dx = torch.randn(M, D, device=dev); part = torch.empty(B * 4 * 2 * D, device=dev)
-    L.call("vaw_ln_bwd", dyb.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), mod[:, D:].data_ptr(), 6 * D, None, dx.data_ptr(), 1, part.data_ptr(), T, B, 4, M, D, st())
+    dx = torch.randn(M, D, device=dev); part = torch.empty(B * 8 * 2 * D, device=dev)
+    L.call("vaw_ln_bwd", dyb.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), mod[:, D:].data_ptr(), 6 * D, None, dx.data_ptr(), 1, part.data_ptr(), T, B, 8, M, D, st())
     dyo = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
-    L.call("vaw_gate_bwd", dx.data_ptr(), dyb.data_ptr(), mod.data_ptr(), 6 * D, dyo.data_ptr(), part.data_ptr(), T, B, 4, M, D, st())
+    L.call("vaw_gate_bwd", dx.data_ptr(), dyb.data_ptr(), mod.data_ptr(), 6 * D, dyo.data_ptr(), part.data_ptr(), T, B, 8, M, D, st())
     hd = D // H
     qkv = bf(B, T, 3, H, hd); o = torch.empty(B, T, H, hd, device=dev, dtype=torch.bfloat16); lse = torch.empty(B, H, T, device=dev)
     L.call("vaw_attn_fwd", qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, H, hd, st())

@@ -2,167 +2,187 @@
 //   LayerNorm (+ adaLN modulate, or affine) forward / backward          (models/dit.py:24-25,122-124,133-137;
 //   gate * branch backward (adaLN-Zero) and residual bookkeeping          models/uvit.py:96-121)
 //   deterministic column reductions for bias / shift / scale / gate gradients
-// All kernels are HBM-bound: one pass over the [rows, D] activation, 128-bit accesses, fp32 math, and two-level
-// (per-CTA partial -> fixed-order finish) reductions so gradients are bit-reproducible run to run.
+// All kernels are HBM-bound: one pass over the [rows, D] activation from DRAM, 128-bit accesses, fp32 math.
+// The backward kernels give every thread a fixed group of 4 columns and let it walk the rows of its chunk, so the
+// per-column sums (d shift / d scale / d gate / bias gradients) live in registers: no shared-memory accumulators,
+// no atomics, high occupancy, and a fixed summation order (bit-reproducible gradients).  Per-CTA partials are folded
+// by the finish kernels in fixed order.
 #include "vaw_common.cuh"
 
 namespace {
 
-constexpr int kMaxD = 2048;  // rows live in registers: KV = ceil(D / 128) float4 per lane, KV in {3, 6, 9, 16}
+constexpr int kMaxD = 2048;  // ln_fwd keeps a row in registers: KV = ceil(D / 128) float4 per lane, KV in {3, 6, 9, 16}
 
 // ---------------------------------------------------------------------------------------------------
 // LayerNorm forward: y = xhat * A + Bv, xhat = (x - mean) * rstd
 //   modulate (DiT):  A = 1 + scale[n, :], Bv = shift[n, :]     (n = row / rows_per_sample; ld_mod = row stride)
 //   affine (U-ViT):  A = weight[:],       Bv = bias[:]
 //   plain:           A = 1, Bv = 0
-// one warp per row, the row lives in registers (two-pass variance like torch's layer_norm).
+// one warp per row at a time, 4 rows per warp, the row lives in registers (two-pass variance like torch).
 // ---------------------------------------------------------------------------------------------------
+constexpr int kLnRowsPerWarp = 4;
+
 template <int KV>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
               long long ld_mod, int rows_per_sample, const float* __restrict__ weight,
               const float* __restrict__ bias, bf16* __restrict__ y, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, int M, int D, float eps) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
   const int nv = D >> 2;  // float4 per row
-  float4 v[KV];
-  float s = 0.f;
+  const int row_base = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kLnRowsPerWarp;
+#pragma unroll 1
+  for (int rr = 0; rr < kLnRowsPerWarp; ++rr) {
+    const int row = row_base + rr;
+    if (row >= M) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
+    float4 v[KV];
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < KV; ++i) {
-    const int idx = i * 32 + lane;
-    if (idx < nv) {
-      v[i] = xr[idx];
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-  }
-  const float mean = warp_sum(s) / (float)D;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < KV; ++i) {
-    const int idx = i * 32 + lane;
-    if (idx < nv) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
-  if (lane == 0) {
-    mean_out[row] = mean;
-    rstd_out[row] = rstd;
-  }
-  const long long mo = scale ? (long long)(row / rows_per_sample) * ld_mod : 0;
-  uint2* yr = reinterpret_cast<uint2*>(y + (long long)row * D);
-#pragma unroll
-  for (int i = 0; i < KV; ++i) {
-    const int idx = i * 32 + lane;
-    if (idx < nv) {
-      float4 A = make_float4(1.f, 1.f, 1.f, 1.f), Bv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (scale) {
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + mo) + idx);
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + mo) + idx);
-        A = make_float4(1.f + sc.x, 1.f + sc.y, 1.f + sc.z, 1.f + sc.w);
-        Bv = sh;
-      } else if (weight) {
-        A = __ldg(reinterpret_cast<const float4*>(weight) + idx);
-        Bv = __ldg(reinterpret_cast<const float4*>(bias) + idx);
+    for (int i = 0; i < KV; ++i) {
+      const int idx = i * 32 + lane;
+      if (idx < nv) {
+        v[i] = ldg_stream_f4(xr + idx);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
       }
-      const float a = (v[i].x - mean) * rstd, b = (v[i].y - mean) * rstd, c = (v[i].z - mean) * rstd,
-                  d = (v[i].w - mean) * rstd;
-      uint2 o;
-      o.x = pack_bf16(fmaf(a, A.x, Bv.x), fmaf(b, A.y, Bv.y));
-      o.y = pack_bf16(fmaf(c, A.z, Bv.z), fmaf(d, A.w, Bv.w));
-      yr[idx] = o;
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < KV; ++i) {
+      const int idx = i * 32 + lane;
+      if (idx < nv) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+    if (lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+    const long long mo = scale ? (long long)(row / rows_per_sample) * ld_mod : 0;
+    uint2* yr = reinterpret_cast<uint2*>(y + (long long)row * D);
+#pragma unroll
+    for (int i = 0; i < KV; ++i) {
+      const int idx = i * 32 + lane;
+      if (idx < nv) {
+        float4 A = make_float4(1.f, 1.f, 1.f, 1.f), Bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (scale) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + mo) + idx);
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + mo) + idx);
+          A = make_float4(1.f + sc.x, 1.f + sc.y, 1.f + sc.z, 1.f + sc.w);
+          Bv = sh;
+        } else if (weight) {
+          A = __ldg(reinterpret_cast<const float4*>(weight) + idx);
+          Bv = __ldg(reinterpret_cast<const float4*>(bias) + idx);
+        }
+        const float a = (v[i].x - mean) * rstd, b = (v[i].y - mean) * rstd, c = (v[i].z - mean) * rstd,
+                    d = (v[i].w - mean) * rstd;
+        uint2 o;
+        o.x = pack_bf16(fmaf(a, A.x, Bv.x), fmaf(b, A.y, Bv.y));
+        o.y = pack_bf16(fmaf(c, A.z, Bv.z), fmaf(d, A.w, Bv.w));
+        yr[idx] = o;
+      }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// LayerNorm backward.  grid = (chunks, groups): group = sample (modulate) or arbitrary row range (affine);
-// every warp walks rows of its chunk, keeps per-column partial sums of dB = sum dy and dA = sum dy * xhat in
-// its own shared-memory slice, the CTA then folds its 8 slices in fixed order into part[group, chunk, {dB,dA}, D].
+// LayerNorm backward.  grid = (chunks, groups): group = sample (modulate) or arbitrary row range (affine).
 //   g = dy * A ;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) ;  dx_io = (add_into ? dx_io : 0) + dx
+//   part[group, chunk, 0, :] = sum_rows dy         (d shift / d bias)
+//   part[group, chunk, 1, :] = sum_rows dy * xhat  (d scale / d weight)
+// phase 1: warps sweep the chunk's rows and leave (mean(g), mean(g*xhat)) per row in shared memory
+// phase 2: every thread owns 4 columns and walks the rows (x / dy come back from L1/L2), column sums in registers
 // ---------------------------------------------------------------------------------------------------
-template <int KV>
-__global__ void __launch_bounds__(256)
+constexpr int kBwdMaxRows = 64;  // rows per chunk handled by one CTA (shared-memory row statistics)
+
+__global__ void __launch_bounds__(512)
 ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, const float* __restrict__ scale, long long ld_mod,
               const float* __restrict__ weight, float* __restrict__ dx_io, int add_into, float* __restrict__ part,
               int rows_per_group, int chunks, int M, int D) {
-  extern __shared__ float sm_acc[];  // [8 warps][2][D]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float s_m1[kBwdMaxRows], s_m2[kBwdMaxRows], s_mean[kBwdMaxRows], s_rstd[kBwdMaxRows];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int chunk = blockIdx.x, group = blockIdx.y;
   const int nv = D >> 2;
-  float* acc = sm_acc + (long long)warp * 2 * D;
-  for (int i = lane; i < 2 * D; i += 32) acc[i] = 0.f;
-  __syncwarp();
   const int rows_per_chunk = (rows_per_group + chunks - 1) / chunks;
   const int r_begin = group * rows_per_group + chunk * rows_per_chunk;
   const int r_end = min(min(r_begin + rows_per_chunk, (group + 1) * rows_per_group), M);
-  const long long mo = scale ? (long long)group * ld_mod : 0;
-  for (int row = r_begin + warp; row < r_end; row += 8) {
+  const int nrows = max(r_end - r_begin, 0);
+  const float4* Ap = scale ? reinterpret_cast<const float4*>(scale + (long long)group * ld_mod)
+                           : reinterpret_cast<const float4*>(weight);
+  const float add1 = scale ? 1.f : 0.f;  // A = 1 + scale (modulate) | weight (affine) | 1 (plain)
+  const float inv_d = 1.f / (float)D;
+
+  // ---- phase 1: row statistics ----
+  for (int r = warp; r < nrows; r += nwarps) {
+    const int row = r_begin + r;
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + (long long)row * D);
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float4 xh[KV], gv[KV];
     float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < KV; ++i) {
-      const int idx = i * 32 + lane;
-      if (idx < nv) {
-        const float4 xv = xr[idx];
-        const uint2 du = dyr[idx];
-        const float2 d0 = unpack_bf16(du.x), d1 = unpack_bf16(du.y);
-        xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-        float4 A = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (scale) {
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + mo) + idx);
-          A = make_float4(1.f + sc.x, 1.f + sc.y, 1.f + sc.z, 1.f + sc.w);
-        } else if (weight) {
-          A = __ldg(reinterpret_cast<const float4*>(weight) + idx);
-        }
-        gv[i] = make_float4(d0.x * A.x, d0.y * A.y, d1.x * A.z, d1.y * A.w);
-        s1 += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
-        s2 += (gv[i].x * xh[i].x + gv[i].y * xh[i].y) + (gv[i].z * xh[i].z + gv[i].w * xh[i].w);
-        // column partials: dB += dy, dA += dy * xhat (each lane owns its columns -> no conflicts)
-        float4* aB = reinterpret_cast<float4*>(acc) + idx;
-        float4* aA = reinterpret_cast<float4*>(acc + D) + idx;
-        float4 b = *aB, a = *aA;
-        b.x += d0.x; b.y += d0.y; b.z += d1.x; b.w += d1.y;
-        a.x += d0.x * xh[i].x; a.y += d0.y * xh[i].y; a.z += d1.x * xh[i].z; a.w += d1.y * xh[i].w;
-        *aB = b;
-        *aA = a;
+    for (int idx = lane; idx < nv; idx += 32) {
+      const float4 xv = xr[idx];
+      const uint2 du = dyr[idx];
+      const float2 d0 = unpack_bf16(du.x), d1 = unpack_bf16(du.y);
+      float4 A = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (Ap) {
+        const float4 a = __ldg(Ap + idx);
+        A = make_float4(a.x + add1, a.y + add1, a.z + add1, a.w + add1);
       }
+      const float g0 = d0.x * A.x, g1 = d0.y * A.y, g2 = d1.x * A.z, g3 = d1.y * A.w;
+      s1 += (g0 + g1) + (g2 + g3);
+      s2 += (g0 * ((xv.x - mean) * rstd) + g1 * ((xv.y - mean) * rstd)) +
+            (g2 * ((xv.z - mean) * rstd) + g3 * ((xv.w - mean) * rstd));
     }
-    const float m1 = warp_sum(s1) / (float)D, m2 = warp_sum(s2) / (float)D;
-    float4* dxr = reinterpret_cast<float4*>(dx_io + (long long)row * D);
-#pragma unroll
-    for (int i = 0; i < KV; ++i) {
-      const int idx = i * 32 + lane;
-      if (idx < nv) {
-        float4 o;
-        o.x = rstd * (gv[i].x - m1 - xh[i].x * m2);
-        o.y = rstd * (gv[i].y - m1 - xh[i].y * m2);
-        o.z = rstd * (gv[i].z - m1 - xh[i].z * m2);
-        o.w = rstd * (gv[i].w - m1 - xh[i].w * m2);
-        if (add_into) {
-          const float4 p = dxr[idx];
-          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-        }
-        dxr[idx] = o;
-      }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      s_m1[r] = s1 * inv_d;
+      s_m2[r] = s2 * inv_d;
+      s_mean[r] = mean;
+      s_rstd[r] = rstd;
     }
   }
   __syncthreads();
-  if (part) {
-    float* dst = part + ((long long)group * chunks + chunk) * 2 * D;
-    for (int i = threadIdx.x; i < 2 * D; i += 256) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) s += sm_acc[(long long)w * 2 * D + i];
-      dst[i] = s;
+
+  // ---- phase 2: column owners ----
+  for (int cg = threadIdx.x; cg < nv; cg += blockDim.x) {
+    float4 A = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (Ap) {
+      const float4 a = __ldg(Ap + cg);
+      A = make_float4(a.x + add1, a.y + add1, a.z + add1, a.w + add1);
+    }
+    float4 accB = make_float4(0.f, 0.f, 0.f, 0.f), accA = accB;
+#pragma unroll 4
+    for (int r = 0; r < nrows; ++r) {
+      const long long o = (long long)(r_begin + r) * D;
+      const float4 xv = *(reinterpret_cast<const float4*>(x + o) + cg);
+      const uint2 du = *(reinterpret_cast<const uint2*>(dy + o) + cg);
+      const float2 d0 = unpack_bf16(du.x), d1 = unpack_bf16(du.y);
+      const float mean = s_mean[r], rstd = s_rstd[r], m1 = s_m1[r], m2 = s_m2[r];
+      const float h0 = (xv.x - mean) * rstd, h1 = (xv.y - mean) * rstd, h2 = (xv.z - mean) * rstd,
+                  h3 = (xv.w - mean) * rstd;
+      float4 out;
+      out.x = rstd * (d0.x * A.x - m1 - h0 * m2);
+      out.y = rstd * (d0.y * A.y - m1 - h1 * m2);
+      out.z = rstd * (d1.x * A.z - m1 - h2 * m2);
+      out.w = rstd * (d1.y * A.w - m1 - h3 * m2);
+      float4* dxp = reinterpret_cast<float4*>(dx_io + o) + cg;
+      if (add_into) {
+        const float4 p = *dxp;
+        out.x += p.x; out.y += p.y; out.z += p.z; out.w += p.w;
+      }
+      *dxp = out;
+      accB.x += d0.x; accB.y += d0.y; accB.z += d1.x; accB.w += d1.y;
+      accA.x += d0.x * h0; accA.y += d0.y * h1; accA.z += d1.x * h2; accA.w += d1.y * h3;
+    }
+    if (part) {
+      float* dst = part + ((long long)group * chunks + chunk) * 2 * D;
+      *(reinterpret_cast<float4*>(dst) + cg) = accB;
+      *(reinterpret_cast<float4*>(dst + D) + cg) = accA;
     }
   }
 }
@@ -173,55 +193,40 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const fl
 //   part[n, chunk, 0, :] = sum_rows dx             (-> bias gradient: db = sum_n gate[n] * s[n])
 //   part[n, chunk, 1, :] = sum_rows dx * y         (-> dgate[n])
 // gate == null: plain residual (U-ViT): dy = bf16(dx), only the column sum is produced.
+// Column-owner threads, register accumulators (see the header comment).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 gate_bwd_kernel(const float* __restrict__ dx, const bf16* __restrict__ y, const float* __restrict__ gate,
                 long long ld_gate, bf16* __restrict__ dy, float* __restrict__ part, int rows_per_group, int chunks,
                 int M, int D) {
-  extern __shared__ float sm_acc[];  // [8][2][D]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x, group = blockIdx.y;
   const int nv = D >> 2;
-  float* acc = sm_acc + (long long)warp * 2 * D;
-  for (int i = lane; i < 2 * D; i += 32) acc[i] = 0.f;
-  __syncwarp();
   const int rows_per_chunk = (rows_per_group + chunks - 1) / chunks;
   const int r_begin = group * rows_per_group + chunk * rows_per_chunk;
   const int r_end = min(min(r_begin + rows_per_chunk, (group + 1) * rows_per_group), M);
   const float4* gp = gate ? reinterpret_cast<const float4*>(gate + (long long)group * ld_gate) : nullptr;
-  for (int row = r_begin + warp; row < r_end; row += 8) {
-    const float4* dxr = reinterpret_cast<const float4*>(dx + (long long)row * D);
-    const uint2* yr = y ? reinterpret_cast<const uint2*>(y + (long long)row * D) : nullptr;
-    uint2* dyr = reinterpret_cast<uint2*>(dy + (long long)row * D);
-    for (int idx = lane; idx < nv; idx += 32) {
-      const float4 d = dxr[idx];
-      float4 gt = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (gp) gt = __ldg(gp + idx);
-      uint2 o;
-      o.x = pack_bf16(d.x * gt.x, d.y * gt.y);
-      o.y = pack_bf16(d.z * gt.z, d.w * gt.w);
-      dyr[idx] = o;
-      float4* aS = reinterpret_cast<float4*>(acc) + idx;
-      float4 s = *aS;
-      s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
-      *aS = s;
-      if (yr) {
-        const uint2 yu = yr[idx];
+  for (int cg = threadIdx.x; cg < nv; cg += blockDim.x) {
+    float4 gt = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (gp) gt = __ldg(gp + cg);
+    float4 accS = make_float4(0.f, 0.f, 0.f, 0.f), accG = accS;
+#pragma unroll 4
+    for (int row = r_begin; row < r_end; ++row) {
+      const long long o = (long long)row * D;
+      const float4 d = ldg_stream_f4(reinterpret_cast<const float4*>(dx + o) + cg);
+      uint2 ov;
+      ov.x = pack_bf16(d.x * gt.x, d.y * gt.y);
+      ov.y = pack_bf16(d.z * gt.z, d.w * gt.w);
+      *(reinterpret_cast<uint2*>(dy + o) + cg) = ov;
+      accS.x += d.x; accS.y += d.y; accS.z += d.z; accS.w += d.w;
+      if (y) {
+        const uint2 yu = ldg_stream_u2(reinterpret_cast<const uint2*>(y + o) + cg);
         const float2 y0 = unpack_bf16(yu.x), y1 = unpack_bf16(yu.y);
-        float4* aG = reinterpret_cast<float4*>(acc + D) + idx;
-        float4 a = *aG;
-        a.x += d.x * y0.x; a.y += d.y * y0.y; a.z += d.z * y1.x; a.w += d.w * y1.y;
-        *aG = a;
+        accG.x += d.x * y0.x; accG.y += d.y * y0.y; accG.z += d.z * y1.x; accG.w += d.w * y1.y;
       }
     }
-  }
-  __syncthreads();
-  float* dst = part + ((long long)group * chunks + chunk) * 2 * D;
-  for (int i = threadIdx.x; i < 2 * D; i += 256) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) s += sm_acc[(long long)w * 2 * D + i];
-    dst[i] = s;
+    float* dst = part + ((long long)group * chunks + chunk) * 2 * D;
+    *(reinterpret_cast<float4*>(dst) + cg) = accS;
+    *(reinterpret_cast<float4*>(dst + D) + cg) = accG;
   }
 }
 
@@ -281,6 +286,7 @@ colsum_bf16_stage1(const bf16* __restrict__ a, long long lda, int M, int N, int 
   const int r1 = min(r0 + rows_per_chunk, M);
   float s0 = 0.f, s1 = 0.f;
   if (col < N) {
+#pragma unroll 4
     for (int r = r0 + rg; r < r1; r += 8) {
       const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(a + (long long)r * lda + col));
       s0 += v.x;
@@ -308,6 +314,13 @@ colsum_stage2(const float* __restrict__ part, int chunks, int N, float* __restri
   out[c] = accumulate ? out[c] + s : s;
 }
 
+inline int threads_for_columns(int D) {
+  int t = ((D / 4) + 31) / 32 * 32;
+  if (t > 512) t = 512;
+  if (t < 64) t = 64;
+  return t;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------
@@ -321,9 +334,11 @@ extern "C" int vaw_ln_fwd(const float* x, const float* shift, const float* scale
   VAW_CHECK_ARG((scale == nullptr) == (shift == nullptr), "vaw_ln_fwd: shift and scale go together");
   VAW_CHECK_ARG((weight == nullptr) == (bias == nullptr), "vaw_ln_fwd: weight and bias go together");
   VAW_CHECK_ARG(!scale || rows_per_sample > 0, "vaw_ln_fwd: rows_per_sample");
+  const int rows_per_cta = 8 * kLnRowsPerWarp;
+  const unsigned grid = (unsigned)((M + rows_per_cta - 1) / rows_per_cta);
 #define VAW_LN_FWD(KV)                                                                                        \
-  ln_fwd_kernel<KV><<<(M + 7) / 8, 256, 0, stream>>>(x, shift, scale, ld_mod, rows_per_sample > 0 ? rows_per_sample : 1, \
-                                                     weight, bias, (bf16*)y, mean, rstd, M, D, eps)
+  ln_fwd_kernel<KV><<<grid, 256, 0, stream>>>(x, shift, scale, ld_mod, rows_per_sample > 0 ? rows_per_sample : 1, \
+                                              weight, bias, (bf16*)y, mean, rstd, M, D, eps)
   if (D <= 384) VAW_LN_FWD(3);
   else if (D <= 768) VAW_LN_FWD(6);
   else if (D <= 1152) VAW_LN_FWD(9);
@@ -333,32 +348,20 @@ extern "C" int vaw_ln_fwd(const float* x, const float* shift, const float* scale
   return VAW_OK;
 }
 
-// chunks: number of partial rows per group; part must hold groups * chunks * 2 * D floats (may be NULL when
-// neither dA nor dB is wanted).  groups * rows_per_group must cover M.
+// chunks: number of partial rows per group (ceil(rows_per_group / chunks) must be <= 64); part must hold
+// groups * chunks * 2 * D floats (may be NULL when neither dA nor dB is wanted).  groups * rows_per_group covers M.
 extern "C" int vaw_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
                           long long ld_mod, const float* weight, float* dx_io, int add_into, float* part,
                           int rows_per_group, int groups, int chunks, int M, int D, cudaStream_t stream) {
   VAW_CHECK_ARG(dy && x && mean && rstd && dx_io && M > 0, "vaw_ln_bwd: bad arguments");
-  VAW_CHECK_ARG(D % 4 == 0 && D <= kMaxD, "vaw_ln_bwd: D=%d must be a multiple of 4 and <= %d", D, kMaxD);
+  VAW_CHECK_ARG(D % 4 == 0, "vaw_ln_bwd: D=%d must be a multiple of 4", D);
   VAW_CHECK_ARG(rows_per_group > 0 && groups > 0 && chunks > 0 && (long long)groups * rows_per_group >= M,
                 "vaw_ln_bwd: bad grouping");
-  const size_t smem = (size_t)8 * 2 * D * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    VAW_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * kMaxD * 4));
-    VAW_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * kMaxD * 4));
-    VAW_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * kMaxD * 4));
-    VAW_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * kMaxD * 4));
-    configured = true;
-  }
-#define VAW_LN_BWD(KV)                                                                                          \
-  ln_bwd_kernel<KV><<<dim3(chunks, groups), 256, smem, stream>>>((const bf16*)dy, x, mean, rstd, scale, ld_mod, weight, \
-                                                                 dx_io, add_into, part, rows_per_group, chunks, M, D)
-  if (D <= 384) VAW_LN_BWD(3);
-  else if (D <= 768) VAW_LN_BWD(6);
-  else if (D <= 1152) VAW_LN_BWD(9);
-  else VAW_LN_BWD(16);
-#undef VAW_LN_BWD
+  VAW_CHECK_ARG((rows_per_group + chunks - 1) / chunks <= kBwdMaxRows,
+                "vaw_ln_bwd: more than %d rows per chunk (rows_per_group=%d chunks=%d)", kBwdMaxRows, rows_per_group,
+                chunks);
+  ln_bwd_kernel<<<dim3(chunks, groups), threads_for_columns(D), 0, stream>>>(
+      (const bf16*)dy, x, mean, rstd, scale, ld_mod, weight, dx_io, add_into, part, rows_per_group, chunks, M, D);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }
@@ -367,17 +370,12 @@ extern "C" int vaw_gate_bwd(const float* dx, const void* y, const float* gate, l
                             float* part, int rows_per_group, int groups, int chunks, int M, int D,
                             cudaStream_t stream) {
   VAW_CHECK_ARG(dx && dy && part && M > 0, "vaw_gate_bwd: bad arguments");
-  VAW_CHECK_ARG(D % 4 == 0 && D <= kMaxD, "vaw_gate_bwd: D=%d must be a multiple of 4 and <= %d", D, kMaxD);
+  VAW_CHECK_ARG(D % 4 == 0, "vaw_gate_bwd: D=%d must be a multiple of 4", D);
   VAW_CHECK_ARG(rows_per_group > 0 && groups > 0 && chunks > 0 && (long long)groups * rows_per_group >= M,
                 "vaw_gate_bwd: bad grouping");
-  const size_t smem = (size_t)8 * 2 * D * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    VAW_CUDA_TRY(cudaFuncSetAttribute(gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * kMaxD * 4));
-    configured = true;
-  }
-  gate_bwd_kernel<<<dim3(chunks, groups), 256, smem, stream>>>(dx, (const bf16*)y, gate, ld_gate, (bf16*)dy, part,
-                                                               rows_per_group, chunks, M, D);
+  gate_bwd_kernel<<<dim3(chunks, groups), threads_for_columns(D), 0, stream>>>(dx, (const bf16*)y, gate, ld_gate,
+                                                                              (bf16*)dy, part, rows_per_group, chunks,
+                                                                              M, D);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }

@@ -97,10 +97,10 @@ struct Carver {
 };
 
 int ln_chunks(const vaw_dit_cfg& c) {
-  // (chunks x B) CTAs of the LN / gate backward kernels; 2 CTAs are resident per SM: stay within one wave
-  int ch = (2 * vaw_num_sms()) / c.B;
-  if (ch < 1) ch = 1;
-  while (ch > 1 && (c.T + ch - 1) / ch < 16) --ch;
+  // (chunks x B) CTAs of the LN / gate backward kernels, ~32 rows each: enough CTAs to fill the chip several times
+  // over at high occupancy, few enough that the per-CTA partial sums stay small
+  int ch = (c.T + 31) / 32;
+  while ((c.T + ch - 1) / ch > 64) ++ch;
   return ch;
 }
 int colsum_rows(int M, int N) {
