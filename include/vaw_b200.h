@@ -190,6 +190,8 @@ int vaw_cond_bwd(const float* dc_silu, const float* c, float* dc, void* dc_bf16,
 int vaw_embedding_grad(const float* dc, const long long* labels, float* dtable, int rows, int B, int D, int accumulate,
                        vaw_stream_t stream);
 int vaw_cast_f32_bf16(const float* src, void* dst, long long n, vaw_stream_t stream);
+int vaw_cast_f32_bf16_2d(const float* src, long long lds, void* dst, long long ldd, int rows, int cols,
+                         vaw_stream_t stream);
 int vaw_add_bf16_into_f32(const void* src, float* dst, long long n, vaw_stream_t stream);
 
 /* ---- K5: REPA alignment loss, type 'mse' (tools/gaussian_diffusion.py:1011-1013) ------------------------------------
@@ -224,6 +226,40 @@ int vaw_dit_forward(const vaw_dit_cfg* cfg, const float* P, const void* Pb, void
  * events: NULL or depth+1 cudaEvent_t recorded as each block's gradients (last block first) become final.          */
 int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const void* Pb, float* G, void* ws, const void* dout,
                      const void* dzs, const long long* y, int accumulate, void** events, vaw_stream_t stream);
+
+/* ---- U-ViT engine (models/uvit.py:139-250) and its glue kernels ---------------------------------------------------- */
+typedef struct vaw_uvit_cfg {
+  int B, T, D, H, depth, hidden; /* T counts the extra tokens; depth = number of blocks (odd) */
+  int C, P, img_h, img_w;
+  int extras, table_rows; /* 1 = time token, 2 = label + time tokens */
+  int conv;               /* final 3x3 convolution (uvit.py:192) */
+} vaw_uvit_cfg;
+int vaw_uvit_param_layout(const vaw_uvit_cfg* cfg, long long* offsets, long long* numels, int cap, int* n_out,
+                          long long* total);
+int vaw_uvit_workspace_bytes(const vaw_uvit_cfg* cfg, long long* bytes);
+/* x_t fp32 [B,C,H,W], t fp32 [B], y int64 [B] (extras == 2) -> out fp32 [B,C,H,W] */
+int vaw_uvit_forward(const vaw_uvit_cfg* cfg, const float* P, const void* Pb, void* ws, const float* x_t,
+                     const float* t, const long long* y, float* out, vaw_stream_t stream);
+int vaw_uvit_backward(const vaw_uvit_cfg* cfg, const float* P, const void* Pb, float* G, void* ws, const float* dout,
+                      const long long* y, int accumulate, vaw_stream_t stream);
+/* token assembly [label, time, patches] + pos_embed (uvit.py:221-231) and its backward pieces */
+int vaw_uvit_assemble(const float* patch_tok, const float* t, const float* table, const long long* labels,
+                      const float* pos, float* x0, int B, int T, int extras, int D, vaw_stream_t stream);
+int vaw_uvit_pos_grad(const float* dx0, float* dpos, int B, int T, int D, int accumulate, vaw_stream_t stream);
+int vaw_uvit_gather_patch_grad(const float* dx0, void* dtok, int B, int T, int extras, int D, vaw_stream_t stream);
+int vaw_embedding_grad_strided(const float* dc, long long ld, const long long* labels, float* dtable, int rows, int B,
+                               int D, int accumulate, vaw_stream_t stream);
+/* skip_linear operand cat([x, skip]) (uvit.py:117-118) and the column split of its gradient */
+int vaw_cat_cast(const float* x, const float* skip, void* cat, long long M, int D, vaw_stream_t stream);
+int vaw_unpack_cols(const void* src, long long ld, int col_off, float* dst, long long M, int D, int accumulate,
+                    vaw_stream_t stream);
+int vaw_unpatchify_strided(void* tokens, int tok_dtype, void* image, int img_dtype, int B, int C, int H, int W, int P,
+                           int to_image, int row0, int rows_per_sample, int zero_extras, vaw_stream_t stream);
+/* final 3x3 convolution (uvit.py:192,248): forward / input gradient (transpose = 1) / weight + bias gradient */
+int vaw_conv3x3(const float* in, const float* w, const float* bias, float* out, int B, int C, int H, int W,
+                int transpose, vaw_stream_t stream);
+int vaw_conv3x3_wgrad(const float* in, const float* dout, float* dw, float* dbias, int B, int C, int H, int W,
+                      int accumulate, vaw_stream_t stream);
 
 unsigned long long vaw_launch_count(void); /* kernels launched by this library in this process */
 

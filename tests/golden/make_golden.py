@@ -25,6 +25,7 @@ import torch
 import tools.gaussian_diffusion as rgd   # noqa: E402  (reference)
 import tools.resample as rrs             # noqa: E402  (reference)
 import models.dit as rdit                # noqa: E402  (reference)
+import models.uvit as ruvit              # noqa: E402  (reference)
 
 
 def ref_args(**kw):
@@ -155,7 +156,33 @@ def dit_golden():
     print("dit_golden.npz", len(out), "arrays")
 
 
+def uvit_golden():
+    torch.manual_seed(4)
+    m = ruvit.UViT(image_size=8, patch_size=2, in_channels=4, embed_dim=64, depth=3, num_heads=1, mlp_ratio=4,
+                   num_classes=10, class_dropout_prob=0.0)
+    m.train()
+    g = torch.Generator().manual_seed(10)
+    x0 = torch.randn(3, 4, 8, 8, generator=g)
+    eps = torch.randn(3, 4, 8, 8, generator=g)
+    t = torch.tensor([7, 450, 985])
+    y = torch.tensor([2, 9, 0])
+    out = {f"param::{k}": v.detach().numpy() for k, v in m.state_dict().items()}
+    out.update(x0=x0.numpy(), eps=eps.numpy(), t=t.numpy(), y=y.numpy())
+    d = make_diffusion("linear", "EPSILON", weight_type="lambda")
+    x_t = d.q_sample(x0, t, eps)
+    out["fwd_out"] = m(x_t, d._scale_timesteps(t), y).detach().numpy()
+    terms = d.training_losses(m, x0, None, t=t, model_kwargs={"y": y}, noise=eps)
+    terms["loss"].mean().backward()
+    out["mse"], out["loss"] = terms["mse"].detach().numpy(), terms["loss"].detach().numpy()
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            out[f"grad::{k}"] = p.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "uvit_golden.npz"), **out)
+    print("uvit_golden.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
+    uvit_golden()
     diffusion_golden()
     sampler_golden()
     dit_golden()

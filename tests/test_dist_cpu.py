@@ -41,7 +41,7 @@ def _worker(rank, world, port, q):
         assert gt[valid].tolist() == [i for r in range(world) for i in range(3 + 2 * r)]
         # --- bucketed gradient averaging + no_sync window
         g = torch.arange(10, dtype=torch.float32) * (rank + 1)
-        sync = FlatGradSync(g, [(6, 10), (0, 6)])
+        sync = FlatGradSync(g, [[(6, 8), (8, 10)], (0, 6)])
         with sync.no_sync():
             sync.launch()
         assert torch.equal(g, torch.arange(10, dtype=torch.float32) * (rank + 1))

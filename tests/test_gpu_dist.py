@@ -1,0 +1,87 @@
+"""GPU tier, needs >= 2 GPUs (skipped otherwise): data-parallel parity over NCCL.
+  * per-rank gradients after the bucketed all-reduce == gradients of one process on the concatenated batch
+  * the loss-aware sampler's history is identical on all ranks and equals the single-process update applied to the
+    rank-ordered concatenation of (t, loss) (reference resample.py:76-79)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "variance-aware-weight_b200"), os.path.join(ROOT, "tests")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from gpu_util import dezero, relerr
+        from oracle import resample as ors
+        from oracle.train_step import synthetic_history
+        from vaw_b200.models.dit import DiT
+        from vaw_b200.optim import DataParallel
+        from vaw_b200.tools import gaussian_diffusion as gd, resample as rs
+        torch.manual_seed(100 + rank)  # different init per rank: the wrapper must broadcast rank 0's weights
+        m = DiT(image_size=16, patch_size=2, in_channels=4, hidden_size=128, depth=3, num_heads=2, class_dropout_prob=0.0,
+                num_classes=10).to(dev).train()
+        dezero(m)
+        net = DataParallel(m)
+        w0 = m.blocks[0].mlp.fc1.weight.detach().clone()
+        ws = [torch.empty_like(w0) for _ in range(world)]
+        dist.all_gather(ws, w0)
+        assert all(torch.equal(ws[0], x) for x in ws), "weights not broadcast"
+        B = 4
+        g = torch.Generator().manual_seed(7)
+        X = torch.randn(world * B, 4, 16, 16, generator=g); Y = torch.randint(0, 10, (world * B,), generator=g)
+        E = torch.randn(world * B, 4, 16, 16, generator=g); T = torch.randint(0, 1000, (world * B,), generator=g)
+        d = gd.create_gaussian_diffusion(noise_schedule="cosine")
+        sl = slice(rank * B, (rank + 1) * B)
+        terms = d.training_losses(net, X[sl].to(dev), None, t=T[sl].to(dev), model_kwargs={"y": Y[sl].to(dev)}, noise=E[sl].to(dev))
+        terms["loss"].mean().backward()
+        torch.cuda.synchronize()
+        dp_grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.requires_grad}
+        # single-process reference on the concatenated batch (same weights), no all-reduce
+        with net.no_sync():
+            for p in m.parameters():
+                p.grad = None
+            terms_all = d.training_losses(net, X.to(dev), None, t=T.to(dev), model_kwargs={"y": Y.to(dev)}, noise=E.to(dev))
+            terms_all["loss"].mean().backward()
+        worst = max(relerr(dp_grads[k], p.grad) for k, p in m.named_parameters() if p.requires_grad)
+        assert worst < 2e-3, f"DP gradient mismatch {worst}"
+        # sampler: identical history on every rank == single-process update with the rank-ordered concatenation
+        s = rs.LossSecondMomentResampler(d)
+        hist, counts = synthetic_history(0)
+        s.load_history(hist, counts, dev)
+        s.update_with_local_losses(T[sl].to(dev), terms["loss"].detach())
+        all_losses = [torch.empty(B, device=dev) for _ in range(world)]
+        dist.all_gather(all_losses, terms["loss"].detach())
+        h_ref, c_ref = ors.update_history(hist.copy(), counts.copy(), T.tolist(), torch.cat(all_losses).cpu().tolist())
+        assert np.array_equal(s._loss_history, h_ref) and np.array_equal(s._loss_counts, c_ref)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_data_parallel_parity():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res

@@ -97,3 +97,21 @@ def test_dit_constructors_and_geometry():
         assert m.y_embedder.embedding_table.weight.shape == (1001, D)  # +1 row for the dropped label (dit.py:89-90)
     with pytest.raises(AssertionError):
         vdit.DiT(learn_align=True, encoder_depth=0, depth=1, hidden_size=64, num_heads=1)
+
+
+def test_uvit_state_dict_names_and_shapes_match_reference():
+    from vaw_b200.models import uvit as vuvit
+    g = np.load(os.path.join(G, "uvit_golden.npz"))
+    ref = {k[len("param::"):]: g[k].shape for k in g.files if k.startswith("param::")}
+    m = vuvit.UViT(image_size=8, patch_size=2, in_channels=4, embed_dim=64, depth=3, num_heads=1, mlp_ratio=4,
+                   num_classes=10, class_dropout_prob=0.0)
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert set(mine) == set(ref), set(mine) ^ set(ref)
+    for k in ref:
+        assert mine[k] == tuple(ref[k]), k
+    m.load_state_dict({k: torch.from_numpy(g["param::" + k]) for k in ref})
+    mm = vuvit.UViT_M(image_size=64, patch_size=4, in_channels=3, num_classes=1000, class_dropout_prob=0.0)
+    assert (mm.embed_dim, mm.num_blocks, mm.num_heads, mm.pos_embed.shape[1]) == (768, 17, 12, 258)
+    assert sum(p.numel() for p in mm.parameters()) == 130_940_979 or abs(sum(p.numel() for p in mm.parameters()) - 130.94e6) < 0.05e6
+    with pytest.raises(NotImplementedError):
+        vuvit.UViT(mlp_time_embed=True)

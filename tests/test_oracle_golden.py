@@ -152,3 +152,25 @@ def test_dit_oracle_matches_reference_forward_and_grads():
             assert np.linalg.norm(got - ref) / denom < 1e-5, k
             checked += 1
     assert checked > 30
+
+
+def test_uvit_oracle_matches_reference_forward_and_grads():
+    from oracle.uvit import uvit_forward
+    g = np.load(os.path.join(G, "uvit_golden.npz"))
+    sd = {k[len("param::"):]: torch.from_numpy(g[k]).clone().requires_grad_(True) for k in g.files if k.startswith("param::")}
+    tb = odiff.tables(odiff.named_beta_schedule("linear", 1000))
+    x0, eps, t, y = (torch.from_numpy(g[k]) for k in ("x0", "eps", "t", "y"))
+    kw = dict(patch_size=2, num_heads=1, depth=3)
+    x_t = torch.from_numpy(odiff.q_sample(tb, x0.numpy(), t.numpy(), eps.numpy()))
+    out = uvit_forward(sd, x_t, t.float(), y, **kw)
+    np.testing.assert_allclose(out.detach().numpy(), g["fwd_out"], rtol=1e-5, atol=1e-6)
+    terms = odiff.training_losses_torch(tb, "EPSILON", "lambda", lambda xt, ts: uvit_forward(sd, xt, ts, y, **kw), x0, t, eps)
+    terms["loss"].mean().backward()
+    np.testing.assert_allclose(terms["mse"].detach().numpy(), g["mse"], rtol=1e-5)
+    n = 0
+    for k in g.files:
+        if k.startswith("grad::"):
+            ref, got = g[k], sd[k[len("grad::"):]].grad.numpy()
+            assert np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-12) < 1e-5, k
+            n += 1
+    assert n > 40

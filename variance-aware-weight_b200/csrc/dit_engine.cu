@@ -11,6 +11,7 @@
 // every GEMM operand is bf16, every reduction fp32.
 #include "vaw_common.cuh"
 #include "vaw_internal.h"
+#include "engine_common.cuh"
 
 namespace {
 
@@ -85,16 +86,6 @@ struct Ws {
   long long bytes;
 };
 
-struct Carver {
-  uint8_t* base;
-  long long cur = 0;
-  template <typename T>
-  T* take(long long n) {
-    T* p = base ? reinterpret_cast<T*>(base + cur) : nullptr;
-    cur += (n * (long long)sizeof(T) + 255) / 256 * 256;
-    return p;
-  }
-};
 
 int ln_chunks(const vaw_dit_cfg& c) {
   // (chunks x B) CTAs of the LN / gate backward kernels, ~32 rows each: enough CTAs to fill the chip several times
@@ -102,15 +93,6 @@ int ln_chunks(const vaw_dit_cfg& c) {
   int ch = (c.T + 31) / 32;
   while ((c.T + ch - 1) / ch > 64) ++ch;
   return ch;
-}
-int colsum_rows(int M, int N) {
-  const int strips = (N + 63) / 64;
-  int chunks = (4 * vaw_num_sms() + strips - 1) / strips;
-  if (chunks < 1) chunks = 1;
-  int rows = (M + chunks - 1) / chunks;
-  rows = (rows + 7) / 8 * 8;
-  if (rows < 8) rows = 8;
-  return rows;
 }
 
 void carve(const vaw_dit_cfg& c, void* base, Ws& w) {
@@ -186,36 +168,6 @@ int check_cfg(const vaw_dit_cfg* c) {
                 "dit: bad REPA projector config");
   return VAW_OK;
 }
-
-struct G {  // small GEMM call builder
-  vaw_gemm_args a;
-  G(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M, int N, int K, int epi) {
-    memset(&a, 0, sizeof(a));
-    a.A = A; a.lda = lda; a.a_mn = a_mn; a.B = B; a.ldb = ldb; a.b_mn = b_mn;
-    a.M = M; a.N = N; a.K = K; a.epilogue = epi;
-  }
-  G& out(void* o, void* o2 = nullptr) { a.out = o; a.out2 = o2; return *this; }
-  G& bias(const float* b) { a.bias = b; return *this; }
-  G& resid(const float* r, int mod = 0) { a.resid = r; a.resid_mod = mod; return *this; }
-  G& gate(const float* g, long long ldg, int rps) { a.gate = g; a.ldg = ldg; a.rows_per_sample = rps; return *this; }
-  G& aux(const void* x) { a.aux = x; return *this; }
-  G& acc(int f) { a.accumulate = f; return *this; }
-  // split-K policy ("tail split"): whole tiles for the full waves, the partial last wave (or, for skinny GEMMs, every
-  // tile) split along K so that all SMs stay busy; partials are folded in fixed order
-  G& autosplit(float* ws, long long ws_elems) {
-    a.split_ws = ws;
-    a.split_ws_elems = ws_elems;
-    a.k_splits = -1;
-    return *this;
-  }
-  int run(cudaStream_t s) { return vaw_gemm_bf16(&a, s); }
-};
-
-#define TRY(expr)            \
-  do {                       \
-    int _rc = (expr);        \
-    if (_rc != VAW_OK) return _rc; \
-  } while (0)
 
 }  // namespace
 
@@ -399,16 +351,22 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
     TRY(vaw_ln_bwd(w.dxn, w.x[2 * i], b.mean1, b.rstd1, mod + D, ldm, nullptr, w.dx, 1, w.part, T, B, ch, M, D, s));
     TRY(vaw_finish_group(w.part, 0, B, ch, D, dmod, ldm, 0, s));      // d shift_msa
     TRY(vaw_finish_group(w.part, 1, B, ch, D, dmod + D, ldm, 0, s));  // d scale_msa
+    // adaLN_modulation.1 of this block: mod_i = silu(c) W_i^T + b_i.  Its gradient is final here, so the block's
+    // whole parameter set can be all-reduced while the remaining blocks are still in backward.
+    {
+      bf16* dmod_b = w.dmod_all_b + (long long)i * 6 * D;
+      TRY(vaw_cast_f32_bf16_2d(dmod, ldm, dmod_b, ldm, B, 6 * D, s));
+      TRY(vaw_colsum_f32_small(dmod, ldm, B, 6 * D, Gd + L.off[P_ADA_B] + (long long)i * 6 * D, acc, s));
+      TRY(G(dmod_b, ldm, 1, w.c_silu, D, 1, 6 * D, D, B, VAW_EPI_F32)
+              .out(Gd + L.off[P_ADA_W] + (long long)i * 6 * D * D).acc(acc).run(s));
+    }
     if (events && events[i]) VAW_CUDA_TRY(cudaEventRecord(reinterpret_cast<cudaEvent_t>(events[i]), s));
   }
 
   // ---- adaLN linears: mod = silu(c) W^T + b ----
   const int NA = c.depth * 6 * D;
-  TRY(vaw_cast_f32_bf16(w.dmod_all, w.dmod_all_b, (long long)B * NA, s));
   TRY(vaw_cast_f32_bf16(w.dmod_final, w.dmod_final_b, (long long)B * 2 * D, s));
-  TRY(vaw_colsum_f32_small(w.dmod_all, NA, B, NA, Gd + L.off[P_ADA_B], acc, s));
   TRY(vaw_colsum_f32_small(w.dmod_final, 2LL * D, B, 2 * D, Gd + L.off[P_FADA_B], acc, s));
-  TRY(G(w.dmod_all_b, NA, 1, w.c_silu, D, 1, NA, D, B, VAW_EPI_F32).out(Gd + L.off[P_ADA_W]).acc(acc).run(s));
   TRY(G(w.dmod_final_b, 2LL * D, 1, w.c_silu, D, 1, 2 * D, D, B, VAW_EPI_F32).out(Gd + L.off[P_FADA_W]).acc(acc).run(s));
   TRY(G(w.dmod_all_b, NA, 0, Pb + L.off[P_ADA_W], D, 1, B, D, NA, VAW_EPI_F32).out(w.dcs)
           .autosplit(w.split_ws, w.split_elems).run(s));

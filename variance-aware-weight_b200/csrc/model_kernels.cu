@@ -76,13 +76,13 @@ __global__ void cond_bwd_kernel(const float* __restrict__ dcs, const float* __re
   dc_bf16[i] = __float2bfloat16_rn(v);
 }
 // dense embedding gradient, deterministic: one CTA per table row scans the batch in order
-__global__ void embedding_grad_kernel(const float* __restrict__ dc, const long long* __restrict__ labels,
+__global__ void embedding_grad_kernel(const float* __restrict__ dc, long long ld, const long long* __restrict__ labels,
                                       float* __restrict__ dtable, int B, int D, int accumulate) {
   const int r = blockIdx.x;
   for (int j = threadIdx.x; j < D; j += blockDim.x) {
     float s = 0.f;
     for (int n = 0; n < B; ++n)
-      if (labels[n] == r) s += dc[(long long)n * D + j];
+      if (labels[n] == r) s += dc[(long long)n * ld + j];
     float* o = dtable + (long long)r * D + j;
     *o = accumulate ? *o + s : s;
   }
@@ -101,6 +101,22 @@ cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long
   }
   for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// strided 2-D cast: dst[r, c] = bf16(src[r, c]) for a [rows, cols] window of row-major matrices
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_2d_kernel(const float* __restrict__ src, long long lds, bf16* __restrict__ dst, long long ldd, int rows,
+                        int cols) {
+  const int c4 = cols >> 2;
+  const long long total = (long long)rows * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c4), c = (int)(i % c4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src + (long long)r * lds + c);
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + (long long)r * ldd + c) = o;
+  }
 }
 
 // dst(fp32) += src(bf16)
@@ -263,7 +279,16 @@ extern "C" int vaw_cond_bwd(const float* dc_silu, const float* c, float* dc, voi
 extern "C" int vaw_embedding_grad(const float* dc, const long long* labels, float* dtable, int rows, int B, int D,
                                   int accumulate, cudaStream_t stream) {
   VAW_CHECK_ARG(dc && labels && dtable && rows > 0 && B > 0 && D > 0, "vaw_embedding_grad: bad arguments");
-  embedding_grad_kernel<<<rows, 128, 0, stream>>>(dc, labels, dtable, B, D, accumulate);
+  embedding_grad_kernel<<<rows, 128, 0, stream>>>(dc, (long long)D, labels, dtable, B, D, accumulate);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+// same with a row stride ld for dc (U-ViT: the label token's gradient rows sit T*D apart)
+extern "C" int vaw_embedding_grad_strided(const float* dc, long long ld, const long long* labels, float* dtable, int rows,
+                                          int B, int D, int accumulate, cudaStream_t stream) {
+  VAW_CHECK_ARG(dc && labels && dtable && rows > 0 && B > 0 && D > 0 && ld >= D, "vaw_embedding_grad_strided: bad arguments");
+  embedding_grad_kernel<<<rows, 128, 0, stream>>>(dc, ld, labels, dtable, B, D, accumulate);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }
@@ -273,6 +298,15 @@ extern "C" int vaw_cast_f32_bf16(const float* src, void* dst, long long n, cudaS
   VAW_CHECK_ARG((((uintptr_t)src & 15) | ((uintptr_t)dst & 7)) == 0, "vaw_cast_f32_bf16: misaligned buffers");
   if (n == 0) return VAW_OK;
   cast_f32_bf16_kernel<<<grid_for(n / 4 + 1), 256, 0, stream>>>(src, (bf16*)dst, n);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+extern "C" int vaw_cast_f32_bf16_2d(const float* src, long long lds, void* dst, long long ldd, int rows, int cols,
+                                    cudaStream_t stream) {
+  VAW_CHECK_ARG(src && dst && rows > 0 && cols > 0 && cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0,
+                "vaw_cast_f32_bf16_2d: bad arguments (cols, lds, ldd multiples of 4)");
+  cast_f32_bf16_2d_kernel<<<grid_for((long long)rows * cols / 4), 256, 0, stream>>>(src, lds, (bf16*)dst, ldd, rows, cols);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }

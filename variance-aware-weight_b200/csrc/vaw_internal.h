@@ -32,6 +32,14 @@ enum : int {
   VAW_EPI_RES = 5, VAW_EPI_DGELU_TANH = 6, VAW_EPI_DGELU_ERF = 7, VAW_EPI_SILU = 8, VAW_EPI_DSILU = 9
 };
 
+// U-ViT geometry (models/uvit.py:139-205)
+struct vaw_uvit_cfg {
+  int B, T, D, H, depth, hidden;   // batch, tokens/sample incl. extras, width, heads, blocks (odd), mlp hidden
+  int C, P, img_h, img_w;          // channels, patch size, image size
+  int extras, table_rows;          // 1 (time token) or 2 (label + time); label-embedding rows
+  int conv;                        // 1: final 3x3 convolution (uvit.py:192)
+};
+
 // DiT geometry (models/dit.py:157-204)
 struct vaw_dit_cfg {
   int B, T, D, H, depth, hidden;        // batch, tokens/sample, width, heads, blocks, mlp hidden
@@ -68,7 +76,24 @@ int vaw_cond_combine(const float* t_emb, const float* table, const long long* la
 int vaw_cond_bwd(const float* dc_silu, const float* c, float* dc, void* dc_bf16, int n, cudaStream_t stream);
 int vaw_embedding_grad(const float* dc, const long long* labels, float* dtable, int rows, int B, int D, int accumulate,
                        cudaStream_t stream);
+int vaw_embedding_grad_strided(const float* dc, long long ld, const long long* labels, float* dtable, int rows, int B,
+                               int D, int accumulate, cudaStream_t stream);
 int vaw_cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
+int vaw_uvit_assemble(const float* patch_tok, const float* t, const float* table, const long long* labels,
+                      const float* pos, float* x0, int B, int T, int extras, int D, cudaStream_t stream);
+int vaw_uvit_pos_grad(const float* dx0, float* dpos, int B, int T, int D, int accumulate, cudaStream_t stream);
+int vaw_uvit_gather_patch_grad(const float* dx0, void* dtok, int B, int T, int extras, int D, cudaStream_t stream);
+int vaw_cat_cast(const float* x, const float* skip, void* cat, long long M, int D, cudaStream_t stream);
+int vaw_unpack_cols(const void* src, long long ld, int col_off, float* dst, long long M, int D, int accumulate,
+                    cudaStream_t stream);
+int vaw_unpatchify_strided(void* tokens, int tok_dtype, void* image, int img_dtype, int B, int C, int H, int W, int P,
+                           int to_image, int row0, int rows_per_sample, int zero_extras, cudaStream_t stream);
+int vaw_conv3x3(const float* in, const float* w, const float* bias, float* out, int B, int C, int H, int W,
+                int transpose, cudaStream_t stream);
+int vaw_conv3x3_wgrad(const float* in, const float* dout, float* dw, float* dbias, int B, int C, int H, int W,
+                      int accumulate, cudaStream_t stream);
+int vaw_cast_f32_bf16_2d(const float* src, long long lds, void* dst, long long ldd, int rows, int cols,
+                         cudaStream_t stream);
 int vaw_add_bf16_into_f32(const void* src, float* dst, long long n, cudaStream_t stream);
 int vaw_colsum_f32_small(const float* a, long long lda, int rows, int N, float* out, int accumulate,
                          cudaStream_t stream);

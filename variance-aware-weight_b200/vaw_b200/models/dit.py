@@ -31,22 +31,7 @@ L.register("vaw_dit_backward", [C.POINTER(DiTCfg)] + [C.c_void_p] * 7 + [C.c_int
 L.register("vaw_cast_f32_bf16", [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p])
 
 
-class _ParamHolder(nn.Module):
-    """Carries `weight` / `bias` so that state_dict keys match the reference; computes nothing itself."""
-
-    def __init__(self, weight_shape, bias_shape=None):
-        super().__init__()
-        self.weight = nn.Parameter(torch.empty(weight_shape))
-        if bias_shape is not None:
-            self.bias = nn.Parameter(torch.empty(bias_shape))
-
-
-class _Slot(nn.Module):
-    """Placeholder for the parameter-free entries of the reference's nn.Sequential (SiLU) so indices line up."""
-
-
-class _Named(nn.Module):
-    pass
+from ._flat import FlatEngineModule, Named as _Named, ParamHolder as _ParamHolder, Slot as _Slot
 
 
 def _sincos_1d(dim, pos):
@@ -64,7 +49,7 @@ def sincos_pos_embed_2d(dim, grid):
     return np.concatenate([_sincos_1d(dim // 2, mesh[0]), _sincos_1d(dim // 2, mesh[1])], axis=1)
 
 
-class DiT(nn.Module):
+class DiT(FlatEngineModule):
     def __init__(self, image_size=32, patch_size=2, in_channels=4, hidden_size=1152, depth=28, num_heads=16,
                  mlp_ratio=4.0, class_dropout_prob=0.1, num_classes=1000, learn_sigma=False, learn_align=False,
                  encoder_depth=8, z_dims=768, projector_dim=2048):
@@ -128,14 +113,6 @@ class DiT(nn.Module):
                                 table_rows=table_rows, freq_dim=256, learn_align=int(learn_align),
                                 encoder_depth=encoder_depth if learn_align else 0,
                                 proj_dim=projector_dim if learn_align else 0, z_dim=z_dims if learn_align else 0)
-        self._flat = None      # fp32 [n] leaf tensor holding every parameter
-        self._shadow = None    # bf16 [n]
-        self._gflat = None     # fp32 [n]
-        self._shadow_version = -1
-        self._ws = None
-        self._ws_batch = -1
-        self._fwd_serial = 0
-        self._events = None
         self.initialize_weights()
 
     # ------------------------------------------------------------------------------------------------
@@ -185,59 +162,26 @@ class DiT(nn.Module):
                 slots.append((p, off[base + j]))
         return slots, total
 
-    def _ensure_flat(self, device):
-        """(Re)pack the parameters into the flat buffer if they are not already views of it (after .to(), deepcopy,
-        load_state_dict(assign=True) ...)."""
-        slots, total = self._slots()
-        ok = (self._flat is not None and self._flat.device == device and all(
-            p.data_ptr() == self._flat.data_ptr() + 4 * o and p.device == device for p, o in slots))
-        if ok:
-            return
-        flat = torch.zeros(total, dtype=torch.float32, device=device)
-        gflat = torch.zeros(total, dtype=torch.float32, device=device)
-        with torch.no_grad():
-            for p, o in slots:
-                n = p.numel()
-                flat[o:o + n].copy_(p.detach().reshape(-1).to(device=device, dtype=torch.float32))
-                old_grad = p.grad
-                p.data = flat[o:o + n].view(p.shape)
-                if old_grad is not None:
-                    gflat[o:o + n].copy_(old_grad.reshape(-1).to(device=device, dtype=torch.float32))
-                    p.grad = gflat[o:o + n].view(p.shape)
-        flat.requires_grad_(True)
-        self._flat, self._gflat = flat, gflat
-        self._shadow = torch.empty(total, dtype=torch.bfloat16, device=device)
-        self._shadow_version = -1
-        self._slot_cache = slots
-
-    def _refresh_shadow(self):
-        # every in-place update of a parameter (optimizer step, load_state_dict, init) bumps its version counter
-        v = sum(p._version for p, _ in self._slot_cache)
-        if v != self._shadow_version:
-            L.call("vaw_cast_f32_bf16", self._flat.data_ptr(), self._shadow.data_ptr(), self._flat.numel(), L.stream_ptr())
-            self._shadow_version = v
-
-    def _ensure_workspace(self, batch, device):
-        if self._ws is None or self._ws_batch != batch or self._ws.device != device:
-            cfg = self._cfg(batch)
-            nbytes = C.c_longlong()
-            L.call("vaw_dit_workspace_bytes", C.byref(cfg), C.byref(nbytes))
-            self._ws = None
-            self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
-            self._ws_batch = batch
-
-    def flat_parameters(self):
-        """(flat fp32 params, flat fp32 grads, bf16 shadow) — used by the fused optimizer and the DP all-reduce."""
-        return self._flat, self._gflat, self._shadow
+    def _workspace_bytes(self, batch):
+        cfg = self._cfg(batch)
+        nbytes = C.c_longlong()
+        L.call("vaw_dit_workspace_bytes", C.byref(cfg), C.byref(nbytes))
+        return nbytes.value
 
     def block_grad_ranges(self):
-        """Element ranges [(begin, end)] of the flat gradient buffer per transformer block, for bucketed all-reduce."""
+        """Element ranges of the flat gradient buffer that become final with each transformer block (its eight
+        attention / MLP tensors plus its slice of the stacked adaLN weights and biases), the ranges that only become
+        final at the end of backward (embedders, final layer, projectors), and the buffer length."""
         off, num, total = self._layout()
-        ranges = []
+        D = self.hidden_size
+        per_block = []
         for i in range(self.depth):
             base = 20 + 8 * i
-            ranges.append((off[base], off[base + 7] + num[base + 7]))
-        return ranges, (0, off[20]), total
+            per_block.append([(off[base], off[base + 7] + num[base + 7]),
+                              (off[18] + i * 6 * D * D, off[18] + (i + 1) * 6 * D * D),
+                              (off[19] + i * 6 * D, off[19] + (i + 1) * 6 * D)])
+        tail = [(0, off[18])]
+        return per_block, tail, total
 
     # ------------------------------------------------------------------------------------------------
     def initialize_weights(self):
@@ -299,15 +243,6 @@ class DiT(nn.Module):
         out, zs = _DiTFunction.apply(self, x.float().contiguous(), t.float().contiguous(), y, self._flat)
         return out, zs
 
-    # grad bookkeeping used by _DiTFunction.backward
-    def _bind_grads(self):
-        fresh = any(p.grad is None for p, _ in self._slot_cache if p.requires_grad)
-        if fresh:
-            for p, o in self._slot_cache:
-                if p.requires_grad:
-                    p.grad = self._gflat[o:o + p.numel()].view(p.shape)
-        return fresh
-
 
 class _DiTFunction(torch.autograd.Function):
     @staticmethod
@@ -352,7 +287,6 @@ class _DiTFunction(torch.autograd.Function):
         return None, None, None, None, None
 
 
-DiT._post_backward = None
 
 
 def DiT_S(image_size, patch_size, in_channels, class_dropout_prob, num_classes, learn_sigma, **kwargs):

@@ -80,9 +80,9 @@ class DataParallel(torch.nn.Module):
         with torch.no_grad():
             dist.broadcast(m._flat.data, 0, group=self._group)
         m._shadow_version = -1
-        ranges, head, total = m.block_grad_ranges()
-        # gradients become final block L-1 first ... block 0, then everything before the blocks (embedders, adaLN, final)
-        buckets = list(reversed(ranges)) + [head]
+        per_block, tail, total = m.block_grad_ranges()
+        # gradients become final block L-1 first ... block 0, then the embedders / final layer / projectors
+        buckets = list(reversed(per_block)) + [tail]
         self._sync = FlatGradSync(m._gflat, buckets, self._group)
         ev = [torch.cuda.Event() for _ in range(m.depth + 1)]
         for e in ev:

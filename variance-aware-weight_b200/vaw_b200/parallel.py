@@ -55,14 +55,19 @@ def gather_tloss(local_ts: torch.Tensor, local_losses: torch.Tensor, ragged: boo
 class FlatGradSync:
     """Bucketed average all-reduce over a flat gradient buffer.
 
-    buckets: list of (begin, end) element ranges in the order their gradients become final during backward.
+    buckets: list of buckets in the order their gradients become final during backward; a bucket is one (begin, end)
+    element range or a list of ranges (a transformer block's tensors plus its slice of the stacked adaLN weights).
     With CUDA tensors the collectives run on a dedicated stream gated by per-bucket events recorded by the engine;
     call `launch(events)` right after backward was enqueued and `wait()` before the optimizer reads the gradients.
     """
 
     def __init__(self, gflat: torch.Tensor, buckets, process_group=None):
         self.gflat = gflat
-        self.buckets = [(int(b), int(e)) for b, e in buckets if e > b]
+        norm = []
+        for bk in buckets:
+            ranges = [bk] if isinstance(bk[0], (int, float)) else list(bk)
+            norm.append([(int(b), int(e)) for b, e in ranges if e > b])
+        self.buckets = norm
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist_ready() else 1
         self.stream = torch.cuda.Stream() if gflat.is_cuda else None
@@ -89,16 +94,18 @@ class FlatGradSync:
         if not self.enabled or self.world == 1:
             return
         if self.stream is None:
-            for b, e in self.buckets:
-                self._reduce(self.gflat[b:e])
+            for ranges in self.buckets:
+                for b, e in ranges:
+                    self._reduce(self.gflat[b:e])
             return
         with torch.cuda.stream(self.stream):
-            for i, (b, e) in enumerate(self.buckets):
+            for i, ranges in enumerate(self.buckets):
                 if events is not None and events[i] is not None:
                     self.stream.wait_event(events[i])
                 else:
                     self.stream.wait_stream(torch.cuda.default_stream())
-                self._reduce(self.gflat[b:e])
+                for b, e in ranges:
+                    self._reduce(self.gflat[b:e])
 
     def wait(self):
         if self.stream is not None and self.enabled and self.world > 1:
