@@ -9,6 +9,8 @@ installed; see oracle/ref_stubs/README.md).  Everything written here is an input
     diffusion_golden.npz   schedules, tables, compute_mse_loss_weight over all t, q_sample / compute_target,
                            training_losses (+ autograd gradient w.r.t. the model output)
     sampler_golden.npz     LossSecondMomentResampler.weights / sample / update_with_all_losses, UniformSampler.sample
+    unet_golden.npz        two tiny UNets (both attention orders / conditioning styles): weights, forward, losses, grads
+    unet_shapes.json       state-dict names and shapes of every UNet factory (built on the meta device)
     dit_golden.npz         a tiny DiT (with REPA projector): weights, forward outputs, full training_losses + grads
 """
 import os
@@ -22,10 +24,14 @@ sys.path[:0] = [os.path.join(ROOT, "oracle", "ref_stubs"), "/root/reference"]
 import numpy as np
 import torch
 
+sys.path.insert(0, HERE)
+from fill import fill_by_name, grad_digest   # noqa: E402
+
 import tools.gaussian_diffusion as rgd   # noqa: E402  (reference)
 import tools.resample as rrs             # noqa: E402  (reference)
 import models.dit as rdit                # noqa: E402  (reference)
 import models.uvit as ruvit              # noqa: E402  (reference)
+import models.unet as runet              # noqa: E402  (reference)
 
 
 def ref_args(**kw):
@@ -181,7 +187,59 @@ def uvit_golden():
     print("uvit_golden.npz", len(out), "arrays")
 
 
+UNET_CASES = {
+    # the shipped style: scale-shift norm, ResBlock up/down, new attention order, class-conditional
+    "a": dict(image_size=8, num_channels=32, num_res_blocks=1, channel_mult="1,2", in_channels=3, num_classes=10,
+              class_cond=True, attention_resolutions="4", num_heads=2, use_scale_shift_norm=True, resblock_updown=True,
+              use_new_attention_order=True),
+    # the other branches: additive conditioning, conv down/up-sampling, legacy attention order, unconditional
+    "b": dict(image_size=8, num_channels=32, num_res_blocks=1, channel_mult="1,2", in_channels=3, num_classes=10,
+              class_cond=False, attention_resolutions="4,8", num_heads=1, num_head_channels=16,
+              use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=False),
+}
+
+
+def unet_golden():
+    out = {}
+    for tag, cfg in UNET_CASES.items():
+        torch.manual_seed(5)
+        m = runet.create_unet_model(**cfg)
+        fill_by_name(m)   # name-keyed deterministic weights (tests/golden/fill.py): the tests refill their own model
+        m.train()
+        g = torch.Generator().manual_seed(12)
+        x0 = torch.randn(3, 3, 8, 8, generator=g)
+        eps = torch.randn(3, 3, 8, 8, generator=g)
+        t = torch.tensor([5, 420, 977])
+        y = torch.tensor([3, 8, 1])
+        kw = {"y": y} if cfg["class_cond"] else {}
+        out.update({f"{tag}::x0": x0.numpy(), f"{tag}::eps": eps.numpy(), f"{tag}::t": t.numpy(), f"{tag}::y": y.numpy()})
+        d = make_diffusion("linear", "EPSILON", weight_type="min_snr_5")
+        x_t = d.q_sample(x0, t, eps)
+        out[f"{tag}::fwd_out"] = m(x_t, d._scale_timesteps(t), **kw).detach().numpy()
+        terms = d.training_losses(m, x0, None, t=t, model_kwargs=kw, noise=eps)
+        terms["loss"].mean().backward()
+        out[f"{tag}::mse"], out[f"{tag}::loss"] = terms["mse"].detach().numpy(), terms["loss"].detach().numpy()
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                out[f"{tag}::grad::{k}"] = grad_digest(p.grad)
+    # parameter names/shapes of every shipped factory (checkpoint compatibility), no values
+    shapes = {}
+    for name, fn in runet.UNet_models.items():
+        with torch.device("meta"):
+            mm = fn()
+        shapes[name] = {k: list(v.shape) for k, v in mm.state_dict().items()}
+    import json
+    with open(os.path.join(HERE, "unet_shapes.json"), "w") as f:
+        json.dump(shapes, f, separators=(",", ":"))
+    np.savez_compressed(os.path.join(HERE, "unet_golden.npz"), **out)
+    print("unet_golden.npz", len(out), "arrays; unet_shapes.json", {k: len(v) for k, v in shapes.items()})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "unet":
+        unet_golden()
+        sys.exit(0)
+    unet_golden()
     uvit_golden()
     diffusion_golden()
     sampler_golden()

@@ -96,6 +96,14 @@ def call(name: str, *args) -> None:
         raise VawError(f"{name} failed ({rc}): {msg.decode() if msg else ''}")
 
 
+def launch_count() -> int:
+    """Kernels launched by the library in this process (include/vaw_b200.h: vaw_launch_count)."""
+    fn = lib().vaw_launch_count
+    fn.restype = C.c_ulonglong
+    fn.argtypes = []
+    return int(fn())
+
+
 def ptr(t) -> int | None:
     """Device (or host) pointer of a torch tensor / numpy array, None -> NULL."""
     if t is None:
