@@ -95,3 +95,15 @@ def test_warmup_transition_and_idempotent_weights():
     hist2 = hist.copy(); hist2[123, 9] = np.float64(np.float32(0.25))
     assert np.array_equal(w1, ors.second_moment_weights(hist2, np.full(1000, 10)))
     assert abs(w1.sum() - 1.0) < 1e-12
+
+
+def test_history_survives_device_spelling():
+    """'cuda' and 'cuda:0' name the same device: alternating them between sample() and update must not reset the
+    device-resident history (regression)."""
+    d = gd.create_gaussian_diffusion()
+    s = rs.LossSecondMomentResampler(d)
+    np.random.seed(1)
+    for i in range(4):
+        t, _ = s.sample(16, "cuda" if i % 2 == 0 else torch.device("cuda", 0))
+        s.update_with_local_losses(t, torch.rand(16, device="cuda"))
+    assert int(s._loss_counts.sum()) == 64

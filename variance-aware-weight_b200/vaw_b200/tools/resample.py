@@ -106,7 +106,10 @@ class LossSecondMomentResampler(LossAwareSampler):
         device = th.device(device)
         if device.type != "cuda":
             raise L.VawError("LossSecondMomentResampler keeps its history on a CUDA device (no CPU fallback)")
+        if device.index is None:   # "cuda" and "cuda:<current>" are the same place; compare like with like
+            device = th.device("cuda", th.cuda.current_device())
         if self._hist_dev is None or self._hist_dev.device != device:
+            self._sync_host()      # moving devices carries the history along
             self._hist_dev = th.from_numpy(self._host_hist).to(device).contiguous()
             self._count_dev = th.from_numpy(self._host_counts.astype(np.int32)).to(device).contiguous()
 
