@@ -1,0 +1,116 @@
+"""GPU tier: the HBM-bound row kernels of a block (LayerNorm forward/backward with adaLN modulate or affine, the
+gate*branch backward, the partial-sum finishers) through the C ABI, against fp32 torch on the same inputs.
+Covers the shared-memory staged LayerNorm backward (D % 8 == 0) and its two-pass fallback (D % 8 == 4)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from gpu_util import relerr
+from vaw_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+P = C.c_void_p
+L.register("vaw_ln_fwd", [P] * 3 + [C.c_longlong, C.c_int] + [P] * 5 + [C.c_int, C.c_int, C.c_float, P])
+L.register("vaw_ln_bwd", [P] * 5 + [C.c_longlong] + [P] * 2 + [C.c_int, P] + [C.c_int] * 5 + [P])
+L.register("vaw_gate_bwd", [P] * 3 + [C.c_longlong] + [P] * 2 + [C.c_int] * 5 + [P])
+L.register("vaw_finish_group", [P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_longlong, C.c_int, P])
+L.register("vaw_finish_all", [P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_longlong, P, C.c_int, P])
+
+
+def _ln_ref(x, A, Bv, eps=1e-6):
+    xh = torch.nn.functional.layer_norm(x, x.shape[-1:], eps=eps)
+    return xh * A + Bv, xh
+
+
+@pytest.mark.parametrize("B,T,D,chunks,mode", [
+    (4, 256, 1152, 8, "mod"), (3, 258, 768, 9, "mod"), (5, 64, 384, 2, "mod"), (2, 100, 132, 4, "mod"),
+    (1, 37, 1152, 3, "affine"), (6, 17, 512, 1, "affine"), (2, 257, 1536, 5, "plain"), (2, 64, 2048, 2, "mod"),
+    (3, 300, 128, 1, "mod"),
+])
+@pytest.mark.parametrize("add_into", [0, 1])
+def test_layernorm_fwd_bwd(B, T, D, chunks, mode, add_into):
+    torch.manual_seed(B * 1000 + D)
+    M = B * T
+    x = torch.randn(M, D, device=DEV) * 1.5 + 0.3
+    mod = torch.randn(B, 3 * D, device=DEV) * 0.3
+    shift, scale = mod[:, :D], mod[:, D:2 * D]
+    w, b = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
+    y = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    st = L.stream_ptr()
+    if mode == "mod":
+        L.call("vaw_ln_fwd", x.data_ptr(), shift.data_ptr(), scale.data_ptr(), 3 * D, T, None, None, y.data_ptr(),
+               mean.data_ptr(), rstd.data_ptr(), M, D, 1e-6, st)
+        A = (1 + scale).repeat_interleave(T, 0); Bv = shift.repeat_interleave(T, 0)
+        groups, rpg = B, T
+    elif mode == "affine":
+        L.call("vaw_ln_fwd", x.data_ptr(), None, None, 0, 1, w.data_ptr(), b.data_ptr(), y.data_ptr(),
+               mean.data_ptr(), rstd.data_ptr(), M, D, 1e-6, st)
+        A, Bv = w.expand(M, D), b.expand(M, D)
+        groups, rpg = B, T
+    else:
+        L.call("vaw_ln_fwd", x.data_ptr(), None, None, 0, 1, None, None, y.data_ptr(), mean.data_ptr(),
+               rstd.data_ptr(), M, D, 1e-6, st)
+        A, Bv = torch.ones(M, D, device=DEV), torch.zeros(M, D, device=DEV)
+        groups, rpg = B, T
+    y_ref, xh = _ln_ref(x, A, Bv)
+    assert relerr(y, y_ref) < 4e-3            # bf16 output rounding
+    torch.testing.assert_close(mean, x.mean(1), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(rstd, (x.var(1, unbiased=False) + 1e-6).rsqrt(), rtol=1e-5, atol=1e-5)
+
+    dy = torch.randn(M, D, device=DEV).bfloat16()
+    dx0 = torch.randn(M, D, device=DEV)
+    dx = dx0.clone()
+    rpc = -(-rpg // chunks)
+    if rpc > 64 and D % 8 != 0:
+        pytest.skip("fallback kernel handles at most 64 rows per chunk")
+    part = torch.full((groups, chunks, 2, D), float("nan"), device=DEV)
+    L.call("vaw_ln_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+           scale.data_ptr() if mode == "mod" else None, 3 * D if mode == "mod" else 0,
+           w.data_ptr() if mode == "affine" else None, dx.data_ptr(), add_into, part.data_ptr(), rpg, groups, chunks,
+           M, D, st)
+    xr = x.clone().requires_grad_(True)
+    yr, _ = _ln_ref(xr, A, Bv)
+    yr.backward(dy.float())
+    want = xr.grad + (dx0 if add_into else 0)
+    assert relerr(dx, want) < 2e-5
+    dyf = dy.float()
+    sum_dy = dyf.view(groups, rpg, D).sum(1)
+    sum_dyxh = (dyf * xh).view(groups, rpg, D).sum(1)
+    assert not torch.isnan(part).any()
+    assert relerr(part[:, :, 0].sum(1), sum_dy) < 1e-5
+    assert relerr(part[:, :, 1].sum(1), sum_dyxh) < 1e-5
+    # finishers: per-group vector and weighted all-group vector
+    out_g = torch.zeros(groups, D, device=DEV)
+    L.call("vaw_finish_group", part.data_ptr(), 1, groups, chunks, D, out_g.data_ptr(), D, 0, st)
+    assert relerr(out_g, sum_dyxh) < 1e-5
+    out_a = torch.ones(D, device=DEV)
+    L.call("vaw_finish_all", part.data_ptr(), 0, groups, chunks, D, None, 0, out_a.data_ptr(), 1, st)
+    assert relerr(out_a, 1 + sum_dy.sum(0)) < 1e-5
+    # determinism: a second run gives the same bits
+    dx2 = dx0.clone(); part2 = torch.empty_like(part)
+    L.call("vaw_ln_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+           scale.data_ptr() if mode == "mod" else None, 3 * D if mode == "mod" else 0,
+           w.data_ptr() if mode == "affine" else None, dx2.data_ptr(), add_into, part2.data_ptr(), rpg, groups, chunks,
+           M, D, st)
+    assert torch.equal(dx, dx2) and torch.equal(part, part2)
+
+
+@pytest.mark.parametrize("B,T,D,chunks,gated", [(4, 256, 1152, 8, True), (3, 258, 768, 9, False), (2, 50, 132, 2, True)])
+def test_gate_bwd(B, T, D, chunks, gated):
+    torch.manual_seed(D)
+    M = B * T
+    dx = torch.randn(M, D, device=DEV)
+    y = torch.randn(M, D, device=DEV).bfloat16()
+    gate = torch.randn(B, 2 * D, device=DEV)[:, D:]
+    dy = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    part = torch.empty(B, chunks, 2, D, device=DEV)
+    L.call("vaw_gate_bwd", dx.data_ptr(), y.data_ptr() if gated else None, gate.data_ptr() if gated else None, 2 * D,
+           dy.data_ptr(), part.data_ptr(), T, B, chunks, M, D, L.stream_ptr())
+    g = gate.repeat_interleave(T, 0) if gated else 1.0
+    assert relerr(dy, dx * g) < 4e-3
+    assert relerr(part[:, :, 0].sum(1), dx.view(B, T, D).sum(1)) < 1e-5
+    if gated:
+        assert relerr(part[:, :, 1].sum(1), (dx * y.float()).view(B, T, D).sum(1)) < 1e-5

@@ -8,6 +8,7 @@
 // no atomics, high occupancy, and a fixed summation order (bit-reproducible gradients).  Per-CTA partials are folded
 // by the finish kernels in fixed order.
 #include "vaw_common.cuh"
+#include "vaw_async.cuh"
 
 namespace {
 
@@ -188,6 +189,169 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const fl
 }
 
 // ---------------------------------------------------------------------------------------------------
+// LayerNorm backward, shared-memory staged (the production path; the kernel above is the fallback for D % 8 != 0).
+// A CTA walks its chunk in sub-chunks of R rows.  The rows of a sub-chunk are contiguous in memory, so x (fp32) and
+// dy (bf16) arrive with two 1-D bulk copies (TMA engine, mbarrier completion) and are read twice from shared memory
+// instead of twice from L2/DRAM (the two-pass version re-fetched ~45 % of its bytes from DRAM, ncu).  Two CTAs per
+// SM: one computes while the other's copies are in flight.
+// Threads form `halves` x nvp column owners: thread (h, cg) owns float4 column cg for rows h, h+halves, ...; column
+// sums stay in registers across sub-chunks and are folded over h in fixed order at the end (deterministic).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kStagedBudget = 110592;  // bytes of staged rows per CTA (2 stages of x fp32 + dy bf16): 2 x 8 rows at D = 1152
+
+__global__ void __launch_bounds__(576, 2)
+ln_bwd_staged_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean_in,
+                     const float* __restrict__ rstd_in, const float* __restrict__ scale, long long ld_mod,
+                     const float* __restrict__ weight, float* __restrict__ dx_io, int add_into,
+                     float* __restrict__ part, int rows_per_group, int chunks, int M, int D, int R, int nvp) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  // stage s: x [R, D] fp32 | dy [R, D] bf16 ; then per stage [4, R] floats (m1, m2, mean, rstd) ; then 2 mbarriers
+  const size_t stage_bytes = (size_t)R * D * 6;
+  float* s_stat_all = reinterpret_cast<float*>(ln_smem + 2 * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + 2 * stage_bytes + (size_t)R * 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int halves = blockDim.x / nvp;
+  const int half = threadIdx.x / nvp, cg = threadIdx.x % nvp;
+  const int chunk = blockIdx.x, group = blockIdx.y;
+  const int nv = D >> 2;
+  const bool owner = cg < nv;
+  const int rows_per_chunk = (rows_per_group + chunks - 1) / chunks;
+  const int c_begin = group * rows_per_group + chunk * rows_per_chunk;
+  const int c_end = min(min(c_begin + rows_per_chunk, (group + 1) * rows_per_group), M);
+  const int nsub = c_end > c_begin ? (c_end - c_begin + R - 1) / R : 0;
+  const float4* Ap = scale ? reinterpret_cast<const float4*>(scale + (long long)group * ld_mod)
+                           : reinterpret_cast<const float4*>(weight);
+  const float add1 = scale ? 1.f : 0.f;
+  const float inv_d = 1.f / (float)D;
+
+  auto issue = [&](int sub) {   // thread 0: bulk copies of sub-chunk `sub` into stage sub & 1
+    const int r0 = c_begin + sub * R;
+    const int nrows = min(R, c_end - r0);
+    uint8_t* st = ln_smem + (size_t)(sub & 1) * stage_bytes;
+    const uint32_t bx = (uint32_t)nrows * D * 4, bd = (uint32_t)nrows * D * 2;
+    mbar_expect_tx(&bars[sub & 1], bx + bd);
+    bulk_g2s(st, x + (long long)r0 * D, bx, &bars[sub & 1]);
+    bulk_g2s(st + (size_t)R * D * 4, dy + (long long)r0 * D, bd, &bars[sub & 1]);
+  };
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init_cta();
+    if (nsub > 0) issue(0);
+    if (nsub > 1) issue(1);
+  }
+  __syncthreads();
+
+  float4 A = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (Ap && owner) {
+    const float4 a = __ldg(Ap + cg);
+    A = make_float4(a.x + add1, a.y + add1, a.z + add1, a.w + add1);
+  }
+  float4 accB = make_float4(0.f, 0.f, 0.f, 0.f), accA = accB;
+
+  for (int sub = 0; sub < nsub; ++sub) {
+    const int r0 = c_begin + sub * R;
+    const int nrows = min(R, c_end - r0);
+    const int stg = sub & 1;
+    const float* sx = reinterpret_cast<const float*>(ln_smem + (size_t)stg * stage_bytes);
+    const bf16* sdy = reinterpret_cast<const bf16*>(ln_smem + (size_t)stg * stage_bytes + (size_t)R * D * 4);
+    float* s_m1 = s_stat_all + stg * 4 * R, *s_m2 = s_m1 + R, *s_mean = s_m1 + 2 * R, *s_rstd = s_m1 + 3 * R;
+    if (threadIdx.x < nrows) {   // row statistics of the forward pass ride along
+      s_mean[threadIdx.x] = mean_in[r0 + threadIdx.x];
+      s_rstd[threadIdx.x] = rstd_in[r0 + threadIdx.x];
+    }
+    mbar_wait(&bars[stg], (uint32_t)(sub >> 1) & 1u);
+    __syncthreads();
+
+    // ---- row statistics: mean(g), mean(g * xhat), one warp per row ----
+    for (int r = warp; r < nrows; r += nwarps) {
+      const float4* xr = reinterpret_cast<const float4*>(sx + (size_t)r * D);
+      const uint2* dyr = reinterpret_cast<const uint2*>(sdy + (size_t)r * D);
+      const float mean = s_mean[r], rstd = s_rstd[r];
+      float s1 = 0.f, s2 = 0.f;
+      for (int idx = lane; idx < nv; idx += 32) {
+        const float4 xv = xr[idx];
+        const uint2 du = dyr[idx];
+        const float2 d0 = unpack_bf16(du.x), d1 = unpack_bf16(du.y);
+        float4 Aw = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (Ap) {
+          const float4 a = __ldg(Ap + idx);
+          Aw = make_float4(a.x + add1, a.y + add1, a.z + add1, a.w + add1);
+        }
+        const float g0 = d0.x * Aw.x, g1 = d0.y * Aw.y, g2 = d1.x * Aw.z, g3 = d1.y * Aw.w;
+        s1 += (g0 + g1) + (g2 + g3);
+        s2 += (g0 * ((xv.x - mean) * rstd) + g1 * ((xv.y - mean) * rstd)) +
+              (g2 * ((xv.z - mean) * rstd) + g3 * ((xv.w - mean) * rstd));
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        s_m1[r] = s1 * inv_d;
+        s_m2[r] = s2 * inv_d;
+      }
+    }
+    __syncthreads();
+
+    // ---- column owners: dx and the column sums, 4 rows per step (dx_io loads issued before the math) ----
+    if (owner) {
+      for (int rb = half; rb < nrows; rb += 4 * halves) {
+        float4 prev[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = rb + j * halves;
+          prev[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (add_into && r < nrows)
+            prev[j] = ldg_stream_f4(reinterpret_cast<const float4*>(dx_io + (long long)(r0 + r) * D) + cg);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = rb + j * halves;
+          if (r < nrows) {
+            const float4 xv = *(reinterpret_cast<const float4*>(sx + (size_t)r * D) + cg);
+            const uint2 du = *(reinterpret_cast<const uint2*>(sdy + (size_t)r * D) + cg);
+            const float2 d0 = unpack_bf16(du.x), d1 = unpack_bf16(du.y);
+            const float mean = s_mean[r], rstd = s_rstd[r], m1 = s_m1[r], m2 = s_m2[r];
+            const float h0 = (xv.x - mean) * rstd, h1 = (xv.y - mean) * rstd, h2 = (xv.z - mean) * rstd,
+                        h3 = (xv.w - mean) * rstd;
+            float4 out;
+            out.x = rstd * (d0.x * A.x - m1 - h0 * m2) + prev[j].x;
+            out.y = rstd * (d0.y * A.y - m1 - h1 * m2) + prev[j].y;
+            out.z = rstd * (d1.x * A.z - m1 - h2 * m2) + prev[j].z;
+            out.w = rstd * (d1.y * A.w - m1 - h3 * m2) + prev[j].w;
+            *(reinterpret_cast<float4*>(dx_io + (long long)(r0 + r) * D) + cg) = out;
+            accB.x += d0.x; accB.y += d0.y; accB.z += d1.x; accB.w += d1.y;
+            accA.x += d0.x * h0; accA.y += d0.y * h1; accA.z += d1.x * h2; accA.w += d1.y * h3;
+          }
+        }
+      }
+    }
+    __syncthreads();   // every read of this stage is done: refill it with the sub-chunk after next
+    if (threadIdx.x == 0 && sub + 2 < nsub) issue(sub + 2);
+  }
+
+  if (!part) return;
+  // fold the halves in fixed order through shared memory (the staged rows are dead now)
+  float4* red = reinterpret_cast<float4*>(ln_smem);   // [halves - 1, 2, nvp] float4
+  if (half > 0 && owner) {
+    red[((half - 1) * 2 + 0) * nvp + cg] = accB;
+    red[((half - 1) * 2 + 1) * nvp + cg] = accA;
+  }
+  __syncthreads();
+  if (half == 0 && owner) {
+    for (int h = 1; h < halves; ++h) {
+      const float4 b = red[((h - 1) * 2 + 0) * nvp + cg], a = red[((h - 1) * 2 + 1) * nvp + cg];
+      accB.x += b.x; accB.y += b.y; accB.z += b.z; accB.w += b.w;
+      accA.x += a.x; accA.y += a.y; accA.z += a.z; accA.w += a.w;
+    }
+    float* dst = part + ((long long)group * chunks + chunk) * 2 * D;
+    *(reinterpret_cast<float4*>(dst) + cg) = accB;
+    *(reinterpret_cast<float4*>(dst + D) + cg) = accA;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Residual-branch backward: dx (fp32 grad of the block output x_out = x_in + gate * y) ->
 //   dy[row, :]   = bf16(dx * gate[n, :])           (operand of the branch's dgrad / wgrad GEMMs)
 //   part[n, chunk, 0, :] = sum_rows dx             (-> bias gradient: db = sum_n gate[n] * s[n])
@@ -357,6 +521,26 @@ extern "C" int vaw_ln_bwd(const void* dy, const float* x, const float* mean, con
   VAW_CHECK_ARG(D % 4 == 0, "vaw_ln_bwd: D=%d must be a multiple of 4", D);
   VAW_CHECK_ARG(rows_per_group > 0 && groups > 0 && chunks > 0 && (long long)groups * rows_per_group >= M,
                 "vaw_ln_bwd: bad grouping");
+  const int nvp = ((D / 4) + 31) / 32 * 32;
+  int R = kStagedBudget / (12 * D);   // rows per stage, two stages
+  if (R > 32) R = 32;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0;
+  if (D % 8 == 0 && R >= 4 && nvp <= 576 && aligned) {
+    int halves = 1;
+    while (halves * 2 * nvp <= 576 && halves * 2 * 4 <= R) halves *= 2;
+    const size_t smem = 2 * (size_t)R * D * 6 + (size_t)R * 32 + 16;
+    static bool configured = false;
+    if (!configured) {
+      VAW_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kStagedBudget + 32 * 32 + 16));
+      configured = true;
+    }
+    ln_bwd_staged_kernel<<<dim3(chunks, groups), halves * nvp, smem, stream>>>(
+        (const bf16*)dy, x, mean, rstd, scale, ld_mod, weight, dx_io, add_into, part, rows_per_group, chunks, M, D, R,
+        nvp);
+    VAW_LAUNCH_CHECK();
+    return VAW_OK;
+  }
   VAW_CHECK_ARG((rows_per_group + chunks - 1) / chunks <= kBwdMaxRows,
                 "vaw_ln_bwd: more than %d rows per chunk (rows_per_group=%d chunks=%d)", kBwdMaxRows, rows_per_group,
                 chunks);

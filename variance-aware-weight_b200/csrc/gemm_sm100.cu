@@ -21,6 +21,7 @@
 // L2, which is what bounds the single-CTA kernel (128x256x16 per 128 cycles needs 96 B/cycle of operand reads plus
 // the same again of TMA writes against a 128 B/cycle shared-memory port).
 #include "vaw_common.cuh"
+#include "vaw_async.cuh"
 #include "vaw_internal.h"
 #include <stdlib.h>
 
@@ -69,18 +70,7 @@ struct EpiParams {
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's leader CTA
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
   asm volatile(
@@ -89,30 +79,6 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-// Bounded wait: a pipeline bug must surface as a trapped kernel (launch failure), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
-  while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > 4000000000ull) __trap();
-  }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -566,6 +532,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 }
 
 // Split-K fix-up (EPI_F32 only): one CTA per split tile sums its `splits` slabs in fixed order and applies
+constexpr int kFixupSlices = 8;
 // bias / accumulate:  out[r, c] = (accumulate ? out : 0) + bias[c] + sum_s slab[s][r, c]
 template <int TM, int BN>
 __global__ void __launch_bounds__(256)
@@ -574,8 +541,9 @@ splitk_fixup_kernel(const float* __restrict__ ws, int first_tile, int splits, in
   const int tile = first_tile + blockIdx.x;
   const int m0 = (tile / n_tiles) * TM, n0 = (tile % n_tiles) * BN;
   const float* base = ws + (long long)blockIdx.x * splits * (TM * BN);
-  for (int i = threadIdx.x; i < TM * BN / 4; i += 256) {
-    const int r = i / (BN / 4), c = (i % (BN / 4)) * 4;
+  constexpr int kRows = TM / kFixupSlices;   // a tile is folded by kFixupSlices CTAs (blockIdx.y), kRows rows each
+  for (int i = threadIdx.x; i < kRows * BN / 4; i += 256) {
+    const int r = blockIdx.y * kRows + i / (BN / 4), c = (i % (BN / 4)) * 4;
     if (m0 + r >= M || n0 + c >= N) continue;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int s = 0; s < splits; ++s) {
@@ -836,7 +804,7 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
     const int rem = tiles - full;
     float* o = reinterpret_cast<float*>(a->out);
 #define VAW_FIXUP(TM_, BN_)                                                                                          \
-  splitk_fixup_kernel<TM_, BN_><<<rem, 256, 0, stream>>>(a->split_ws, full, splits, n_tiles, o, a->bias, a->M, a->N, \
+  splitk_fixup_kernel<TM_, BN_><<<dim3(rem, kFixupSlices), 256, 0, stream>>>(a->split_ws, full, splits, n_tiles, o, a->bias, a->M, a->N, \
                                                          ldo, a->accumulate)
     if (pair) {
       if (bn == 128) VAW_FIXUP(256, 128); else if (bn == 192) VAW_FIXUP(256, 192); else VAW_FIXUP(256, 256);
