@@ -12,6 +12,8 @@
 // Softmax statistics are kept in the log2 domain: L2[q] = max_k(s*c) + log2(sum_k 2^(s*c - max)), c = scale*log2(e),
 // so that P = exp2(s*c - L2) in the backward pass.
 #include "vaw_common.cuh"
+#include "vaw_internal.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -432,6 +434,13 @@ int launch_bwd(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse
 extern "C" int vaw_attn_fwd(const void* qkv, void* o, float* lse2, int B, int T, int H, int head_dim,
                             cudaStream_t stream) {
   VAW_CHECK_ARG(qkv && o && lse2 && B > 0 && T > 0 && H > 0, "vaw_attn_fwd: bad arguments");
+  {  // tcgen05 path for T <= 256 (attention_sm100.cu); VAW_ATTN_LEGACY=1 keeps the mma.sync kernels (A/B testing)
+    static const bool legacy = getenv("VAW_ATTN_LEGACY") && atoi(getenv("VAW_ATTN_LEGACY")) != 0;
+    if (!legacy) {
+      const int rc = vaw_attn_fwd_sm100(qkv, o, lse2, B, T, H, head_dim, stream);
+      if (rc != VAW_ERR_UNSUPPORTED) return rc;
+    }
+  }
   if (head_dim == 64) return launch_fwd<64>((const bf16*)qkv, (bf16*)o, lse2, B, T, H, stream);
   if (head_dim == 72) return launch_fwd<72>((const bf16*)qkv, (bf16*)o, lse2, B, T, H, stream);
   vaw_set_error("vaw_attn_fwd: head_dim %d not supported (64, 72)", head_dim);

@@ -1,0 +1,420 @@
+// attention_sm100.cu — tcgen05 / TMEM self-attention forward for sequences of up to 256 tokens (every DiT config:
+// T = 256, head_dim 64 or 72).  Replaces F.scaled_dot_product_attention inside timm Attention (models/dit.py:126).
+//
+// One CTA = one (batch, head, 128-query tile); two CTAs are resident per SM (100 KB of shared memory and 256 TMEM
+// columns each), so one CTA's softmax overlaps the other's loads and MMAs without any intra-CTA pipeline.
+//   1. TMA (4-D tensor maps over the packed qkv activation [B, T, 3*H, hd], out-of-bounds zero fill) brings the Q tile
+//      and the whole K and V of the head into shared memory.  head_dim 72 is split 64 + 16: a SWIZZLE_128B box for the
+//      first 64 columns and a SWIZZLE_32B box for columns 64..79, of which 72..79 are zero-filled by the TMA unit.
+//   2. S = Q K^T  [128 x Nk] fp32 in TMEM columns [0, Nk): 4 (+1) tcgen05.mma (K = 16 each), both operands K-major.
+//   3. softmax: two threads per query row (TMEM lane = row), one per 128-key half; two passes over the half row with
+//      tcgen05.ld (max, then exp2 / sum, exchanged through shared memory); P is written back as packed bf16 pairs with
+//      tcgen05.st in place of the S columns the same thread has already consumed.
+//   4. O = P V  [128 x hd]: A operand read from TMEM (P), B = V from shared memory (MN-major), accumulator in the
+//      TMEM columns the softmax freed.
+//   5. epilogue: O / rowsum -> bf16 -> out[b, t, h, :]; L2[q] = max*c + log2(rowsum) (log2-domain, see attention.cu).
+#include "vaw_common.cuh"
+#include "vaw_async.cuh"
+#include "vaw_internal.h"
+#include <cuda.h>
+
+namespace {
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]   (A: lane = row, 32-bit column c holds the bf16 pair k = 2c, 2c+1)
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptors (cute/arch/mma_sm100_desc.hpp field layout, see gemm_sm100.cu):
+//   SWIZZLE_128B tiles: rows of 128 B, 8-row groups 1024 B apart (SBO = 1024)
+//   SWIZZLE_32B  tiles: rows of  32 B, 8-row groups  256 B apart (SBO =  256)
+// The same tile serves as a K-major operand (rows = M/N index) or an MN-major operand (rows = K index); LBO (stride
+// between swizzle-wide column blocks) is never exercised here because every operand is one block wide.
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1u << 16) | ((uint64_t)64u << 32) | ((uint64_t)1u << 46) |
+         ((uint64_t)2u << 61);
+}
+__device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1u << 16) | ((uint64_t)16u << 32) | ((uint64_t)1u << 46) |
+         ((uint64_t)6u << 61);
+}
+// instruction descriptor: D fp32, A/B bf16, M = 128
+__device__ __forceinline__ uint32_t idesc_bf16(int n, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// running maximum of one 32-column chunk of a score row (keys >= T are ignored)
+__device__ __forceinline__ void row_max_chunk(const uint32_t (&v)[32], int key0, int T, float& m0, float& m1, float& m2,
+                                              float& m3) {
+  if (key0 + 32 <= T) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      m0 = fmaxf(m0, __uint_as_float(v[j]));
+      m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+      m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+      m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (key0 + j < T) m0 = fmaxf(m0, __uint_as_float(v[j]));
+  }
+}
+// p = 2^(s*c - m*c) for one chunk: packed bf16 pairs for the P operand, fp32 partial row sums
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], uint32_t (&pk)[16], int key0, int T, float c,
+                                              float mneg, float& s0, float& s1, float& s2, float& s3) {
+  if (key0 + 32 <= T) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), c, mneg));
+      const float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), c, mneg));
+      const float p2 = ex2_approx(fmaf(__uint_as_float(v[j + 2]), c, mneg));
+      const float p3 = ex2_approx(fmaf(__uint_as_float(v[j + 3]), c, mneg));
+      s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+      pk[j >> 1] = pack_bf16(p0, p1);
+      pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float p0 = key0 + j < T ? ex2_approx(fmaf(__uint_as_float(v[j]), c, mneg)) : 0.f;
+      const float p1 = key0 + j + 1 < T ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), c, mneg)) : 0.f;
+      s0 += p0; s1 += p1;
+      pk[j >> 1] = pack_bf16(p0, p1);
+    }
+  }
+}
+
+constexpr int kTile = 128;  // query rows per CTA, key rows per TMA box
+constexpr int kMaxKeys = 256;
+
+template <int HD>
+struct Smem {
+  static constexpr bool kTail = HD > 64;
+  static constexpr int kQm = 0;                        // Q  main  [128 x 64]  SW128
+  static constexpr int kKm = kQm + kTile * 128;        // K  main  [256 x 64]
+  static constexpr int kVm = kKm + kMaxKeys * 128;     // V  main  [256 x 64]
+  static constexpr int kQt = kVm + kMaxKeys * 128;     // Q  tail  [128 x 16]  SW32
+  static constexpr int kKt = kQt + (kTail ? kTile * 32 : 0);
+  static constexpr int kVt = kKt + (kTail ? kMaxKeys * 32 : 0);
+  static constexpr int kBars = kVt + (kTail ? kMaxKeys * 32 : 0);
+  static constexpr int kStat = kBars + 64;              // row max / row sum exchange between the two key halves
+  static constexpr int kBytes = kStat + 4 * kTile * 4 + 1024;  // + alignment slack
+};
+
+template <int HD>
+__global__ void __launch_bounds__(256, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_tail,
+                   bf16* __restrict__ o, float* __restrict__ lse2, int T, int H, float scale_log2e) {
+  using S = Smem<HD>;
+  constexpr bool kTail = S::kTail;
+  // TMEM columns after the softmax (S occupied [0, 256)): each key half rewrites its own S columns in place with P
+  //   [0, 64) P keys 0..127 | [64, 80) O tail | [128, 192) P keys 128..255 | [192, 256) O main
+  constexpr int kOCol = 192, kOTailCol = 64, kPHiCol = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + S::kBars);
+  uint64_t* bar_v = bar_qk + 1;
+  uint64_t* bar_s = bar_qk + 2;
+  uint64_t* bar_o = bar_qk + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 4);
+  float* s_max = reinterpret_cast<float*>(smem + S::kStat);
+  float* s_sum = s_max + 2 * kTile;
+
+  const int warp = threadIdx.x >> 5;
+  const int q0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
+  const int nk = (T + 15) & ~15;                 // key columns of S (multiple of 16, <= 256)
+  const int kboxes = (T + kTile - 1) / kTile;    // 128-row TMA boxes holding keys
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_mbar_init_cta();
+    const uint32_t box_bytes = kTile * 128 + (kTail ? kTile * 32 : 0);
+    mbar_expect_tx(bar_qk, box_bytes * (1 + kboxes));
+    tma_load_4d(smem + S::kQm, &tm_main, bar_qk, 0, h, q0, b);
+    if (kTail) tma_load_4d(smem + S::kQt, &tm_tail, bar_qk, 64, h, q0, b);
+    for (int kb = 0; kb < kboxes; ++kb) {
+      tma_load_4d(smem + S::kKm + kb * kTile * 128, &tm_main, bar_qk, 0, H + h, kb * kTile, b);
+      if (kTail) tma_load_4d(smem + S::kKt + kb * kTile * 32, &tm_tail, bar_qk, 64, H + h, kb * kTile, b);
+    }
+    mbar_expect_tx(bar_v, box_bytes * kboxes);
+    for (int kb = 0; kb < kboxes; ++kb) {
+      tma_load_4d(smem + S::kVm + kb * kTile * 128, &tm_main, bar_v, 0, 2 * H + h, kb * kTile, b);
+      if (kTail) tma_load_4d(smem + S::kVt + kb * kTile * 32, &tm_tail, bar_v, 64, 2 * H + h, kb * kTile, b);
+    }
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // ---- S = Q K^T ----
+  if (threadIdx.x == 0) {
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+    const uint32_t id = idesc_bf16(nk, 0);
+    const uint32_t aq = smem_u32(smem + S::kQm), ak = smem_u32(smem + S::kKm);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tc_mma_ss(tmem, desc_sw128(aq + k * 32), desc_sw128(ak + k * 32), id, k ? 1u : 0u);
+    if (kTail) tc_mma_ss(tmem, desc_sw32(smem_u32(smem + S::kQt)), desc_sw32(smem_u32(smem + S::kKt)), id, 1u);
+    tc_commit(bar_s);
+  }
+  __syncwarp();
+
+  // ---- softmax: two threads per query row (TMEM lane = threadIdx.x & 127), each owning one half of the keys ----
+  const int lane_row = threadIdx.x & 127;        // query row inside the tile == TMEM lane
+  const int half = threadIdx.x >> 7;             // 0: key chunks 0..3, 1: key chunks 4..7
+  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int nchunks = (nk + 31) >> 5;
+  const int c_lo = half * 4, c_hi = min(nchunks, half * 4 + 4);
+  mbar_wait(bar_s, 0);
+  __syncwarp();
+  tc_fence_after();
+  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+  {
+    uint32_t va[32], vb[32];
+    if (c_lo < c_hi) tmem_ld32(trow + c_lo * 32, va);
+    for (int c = c_lo; c < c_hi; c += 2) {     // chunk c in va, chunk c + 1 in vb; the next load overlaps the math
+      tmem_ld_wait();
+      if (c + 1 < c_hi) tmem_ld32(trow + (c + 1) * 32, vb);
+      row_max_chunk(va, c * 32, T, mx0, mx1, mx2, mx3);
+      if (c + 1 < c_hi) {
+        tmem_ld_wait();
+        if (c + 2 < c_hi) tmem_ld32(trow + (c + 2) * 32, va);
+        row_max_chunk(vb, (c + 1) * 32, T, mx0, mx1, mx2, mx3);
+      }
+    }
+  }
+  float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+  s_max[half * kTile + lane_row] = mx;
+  __syncthreads();
+  mx = fmaxf(s_max[lane_row], s_max[kTile + lane_row]);
+  const float mneg = -mx * scale_log2e;
+  float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+  {
+    uint32_t va[32], vb[32], pk[16];
+    if (c_lo < c_hi) tmem_ld32(trow + c_lo * 32, va);
+    for (int c = c_lo; c < c_hi; c += 2) {
+      tmem_ld_wait();
+      if (c + 1 < c_hi) tmem_ld32(trow + (c + 1) * 32, vb);
+      softmax_chunk(va, pk, c * 32, T, scale_log2e, mneg, sum0, sum1, sum2, sum3);
+      tmem_st16(trow + half * kPHiCol + (c - c_lo) * 16, pk);
+      if (c + 1 < c_hi) {
+        tmem_ld_wait();
+        if (c + 2 < c_hi) tmem_ld32(trow + (c + 2) * 32, va);
+        softmax_chunk(vb, pk, (c + 1) * 32, T, scale_log2e, mneg, sum0, sum1, sum2, sum3);
+        tmem_st16(trow + half * kPHiCol + (c + 1 - c_lo) * 16, pk);
+      }
+    }
+  }
+  s_sum[half * kTile + lane_row] = (sum0 + sum1) + (sum2 + sum3);
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  const float sum = s_sum[lane_row] + s_sum[kTile + lane_row];
+
+  // ---- O = P V ----
+  if (threadIdx.x == 0) {
+    mbar_wait(bar_v, 0);
+    tc_fence_after();
+    const uint32_t idm = idesc_bf16(64, 1), idt = idesc_bf16(16, 1);
+    const uint32_t av = smem_u32(smem + S::kVm), avt = smem_u32(smem + S::kVt);
+    const int ksteps = nk >> 4;
+    for (int k = 0; k < ksteps; ++k) {
+      const uint32_t pa = tmem + (k < 8 ? k * 8 : kPHiCol + (k - 8) * 8);
+      tc_mma_ts(tmem + kOCol, pa, desc_sw128(av + k * 2048), idm, k ? 1u : 0u);
+      if (kTail) tc_mma_ts(tmem + kOTailCol, pa, desc_sw32(avt + k * 512), idt, k ? 1u : 0u);
+    }
+    tc_commit(bar_o);
+  }
+  __syncwarp();
+  mbar_wait(bar_o, 0);
+  __syncwarp();
+  tc_fence_after();
+
+  // ---- epilogue: half 0 writes head columns [0, 32) (+ the tail), half 1 columns [32, 64) ----
+  const int row = q0 + lane_row;
+  const float inv = 1.f / sum;
+  if (row < T && half == 0) lse2[((long long)b * H + h) * T + row] = mx * scale_log2e + log2f(sum);
+  bf16* orow = o + (((long long)b * T + row) * H + h) * HD;
+  {
+    uint32_t v[32];
+    tmem_ld32(trow + kOCol + half * 32, v);
+    tmem_ld_wait();
+    if (row < T) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 w;
+        w.x = pack_bf16(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+        w.y = pack_bf16(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+        w.z = pack_bf16(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv);
+        w.w = pack_bf16(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + half * 32 + j) = w;
+      }
+    }
+  }
+  if (kTail && half == 0) {   // warp-uniform: a half is four whole warps
+    uint32_t v[16];
+    tmem_ld16(trow + kOTailCol, v);
+    tmem_ld_wait();
+    if (row < T) {
+      uint4 w;
+      w.x = pack_bf16(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+      w.y = pack_bf16(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+      w.z = pack_bf16(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+      w.w = pack_bf16(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+      *reinterpret_cast<uint4*>(orow + 64) = w;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// 4-D bf16 map over a packed activation [B, T, S, hd] (S = slots per token: 3*H for qkv, H for o / dO):
+// dims (hd, S, T, B); box (cols, 1, rows, 1).  Out-of-range columns / rows read as zero.
+int make_head_map(CUtensorMap* map, const void* base, int B, int T, int slots, int hd, int box_cols, int box_rows,
+                  CUtensorMapSwizzle swz) {
+  PFN_encodeTiled fn = encode_fn();
+  if (!fn) {
+    vaw_set_error("cuTensorMapEncodeTiled entry point not available");
+    return VAW_ERR_CUDA;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)hd, (cuuint64_t)slots, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)hd * 2, (cuuint64_t)slots * hd * 2, (cuuint64_t)T * slots * hd * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_cols, 1u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    vaw_set_error("cuTensorMapEncodeTiled (attention, %d-wide box) failed with CUresult %d", box_cols, (int)r);
+    return VAW_ERR_CUDA;
+  }
+  return VAW_OK;
+}
+
+template <int HD>
+int launch_fwd_tc(const void* qkv, void* o, float* lse2, int B, int T, int H, cudaStream_t stream) {
+  using S = Smem<HD>;
+  CUtensorMap tm_main, tm_tail;
+  int rc = make_head_map(&tm_main, qkv, B, T, 3 * H, HD, 64, kTile, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_head_map(&tm_tail, qkv, B, T, 3 * H, HD, 16, kTile, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    VAW_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes));
+    configured = true;
+  }
+  const float scale = 1.0f / sqrtf((float)HD);
+  dim3 grid((T + kTile - 1) / kTile, H, B);
+  attn_fwd_tc_kernel<HD><<<grid, 256, S::kBytes, stream>>>(tm_main, tm_tail, (bf16*)o, lse2, T, H,
+                                                            scale * 1.4426950408889634f);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+}  // namespace
+
+// internal entry (vaw_internal.h): returns VAW_ERR_UNSUPPORTED when the shape is outside this kernel's range
+int vaw_attn_fwd_sm100(const void* qkv, void* o, float* lse2, int B, int T, int H, int head_dim, cudaStream_t stream) {
+  if (T > kMaxKeys || (reinterpret_cast<uintptr_t>(qkv) & 15) != 0 || (reinterpret_cast<uintptr_t>(o) & 15) != 0)
+    return VAW_ERR_UNSUPPORTED;
+  if (head_dim == 64) return launch_fwd_tc<64>(qkv, o, lse2, B, T, H, stream);
+  if (head_dim == 72) return launch_fwd_tc<72>(qkv, o, lse2, B, T, H, stream);
+  return VAW_ERR_UNSUPPORTED;
+}
