@@ -14,107 +14,13 @@
 //      TMEM columns the softmax freed.
 //   5. epilogue: O / rowsum -> bf16 -> out[b, t, h, :]; L2[q] = max*c + log2(rowsum) (log2-domain, see attention.cu).
 #include "vaw_common.cuh"
-#include "vaw_async.cuh"
+#include "vaw_tc5.cuh"
 #include "vaw_internal.h"
-#include <cuda.h>
 
 namespace {
 
-// ---- PTX wrappers -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
-          "r"(smem_u32(smem_dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]
-__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]   (A: lane = row, 32-bit column c holds the bf16 pair k = 2c, 2c+1)
-__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
-      "%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+using namespace tc5;
 
-// UMMA shared-memory descriptors (cute/arch/mma_sm100_desc.hpp field layout, see gemm_sm100.cu):
-//   SWIZZLE_128B tiles: rows of 128 B, 8-row groups 1024 B apart (SBO = 1024)
-//   SWIZZLE_32B  tiles: rows of  32 B, 8-row groups  256 B apart (SBO =  256)
-// The same tile serves as a K-major operand (rows = M/N index) or an MN-major operand (rows = K index); LBO (stride
-// between swizzle-wide column blocks) is never exercised here because every operand is one block wide.
-__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1u << 16) | ((uint64_t)64u << 32) | ((uint64_t)1u << 46) |
-         ((uint64_t)2u << 61);
-}
-__device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1u << 16) | ((uint64_t)16u << 32) | ((uint64_t)1u << 46) |
-         ((uint64_t)6u << 61);
-}
-// instruction descriptor: D fp32, A/B bf16, M = 128
-__device__ __forceinline__ uint32_t idesc_bf16(int n, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(128 >> 4) << 24);
-}
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 // running maximum of one 32-column chunk of a score row (keys >= T are ignored)
 __device__ __forceinline__ void row_max_chunk(const uint32_t (&v)[32], int key0, int T, float& m0, float& m1, float& m2,
                                               float& m3) {
@@ -349,44 +255,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
 }
 
 // ---- host ------------------------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-PFN_encodeTiled encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
-  }
-  return fn;
-}
-
-// 4-D bf16 map over a packed activation [B, T, S, hd] (S = slots per token: 3*H for qkv, H for o / dO):
-// dims (hd, S, T, B); box (cols, 1, rows, 1).  Out-of-range columns / rows read as zero.
-int make_head_map(CUtensorMap* map, const void* base, int B, int T, int slots, int hd, int box_cols, int box_rows,
-                  CUtensorMapSwizzle swz) {
-  PFN_encodeTiled fn = encode_fn();
-  if (!fn) {
-    vaw_set_error("cuTensorMapEncodeTiled entry point not available");
-    return VAW_ERR_CUDA;
-  }
-  cuuint64_t dims[4] = {(cuuint64_t)hd, (cuuint64_t)slots, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)hd * 2, (cuuint64_t)slots * hd * 2, (cuuint64_t)T * slots * hd * 2};
-  cuuint32_t box[4] = {(cuuint32_t)box_cols, 1u, (cuuint32_t)box_rows, 1u};
-  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    vaw_set_error("cuTensorMapEncodeTiled (attention, %d-wide box) failed with CUresult %d", box_cols, (int)r);
-    return VAW_ERR_CUDA;
-  }
-  return VAW_OK;
-}
-
 template <int HD>
 int launch_fwd_tc(const void* qkv, void* o, float* lse2, int B, int T, int H, cudaStream_t stream) {
   using S = Smem<HD>;

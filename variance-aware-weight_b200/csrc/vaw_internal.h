@@ -50,6 +50,8 @@ struct vaw_dit_cfg {
 
 // tcgen05 attention (attention_sm100.cu); VAW_ERR_UNSUPPORTED when the shape is outside its range (T > 256)
 int vaw_attn_fwd_sm100(const void* qkv, void* o, float* lse2, int B, int T, int H, int head_dim, cudaStream_t stream);
+int vaw_attn_bwd_sm100(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int B, int T,
+                       int H, int head_dim, cudaStream_t stream);
 
 extern "C" {
 int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream);
