@@ -156,6 +156,10 @@ int vaw_gemm_bf16(const vaw_gemm_args* args, vaw_stream_t stream);
 int vaw_attn_fwd(const void* qkv, void* o, float* lse2, int B, int T, int H, int head_dim, vaw_stream_t stream);
 int vaw_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int B, int T, int H,
                  int head_dim, vaw_stream_t stream);
+/* Same, with a caller-provided fp32 scratch of B*H*T elements: the row sums Delta = rowsum(dO * O) are then produced by
+ * a separate coalesced pass instead of inside every CTA's prologue (faster; used by the engines). NULL = as above. */
+int vaw_attn_bwd_ws(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, float* delta_ws,
+                    int B, int T, int H, int head_dim, vaw_stream_t stream);
 
 /* ---- K4: LayerNorm (+ adaLN modulate | affine) forward / backward, residual-branch backward, reductions ------------
  * Replace nn.LayerNorm + modulate (models/dit.py:24-25,122-124,133-137,151-155) and nn.LayerNorm(affine)
@@ -262,6 +266,9 @@ int vaw_conv3x3_wgrad(const float* in, const float* dout, float* dw, float* dbia
                       int accumulate, vaw_stream_t stream);
 
 unsigned long long vaw_launch_count(void); /* kernels launched by this library in this process */
+/* debug knob: device buffer of 2 x 64 uint64 globaltimer stamps written by one CTA of the tcgen05 attention backward
+ * (role 0 = an elementwise warp, role 1 = the MMA warp); NULL switches tracing off (the default). */
+int vaw_attn_set_trace(void* device_buf);
 
 #ifdef __cplusplus
 }

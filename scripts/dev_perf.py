@@ -9,6 +9,7 @@ import vaw_b200.models.dit  # registers engine sigs
 dev = "cuda"
 L.register("vaw_attn_fwd", [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p])
 L.register("vaw_attn_bwd", [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p])
+L.register("vaw_attn_bwd_ws", [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p])
 L.register("vaw_ln_fwd", [C.c_void_p] * 3 + [C.c_longlong, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_float, C.c_void_p])
 L.register("vaw_ln_bwd", [C.c_void_p] * 5 + [C.c_longlong] + [C.c_void_p] * 2 + [C.c_int, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p])
 L.register("vaw_gate_bwd", [C.c_void_p] * 3 + [C.c_longlong] + [C.c_void_p] * 2 + [C.c_int] * 5 + [C.c_void_p])
@@ -80,8 +81,8 @@ hd = D // H
 qkv = bf(B, T, 3, H, hd); o = torch.empty(B, T, H, hd, device=dev, dtype=torch.bfloat16); lse = torch.empty(B, H, T, device=dev)
 us = timeit(lambda: L.call("vaw_attn_fwd", qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, H, hd, st()))
 print(f"attn_fwd: {us:.1f} us  {4*B*H*T*T*hd/us/1e6:.0f} TFLOP/s")
-do = bf(B, T, H, hd); dqkv = torch.empty_like(qkv)
-us = timeit(lambda: L.call("vaw_attn_bwd", qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, T, H, hd, st()))
+do = bf(B, T, H, hd); dqkv = torch.empty_like(qkv); dws = torch.empty(B * H * T, device=dev)
+us = timeit(lambda: L.call("vaw_attn_bwd_ws", qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), dws.data_ptr(), B, T, H, hd, st()))
 print(f"attn_bwd: {us:.1f} us  {10*B*H*T*T*hd/us/1e6:.0f} TFLOP/s (5 matmuls counted)")
 
 # whole model

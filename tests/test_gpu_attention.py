@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 L.register("vaw_attn_fwd", [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p])
 L.register("vaw_attn_bwd", [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p])
+L.register("vaw_attn_bwd_ws", [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p])
 
 
 @pytest.mark.parametrize("B,T,H,hd", [(2, 256, 3, 64), (2, 256, 2, 72), (3, 258, 2, 64), (2, 64, 2, 72), (1, 100, 1, 64),
@@ -32,12 +33,48 @@ def test_forward_backward(B, T, H, hd):
     dqkv = torch.full_like(qkv, float("nan"))
     L.call("vaw_attn_bwd", qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, T, H, hd,
            L.stream_ptr())
+    # the variant with a caller-provided Delta scratch (used by the engines) must give the same result
+    dqkv_ws = torch.full_like(qkv, float("nan"))
+    ws = torch.empty(B * H * T, device=DEV)
+    L.call("vaw_attn_bwd_ws", qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv_ws.data_ptr(),
+           ws.data_ptr(), B, T, H, hd, L.stream_ptr())
     ref.backward(do.float().permute(0, 2, 1, 3))
     scale = max(g.abs().max().item() for g in (q.grad, k.grad, v.grad))
-    for i, g in enumerate((q.grad, k.grad, v.grad)):
-        got = dqkv[:, :, i].permute(0, 2, 1, 3).float()
-        # relative to the tensor's norm, with a floor for gradients that are analytically zero (e.g. dq, dk at T = 1)
-        assert (got - g).norm().item() <= 1.2e-2 * g.norm().item() + 1e-4 * scale * g.numel() ** 0.5
+    for res in (dqkv, dqkv_ws):
+        for i, g in enumerate((q.grad, k.grad, v.grad)):
+            got = res[:, :, i].permute(0, 2, 1, 3).float()
+            # relative to the tensor's norm, with a floor for gradients that are analytically zero (dq, dk at T = 1)
+            assert (got - g).norm().item() <= 1.2e-2 * g.norm().item() + 1e-4 * scale * g.numel() ** 0.5
+
+
+@pytest.mark.parametrize("legacy", ["0", "1"])
+def test_both_attention_paths_in_a_subprocess(legacy):
+    """The mma.sync kernels stay in the library for T > 256 (U-ViT); VAW_ATTN_LEGACY=1 forces them for every shape so
+    both implementations are exercised on the DiT shapes (the switch is read once per process)."""
+    import os, subprocess, sys
+    code = (
+        "import sys, ctypes as C, torch; sys.path[:0] = %r\n"
+        "from vaw_b200 import _lib as L\n"
+        "import torch.nn.functional as F\n"
+        "L.register('vaw_attn_fwd', [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p])\n"
+        "L.register('vaw_attn_bwd', [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p])\n"
+        "B, T, H, hd = 3, 256, 4, 72\n"
+        "torch.manual_seed(1)\n"
+        "qkv = (torch.randn(B, T, 3, H, hd, device='cuda') * 0.7).bfloat16()\n"
+        "o = torch.empty(B, T, H, hd, device='cuda', dtype=torch.bfloat16); lse = torch.empty(B, H, T, device='cuda')\n"
+        "L.call('vaw_attn_fwd', qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, H, hd, L.stream_ptr())\n"
+        "q, k, v = [qkv[:, :, i].float().permute(0, 2, 1, 3).requires_grad_(True) for i in range(3)]\n"
+        "ref = F.scaled_dot_product_attention(q, k, v)\n"
+        "do = torch.randn_like(o); dqkv = torch.empty_like(qkv)\n"
+        "L.call('vaw_attn_bwd', qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, T, H, hd, L.stream_ptr())\n"
+        "ref.backward(do.float().permute(0, 2, 1, 3))\n"
+        "e = [((dqkv[:, :, i].permute(0, 2, 1, 3).float() - g.grad).norm() / g.grad.norm()).item() for i, g in enumerate((q, k, v))]\n"
+        "eo = ((o.permute(0, 2, 1, 3).float() - ref).norm() / ref.norm()).item()\n"
+        "assert eo < 6e-3 and max(e) < 1.2e-2, (eo, e)\n"
+        "print('ok')\n" % (sys.path[:3],))
+    env = dict(os.environ, VAW_ATTN_LEGACY=legacy)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 
 def test_unsupported_head_dim_fails_loudly():

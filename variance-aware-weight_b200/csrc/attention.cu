@@ -447,13 +447,13 @@ extern "C" int vaw_attn_fwd(const void* qkv, void* o, float* lse2, int B, int T,
   return VAW_ERR_UNSUPPORTED;
 }
 
-extern "C" int vaw_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int B,
-                            int T, int H, int head_dim, cudaStream_t stream) {
+extern "C" int vaw_attn_bwd_ws(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv,
+                               float* delta_ws, int B, int T, int H, int head_dim, cudaStream_t stream) {
   VAW_CHECK_ARG(qkv && o && d_o && lse2 && dqkv && B > 0 && T > 0 && H > 0, "vaw_attn_bwd: bad arguments");
   {
     static const bool legacy = getenv("VAW_ATTN_LEGACY") && atoi(getenv("VAW_ATTN_LEGACY")) != 0;
     if (!legacy) {
-      const int rc = vaw_attn_bwd_sm100(qkv, o, d_o, lse2, dqkv, B, T, H, head_dim, stream);
+      const int rc = vaw_attn_bwd_sm100(qkv, o, d_o, lse2, dqkv, delta_ws, B, T, H, head_dim, stream);
       if (rc != VAW_ERR_UNSUPPORTED) return rc;
     }
   }
@@ -461,4 +461,9 @@ extern "C" int vaw_attn_bwd(const void* qkv, const void* o, const void* d_o, con
   if (head_dim == 72) return launch_bwd<72>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse2, (bf16*)dqkv, B, T, H, stream);
   vaw_set_error("vaw_attn_bwd: head_dim %d not supported (64, 72)", head_dim);
   return VAW_ERR_UNSUPPORTED;
+}
+
+extern "C" int vaw_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int B,
+                            int T, int H, int head_dim, cudaStream_t stream) {
+  return vaw_attn_bwd_ws(qkv, o, d_o, lse2, dqkv, nullptr, B, T, H, head_dim, stream);
 }

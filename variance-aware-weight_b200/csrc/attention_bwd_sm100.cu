@@ -40,6 +40,8 @@ struct BSmem {
   static constexpr int kBars = kDelta + kMaxT * 4;
   static constexpr int kBytes = kBars + 128 + 1024;
 };
+// (An all-SWIZZLE_32B layout - five 16-column blocks per tensor, so that N = 80 goes into one MMA - was measured:
+//  35 % fewer tcgen05.mma but 2.5x more TMA requests of 32 B each; the kernel got 20 % slower.  Kept: 64 + 16.)
 
 __device__ __forceinline__ float dot8(uint4 a, uint4 b) {
   const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
@@ -73,8 +75,10 @@ template <int HD>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_qkv_t,
                    const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_do_t,
+                   const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ CUtensorMap tm_dq_t,
                    const bf16* __restrict__ o, const bf16* __restrict__ d_o, const float* __restrict__ lse2,
-                   bf16* __restrict__ dqkv, int T, int H, float scale, float scale_log2e) {
+                   bf16* __restrict__ dqkv, int T, int H, float scale, float scale_log2e,
+                   const float* __restrict__ delta_in, unsigned long long* __restrict__ trace) {
   using S = BSmem<HD>;
   constexpr bool kTail = S::kTail;
   extern __shared__ uint8_t smem_raw[];
@@ -113,7 +117,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_v = *tmem_slot;
+  const uint32_t tmem = tmem_v;
+  // debug timeline (vaw_attn_set_trace): CTA (h = 0, b = gridDim.y / 2) stamps globaltimer at its hand-off points;
+  // slot layout: [role 0 = elementwise warp 2, role 1 = MMA warp][64 stamps]
+  const bool tracing = trace != nullptr && lane == 0 && h == 0 && b == (int)gridDim.y / 2;
+  int tpos = 0;
+  auto stamp = [&](int role) {
+    if (tracing && tpos < 64) trace[role * 64 + tpos++] = globaltimer_ns();
+  };
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -141,111 +153,171 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      const uint32_t aQ = smem_u32(smem + S::kQ), aK = smem_u32(smem + S::kK), aV = smem_u32(smem + S::kV),
-                     aDO = smem_u32(smem + S::kDO), aQt = smem_u32(smem + S::kQt), aKt = smem_u32(smem + S::kKt),
-                     aVt = smem_u32(smem + S::kVt), aDOt = smem_u32(smem + S::kDOt), aDS = smem_u32(smem + S::kDS);
-      const uint32_t id_kk = idesc_bf16(64, 0, 0);      // S^T, dP^T : N = 64 queries, K-major x K-major
-      const uint32_t id_m = idesc_bf16(64, 1, 0);       // dV, dK main columns: B MN-major
-      const uint32_t id_t = idesc_bf16(16, 1, 0);       // dV, dK tail columns
-      const uint32_t id_qm = idesc_bf16(64, 1, 1);      // dQ: A and B MN-major
-      const uint32_t id_qt = idesc_bf16(16, 1, 1);
-      auto issue_sdp = [&](int s) {
-        const int kt = s / nqs, qs = s - kt * nqs;
-        if (qs == 0) mbar_wait(&kv_full[kt], 0);
-        if (kt == 0) mbar_wait(&qdo_full[qs], 0);
-        tc_fence_after();
+    // The whole warp walks the loop so that every descriptor is warp-uniform (uniform datapath, no per-MMA address
+    // arithmetic in vector registers); only lane 0 issues.  Descriptors are base + (byte offset >> 4) in the low word.
+    const bool leader = lane == 0;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_v, 0);   // provably warp-uniform: stays in uniform registers
+    const uint64_t dQ = desc_sw128(smem_u32(smem + S::kQ)), dK = desc_sw128(smem_u32(smem + S::kK)),
+                   dV = desc_sw128(smem_u32(smem + S::kV)), dDO = desc_sw128(smem_u32(smem + S::kDO)),
+                   dQt = desc_sw32(smem_u32(smem + S::kQt)), dKt = desc_sw32(smem_u32(smem + S::kKt)),
+                   dVt = desc_sw32(smem_u32(smem + S::kVt)), dDOt = desc_sw32(smem_u32(smem + S::kDOt)),
+                   dDS = desc_sw128_mn(smem_u32(smem + S::kDS), 16384);
+    const uint32_t id_kk = idesc_bf16(64, 0, 0);      // S^T, dP^T : N = 64 queries, K-major x K-major
+    const uint32_t id_m = idesc_bf16(64, 1, 0);       // dV, dK main columns: B MN-major
+    const uint32_t id_t = idesc_bf16(16, 1, 0);       // dV, dK tail columns
+    const uint32_t id_qm = idesc_bf16(64, 1, 1);      // dQ: A and B MN-major
+    const uint32_t id_qt = idesc_bf16(16, 1, 1);
+    auto issue_sdp = [&](int s) {
+      const int kt = s / nqs, qs = s - kt * nqs;
+      if (qs == 0) mbar_wait(&kv_full[kt], 0);
+      if (kt == 0) mbar_wait(&qdo_full[qs], 0);
+      tc_fence_after();
+      const uint64_t ak = dK + (uint32_t)(kt * (16384 >> 4)), av = dV + (uint32_t)(kt * (16384 >> 4));
+      const uint64_t bq = dQ + (uint32_t)(qs * (8192 >> 4)), bo = dDO + (uint32_t)(qs * (8192 >> 4));
+      if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_ss(tmem + cS, desc_sw128(aK + kt * 16384 + k * 32), desc_sw128(aQ + qs * 8192 + k * 32), id_kk,
-                    k ? 1u : 0u);
-        if (kTail) tc_mma_ss(tmem + cS, desc_sw32(aKt + kt * 4096), desc_sw32(aQt + qs * 2048), id_kk, 1u);
+        for (int k = 0; k < 4; ++k) tc_mma_ss(tmem + cS, ak + 2 * k, bq + 2 * k, id_kk, k ? 1u : 0u);
+        if (kTail)
+          tc_mma_ss(tmem + cS, dKt + (uint32_t)(kt * (4096 >> 4)), dQt + (uint32_t)(qs * (2048 >> 4)), id_kk, 1u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_ss(tmem + cDP, desc_sw128(aV + kt * 16384 + k * 32), desc_sw128(aDO + qs * 8192 + k * 32), id_kk,
-                    k ? 1u : 0u);
-        if (kTail) tc_mma_ss(tmem + cDP, desc_sw32(aVt + kt * 4096), desc_sw32(aDOt + qs * 2048), id_kk, 1u);
+        for (int k = 0; k < 4; ++k) tc_mma_ss(tmem + cDP, av + 2 * k, bo + 2 * k, id_kk, k ? 1u : 0u);
+        if (kTail)
+          tc_mma_ss(tmem + cDP, dVt + (uint32_t)(kt * (4096 >> 4)), dDOt + (uint32_t)(qs * (2048 >> 4)), id_kk, 1u);
         tc_commit(sdp_full);
-      };
-      issue_sdp(0);
-      for (int s = 0; s < nblocks; ++s) {
-        const int kt = s / nqs, qs = s - kt * nqs;
-        mbar_wait(sdp_free, (uint32_t)s & 1u);
-        if (s + 1 < nblocks) issue_sdp(s + 1);
-        mbar_wait(p_full, (uint32_t)s & 1u);
-        tc_fence_after();
+      }
+      __syncwarp();
+    };
+    stamp(1);
+    issue_sdp(0);
+    stamp(1);
+    for (int s = 0; s < nblocks; ++s) {
+      const int kt = s / nqs, qs = s - kt * nqs;
+      mbar_wait(sdp_free, (uint32_t)s & 1u);
+      stamp(1);
+      if (s + 1 < nblocks) issue_sdp(s + 1);
+      stamp(1);
+      mbar_wait(p_full, (uint32_t)s & 1u);
+      stamp(1);
+      tc_fence_after();
+      const uint64_t bo = dDO + (uint32_t)(qs * (8192 >> 4)), bot = dDOt + (uint32_t)(qs * (2048 >> 4));
+      const uint64_t bq = dQ + (uint32_t)(qs * (8192 >> 4)), bqt = dQt + (uint32_t)(qs * (2048 >> 4));
+      const uint32_t acc0 = qs ? 1u : 0u;
+      if (leader) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {   // dV[kt] += P^T dO[qs]
-          const uint32_t acc = (qs | k) ? 1u : 0u;
-          tc_mma_ts(tmem + cDV, tmem + cPt + k * 8, desc_sw128(aDO + qs * 8192 + k * 2048), id_m, acc);
-          if (kTail) tc_mma_ts(tmem + cDV + 64, tmem + cPt + k * 8, desc_sw32(aDOt + qs * 2048 + k * 512), id_t, acc);
+          tc_mma_ts(tmem + cDV, tmem + cPt + k * 8, bo + 128 * k, id_m, k ? 1u : acc0);
+          if (kTail) tc_mma_ts(tmem + cDV + 64, tmem + cPt + k * 8, bot + 32 * k, id_t, k ? 1u : acc0);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {   // dK[kt] += dS^T Q[qs]
-          const uint32_t acc = (qs | k) ? 1u : 0u;
-          tc_mma_ts(tmem + cDK, tmem + cDSt + k * 8, desc_sw128(aQ + qs * 8192 + k * 2048), id_m, acc);
-          if (kTail) tc_mma_ts(tmem + cDK + 64, tmem + cDSt + k * 8, desc_sw32(aQt + qs * 2048 + k * 512), id_t, acc);
+          tc_mma_ts(tmem + cDK, tmem + cDSt + k * 8, bq + 128 * k, id_m, k ? 1u : acc0);
+          if (kTail) tc_mma_ts(tmem + cDK + 64, tmem + cDSt + k * 8, bqt + 32 * k, id_t, k ? 1u : acc0);
         }
         tc_commit(p_free);
-        if ((qs & 1) || qs == nqs - 1) {   // a 128-query half is complete: dQ[half] += dS K[kt]
-          const uint32_t dq = tmem + cDQ + (qs >> 1) * 80;
+      }
+      if ((qs & 1) || qs == nqs - 1) {   // a 128-query half is complete: dQ[half] += dS K[kt]
+        const uint32_t dq = tmem + cDQ + (qs >> 1) * 80;
+        const uint64_t bk = dK + (uint32_t)(kt * (16384 >> 4)), bkt = dKt + (uint32_t)(kt * (4096 >> 4));
+        const uint32_t accq = kt ? 1u : 0u;
+        if (leader) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const uint32_t acc = (kt | k) ? 1u : 0u;
-            const uint64_t ad = desc_sw128_mn(aDS + k * 2048, 16384);
-            tc_mma_ss(dq, ad, desc_sw128(aK + kt * 16384 + k * 2048), id_qm, acc);
-            if (kTail) tc_mma_ss(dq + 64, ad, desc_sw32(aKt + kt * 4096 + k * 512), id_qt, acc);
+            tc_mma_ss(dq, dDS + 128 * k, bk + 128 * k, id_qm, k ? 1u : accq);
+            if (kTail) tc_mma_ss(dq + 64, dDS + 128 * k, bkt + 32 * k, id_qt, k ? 1u : accq);
           }
           tc_commit(ds_free);
         }
-        if (qs == nqs - 1) tc_commit(acc_full);
       }
+      if (leader && qs == nqs - 1) tc_commit(acc_full);
+      __syncwarp();
+      stamp(1);
     }
-    __syncwarp();
   } else {
     // =========================== elementwise + epilogue warps ===========================
     const int g = warp & 3;              // TMEM lane group this warp may touch
     const int hq = (warp - 2) >> 2;      // which 32 of the block's 64 queries
     const int j = g * 32 + lane;         // key row inside the tile == TMEM lane
     const uint32_t trow = tmem + ((uint32_t)(g * 32) << 16);
+    const bool tr_ew = warp == 2;
+    if (tr_ew) stamp(0);
     {  // per-query constants: -L2[q] and Delta[q] = sum_d dO[q, d] O[q, d]
       const int q = (warp - 2) * 32 + lane;
       float nl2 = -INFINITY, delta = 0.f;
       if (q < T) {
-        const long long off = (((long long)b * T + q) * H + h) * HD;
-        const uint4* po = reinterpret_cast<const uint4*>(o + off);
-        const uint4* pd = reinterpret_cast<const uint4*>(d_o + off);
+        if (delta_in) {   // precomputed by attn_delta_kernel (coalesced, full bandwidth)
+          delta = delta_in[((long long)b * H + h) * T + q];
+        } else {
+          const long long off = (((long long)b * T + q) * H + h) * HD;
+          const uint4* po = reinterpret_cast<const uint4*>(o + off);
+          const uint4* pd = reinterpret_cast<const uint4*>(d_o + off);
 #pragma unroll
-        for (int i = 0; i < HD / 8; ++i) delta += dot8(__ldg(po + i), __ldg(pd + i));
+          for (int i = 0; i < HD / 8; ++i) delta += dot8(__ldg(po + i), __ldg(pd + i));
+        }
         nl2 = -lse2[((long long)b * H + h) * T + q];
       }
       s_nl2[q] = nl2;
       s_delta[q] = delta;
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+    if (tr_ew) stamp(0);
     // accumulator drains (lanes = rows of the output): dV / dK of key tile kt, then dQ
+    // Accumulator drains.  The gradients leave through shared memory and the TMA store engine: a thread's row is
+    // written into the (dead) operand tile of the same geometry - dK over K[kt], dV over V[kt], dQ over Q - in the
+    // swizzled box layout, then one thread issues bulk tensor stores.  (Per-thread 16-byte global stores of rows that
+    // are 6.9 KB apart cost 2 us per drain in the LSU; the staged version is off the critical path.)
+    auto stage_row = [&](int main_off, int tail_off, int row, const uint32_t (&v)[32], const uint32_t (&w)[16],
+                         float mul) {
+      uint8_t* rm = smem + main_off + row * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 x;
+        x.x = pack_bf16(__uint_as_float(v[8 * c]) * mul, __uint_as_float(v[8 * c + 1]) * mul);
+        x.y = pack_bf16(__uint_as_float(v[8 * c + 2]) * mul, __uint_as_float(v[8 * c + 3]) * mul);
+        x.z = pack_bf16(__uint_as_float(v[8 * c + 4]) * mul, __uint_as_float(v[8 * c + 5]) * mul);
+        x.w = pack_bf16(__uint_as_float(v[8 * c + 6]) * mul, __uint_as_float(v[8 * c + 7]) * mul);
+        *reinterpret_cast<uint4*>(rm + (((hq * 4 + c) ^ (row & 7)) * 16)) = x;
+      }
+      if (kTail && hq == 0) {
+        uint8_t* rt = smem + tail_off + row * 32;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint4 x;
+          x.x = pack_bf16(__uint_as_float(w[8 * c]) * mul, __uint_as_float(w[8 * c + 1]) * mul);
+          x.y = pack_bf16(__uint_as_float(w[8 * c + 2]) * mul, __uint_as_float(w[8 * c + 3]) * mul);
+          x.z = pack_bf16(__uint_as_float(w[8 * c + 4]) * mul, __uint_as_float(w[8 * c + 5]) * mul);
+          x.w = pack_bf16(__uint_as_float(w[8 * c + 6]) * mul, __uint_as_float(w[8 * c + 7]) * mul);
+          *reinterpret_cast<uint4*>(rt + ((c ^ ((row >> 2) & 1)) * 16)) = x;
+        }
+      }
+    };
+    auto store_rows = [&](int main_off, int tail_off, int slot, int rb) {   // one thread: rows [64 rb, 64 rb + 64)
+      tma_store_4d(&tm_dq, smem + main_off + rb * 64 * 128, 0, slot, rb * 64, b);
+      if (kTail) tma_store_4d(&tm_dq_t, smem + tail_off + rb * 64 * 32, 64, slot, rb * 64, b);
+    };
     auto drain_dvdk = [&](int kt) {
       mbar_wait(acc_full, (uint32_t)kt & 1u);
       __syncwarp();
       tc_fence_after();
-      const int key = kt * 128 + j;
-      bf16* gk = dqkv + ((((long long)b * T + key) * 3 + 1) * H + h) * HD;
-      bf16* gv = gk + (long long)H * HD;
-      uint32_t v[32];
+      uint32_t v[32], u[32], wv[16], wk[16];
       tmem_ld32(trow + cDV + hq * 32, v);
-      tmem_ld_wait();
-      if (key < T) store_row32(gv + hq * 32, v, 1.f);
-      tmem_ld32(trow + cDK + hq * 32, v);
-      tmem_ld_wait();
-      if (key < T) store_row32(gk + hq * 32, v, scale);
+      tmem_ld32(trow + cDK + hq * 32, u);
       if (kTail && hq == 0) {
-        uint32_t w[16];
-        tmem_ld16(trow + cDV + 64, w);
-        tmem_ld_wait();
-        if (key < T) store_row8(gv + 64, w, 1.f);
-        tmem_ld16(trow + cDK + 64, w);
-        tmem_ld_wait();
-        if (key < T) store_row8(gk + 64, w, scale);
+        tmem_ld16(trow + cDV + 64, wv);
+        tmem_ld16(trow + cDK + 64, wk);
+      }
+      tmem_ld_wait();
+      stage_row(S::kV, S::kVt, kt * 128 + j, v, wv, 1.f);
+      stage_row(S::kK, S::kKt, kt * 128 + j, u, wk, scale);
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        for (int rb = 2 * kt; rb < 2 * kt + 2; ++rb) {
+          if (rb * 64 < T) {
+            store_rows(S::kV, S::kVt, 2 * H + h, rb);
+            store_rows(S::kK, S::kKt, H + h, rb);
+          }
+        }
+        bulk_commit_group();
       }
     };
 
@@ -253,6 +325,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const int kt = s / nqs, qs = s - kt * nqs;
       mbar_wait(sdp_full, (uint32_t)s & 1u);
       __syncwarp();
+      if (tr_ew) stamp(0);
       tc_fence_after();
       uint32_t sv[32], dv[32];
       tmem_ld32(trow + cS + hq * 32, sv);
@@ -261,7 +334,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_free);
-      if (qs == 0 && kt > 0) drain_dvdk(kt - 1);   // before this tile's first dV / dK product may overwrite them
 
       uint32_t pp[16], dd[16];
       const float4* nl = reinterpret_cast<const float4*>(s_nl2 + qs * 64 + hq * 32);
@@ -279,15 +351,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         dd[2 * i + 1] =
             pack_bf16(p2 * (__uint_as_float(dv[4 * i + 2]) - D.z), p3 * (__uint_as_float(dv[4 * i + 3]) - D.w));
       }
+      if (tr_ew) stamp(0);
+      // previous key tile's dV / dK leave TMEM here: after this block's math (the MMA warp has finished them by now)
+      // and before p_full lets the first dV / dK product of this tile overwrite them
+      if (qs == 0 && kt > 0) drain_dvdk(kt - 1);
       if (s > 0) {
         mbar_wait(p_free, (uint32_t)(s - 1) & 1u);
         __syncwarp();
         tc_fence_after();
       }
+      if (tr_ew) stamp(0);
       tmem_st16(trow + cPt + hq * 16, pp);
       tmem_st16(trow + cDSt + hq * 16, dd);
       const int half_idx = kt * halves_per_kt + (qs >> 1);
       if (half_idx > 0) mbar_wait(ds_free, (uint32_t)(half_idx - 1) & 1u);
+      if (tr_ew) stamp(0);
       {  // dS^T row j, queries [hq * 32, hq * 32 + 32) of block (qs & 1): four swizzled 16-byte chunks
         uint8_t* rowp = smem + S::kDS + (qs & 1) * 16384 + j * 128;
 #pragma unroll
@@ -301,58 +379,107 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (tr_ew) stamp(0);
     }
-    drain_dvdk(nkt - 1);   // the last acc_full also covers every dQ product
-    for (int qh = 0; qh * 128 < T; ++qh) {
-      const int q = qh * 128 + j;
-      bf16* gq = dqkv + (((long long)b * T + q) * 3 * H + h) * HD;
-      uint32_t v[32];
-      tmem_ld32(trow + cDQ + qh * 80 + hq * 32, v);
+    drain_dvdk(nkt - 1);
+    if (tr_ew) stamp(0);   // the last acc_full also covers every dQ product
+    {
+      const int nqh = (T + 127) >> 7;
+      uint32_t v[2][32], w[2][16];
+#pragma unroll
+      for (int qh = 0; qh < 2; ++qh) {
+        if (qh < nqh) {
+          tmem_ld32(trow + cDQ + qh * 80 + hq * 32, v[qh]);
+          if (kTail && hq == 0) tmem_ld16(trow + cDQ + qh * 80 + 64, w[qh]);
+        }
+      }
       tmem_ld_wait();
-      if (q < T) store_row32(gq + hq * 32, v, scale);
-      if (kTail && hq == 0) {
-        uint32_t w[16];
-        tmem_ld16(trow + cDQ + qh * 80 + 64, w);
-        tmem_ld_wait();
-        if (q < T) store_row8(gq + 64, w, scale);
+#pragma unroll
+      for (int qh = 0; qh < 2; ++qh)
+        if (qh < nqh) stage_row(S::kQ, S::kQt, qh * 128 + j, v[qh], w[qh], scale);
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        for (int rb = 0; rb * 64 < T; ++rb) store_rows(S::kQ, S::kQt, h, rb);
+        bulk_commit_group();
+        bulk_wait_group_read0();   // shared memory must stay valid until the store engine has read it
       }
     }
   }
+  if (warp == 2) stamp(0);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// Delta[b, h, t] = sum_d dO[b, t, h, d] * O[b, t, h, d]; one thread per (token, head), consecutive threads read
+// consecutive 2*HD-byte segments (coalesced across the warp).
 template <int HD>
-int launch_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int B, int T, int H,
-                  cudaStream_t stream) {
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta, int T, int H,
+                  long long n) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint4* po = reinterpret_cast<const uint4*>(o + i * HD);
+  const uint4* pd = reinterpret_cast<const uint4*>(d_o + i * HD);
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < HD / 8; ++k) acc += dot8(__ldg(po + k), __ldg(pd + k));
+  const int h = (int)(i % H);
+  const long long bt = i / H;
+  const long long b = bt / T;
+  const int t = (int)(bt - b * T);
+  delta[(b * H + h) * T + t] = acc;
+}
+
+unsigned long long* g_attn_trace = nullptr;   // debug: device buffer of 128 stamps (vaw_attn_set_trace)
+
+template <int HD>
+int launch_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, float* delta_ws, int B,
+                  int T, int H, cudaStream_t stream) {
   using S = BSmem<HD>;
   CUtensorMap tq, tqt, td, tdt;
   int rc = make_head_map(&tq, qkv, B, T, 3 * H, HD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = make_head_map(&tqt, qkv, B, T, 3 * H, HD, 16, 64, CU_TENSOR_MAP_SWIZZLE_32B);
   if (!rc) rc = make_head_map(&td, d_o, B, T, H, HD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!rc) rc = make_head_map(&tdt, d_o, B, T, H, HD, 16, 64, CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap tg, tgt;
+  if (!rc) rc = make_head_map(&tg, dqkv, B, T, 3 * H, HD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!rc) rc = make_head_map(&tgt, dqkv, B, T, 3 * H, HD, 16, 64, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
     VAW_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes));
     configured = true;
   }
+  if (delta_ws) {
+    const long long n = (long long)B * T * H;
+    attn_delta_kernel<HD><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const bf16*)o, (const bf16*)d_o, delta_ws, T, H,
+                                                                         n);
+    VAW_LAUNCH_CHECK();
+  }
   const float scale = 1.0f / sqrtf((float)HD);
   attn_bwd_tc_kernel<HD><<<dim3(H, B), kBwdThreads, S::kBytes, stream>>>(
-      tq, tqt, td, tdt, (const bf16*)o, (const bf16*)d_o, lse2, (bf16*)dqkv, T, H, scale, scale * 1.4426950408889634f);
+      tq, tqt, td, tdt, tg, tgt, (const bf16*)o, (const bf16*)d_o, lse2, (bf16*)dqkv, T, H, scale, scale * 1.4426950408889634f,
+      delta_ws, g_attn_trace);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }
 
 }  // namespace
 
-int vaw_attn_bwd_sm100(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int B, int T,
-                       int H, int head_dim, cudaStream_t stream) {
+// debug knob: device buffer [2][64] of globaltimer stamps written by one CTA of the backward kernel (null = off)
+extern "C" int vaw_attn_set_trace(void* device_buf) {
+  g_attn_trace = reinterpret_cast<unsigned long long*>(device_buf);
+  return VAW_OK;
+}
+
+int vaw_attn_bwd_sm100(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, float* delta_ws,
+                       int B, int T, int H, int head_dim, cudaStream_t stream) {
   const uintptr_t al = reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(o) |
                        reinterpret_cast<uintptr_t>(d_o) | reinterpret_cast<uintptr_t>(dqkv);
   if (T > kMaxT || (al & 15) != 0) return VAW_ERR_UNSUPPORTED;
-  if (head_dim == 64) return launch_bwd_tc<64>(qkv, o, d_o, lse2, dqkv, B, T, H, stream);
-  if (head_dim == 72) return launch_bwd_tc<72>(qkv, o, d_o, lse2, dqkv, B, T, H, stream);
+  if (head_dim == 64) return launch_bwd_tc<64>(qkv, o, d_o, lse2, dqkv, delta_ws, B, T, H, stream);
+  if (head_dim == 72) return launch_bwd_tc<72>(qkv, o, d_o, lse2, dqkv, delta_ws, B, T, H, stream);
   return VAW_ERR_UNSUPPORTED;
 }

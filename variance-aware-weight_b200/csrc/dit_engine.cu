@@ -79,6 +79,7 @@ struct Ws {
   // backward temporaries
   float* dx;
   bf16 *dy, *dh, *dqkv, *d_o, *dxn, *dtok, *dz, *dxa;
+  float* attn_delta;   // [B*H*T] rowsum(dO*O) scratch of the attention backward
   float *part, *cpart, *dmod_all, *dmod_final, *dcs, *dc;
   bf16 *dmod_all_b, *dmod_final_b, *dc_b, *dth;
   float* split_ws;
@@ -130,6 +131,7 @@ void carve(const vaw_dit_cfg& c, void* base, Ws& w) {
   w.dh = k.take<bf16>(M * Hd);
   w.dqkv = k.take<bf16>(M * 3 * D);
   w.d_o = k.take<bf16>(M * D);
+  w.attn_delta = k.take<float>((long long)c.B * c.H * c.T);
   w.dxn = k.take<bf16>(M * D);
   w.dtok = k.take<bf16>(M * PPC);
   w.dz = k.take<bf16>(2 * M * pd);
@@ -343,7 +345,7 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
     TRY(G(w.dy, D, 1, b.attn_o, D, 1, D, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_PROJ_W]).acc(acc)
             .autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dy, D, 0, Pb + L.off[pb + B_PROJ_W], D, 1, M, D, D, VAW_EPI_BF16).out(w.d_o).run(s));
-    TRY(vaw_attn_bwd(b.qkv, b.attn_o, w.d_o, b.lse, w.dqkv, B, T, c.H, hd, s));
+    TRY(vaw_attn_bwd_ws(b.qkv, b.attn_o, w.d_o, b.lse, w.dqkv, w.attn_delta, B, T, c.H, hd, s));
     TRY(vaw_colsum_bf16(w.dqkv, 3LL * D, M, 3 * D, w.cpart, colsum_rows(M, 3 * D), Gd + L.off[pb + B_QKV_B], acc, s));
     TRY(G(w.dqkv, 3LL * D, 1, b.xn1, D, 1, 3 * D, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_QKV_W]).acc(acc)
             .autosplit(w.split_ws, w.split_elems).run(s));

@@ -71,6 +71,7 @@ struct UWs {
   // backward temporaries
   float *dx, *dimg;
   bf16 *dy, *dh, *dqkv, *d_o, *dxn, *dtokp, *dtok;
+  float* attn_delta;   // [B*H*T] rowsum(dO*O) scratch of the attention backward
   float *part, *cpart, *split_ws;
   long long split_elems, bytes;
 };
@@ -112,6 +113,7 @@ void u_carve(const vaw_uvit_cfg& c, void* base, UWs& w) {
   w.dh = k.take<bf16>(M * Hd);
   w.dqkv = k.take<bf16>(M * 3 * D);
   w.d_o = k.take<bf16>(M * D);
+  w.attn_delta = k.take<float>((long long)c.B * c.H * c.T);
   w.dxn = k.take<bf16>(M * D);
   w.dtokp = k.take<bf16>(M * Kp);
   w.dtok = k.take<bf16>(B * Lp * D);
@@ -301,7 +303,7 @@ extern "C" int vaw_uvit_backward(const vaw_uvit_cfg* cfg, const float* P, const 
     TRY(G(w.dy, D, 1, b.attn_o, D, 1, D, D, M, VAW_EPI_F32).out(Gd + L.off[pb + UB_PROJ_W]).acc(acc)
             .autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dy, D, 0, Pb + L.off[pb + UB_PROJ_W], D, 1, M, D, D, VAW_EPI_BF16).out(w.d_o).run(s));
-    TRY(vaw_attn_bwd(b.qkv, b.attn_o, w.d_o, b.lse, w.dqkv, B, T, c.H, hd, s));
+    TRY(vaw_attn_bwd_ws(b.qkv, b.attn_o, w.d_o, b.lse, w.dqkv, w.attn_delta, B, T, c.H, hd, s));
     TRY(G(w.dqkv, 3LL * D, 1, b.xn1, D, 1, 3 * D, D, M, VAW_EPI_F32).out(Gd + L.off[pb + UB_QKV_W]).acc(acc)
             .autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dqkv, 3LL * D, 0, Pb + L.off[pb + UB_QKV_W], D, 1, M, D, 3 * D, VAW_EPI_BF16).out(w.dxn).run(s));

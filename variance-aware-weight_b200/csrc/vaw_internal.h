@@ -50,14 +50,16 @@ struct vaw_dit_cfg {
 
 // tcgen05 attention (attention_sm100.cu); VAW_ERR_UNSUPPORTED when the shape is outside its range (T > 256)
 int vaw_attn_fwd_sm100(const void* qkv, void* o, float* lse2, int B, int T, int H, int head_dim, cudaStream_t stream);
-int vaw_attn_bwd_sm100(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int B, int T,
-                       int H, int head_dim, cudaStream_t stream);
+int vaw_attn_bwd_sm100(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, float* delta_ws,
+                       int B, int T, int H, int head_dim, cudaStream_t stream);
 
 extern "C" {
 int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream);
 int vaw_attn_fwd(const void* qkv, void* o, float* lse2, int B, int T, int H, int head_dim, cudaStream_t stream);
 int vaw_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int B, int T, int H,
                  int head_dim, cudaStream_t stream);
+int vaw_attn_bwd_ws(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, float* delta_ws,
+                    int B, int T, int H, int head_dim, cudaStream_t stream);
 int vaw_ln_fwd(const float* x, const float* shift, const float* scale, long long ld_mod, int rows_per_sample,
                const float* weight, const float* bias, void* y, float* mean, float* rstd, int M, int D, float eps,
                cudaStream_t stream);

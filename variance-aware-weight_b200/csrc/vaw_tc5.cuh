@@ -14,6 +14,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// bulk tensor store shared -> global (clipped at the tensor bounds); completion is tracked by bulk async-groups
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "r"(ncols)
                : "memory");
@@ -88,6 +97,11 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
 __device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1u << 16) | ((uint64_t)16u << 32) | ((uint64_t)1u << 46) |
          ((uint64_t)6u << 61);
+}
+// MN-major SWIZZLE_32B operand made of 16-element column blocks lbo_bytes apart (rows of 32 B, 8-row groups 256 B)
+__device__ __forceinline__ uint64_t desc_sw32_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)16u << 32) |
+         ((uint64_t)1u << 46) | ((uint64_t)6u << 61);
 }
 // MN-major SWIZZLE_128B operand wider than one 64-element block: lbo_bytes = distance between 64-wide blocks
 __device__ __forceinline__ uint64_t desc_sw128_mn(uint32_t saddr, uint32_t lbo_bytes) {
