@@ -71,7 +71,7 @@ def test_both_attention_paths_in_a_subprocess(legacy):
         "e = [((dqkv[:, :, i].permute(0, 2, 1, 3).float() - g.grad).norm() / g.grad.norm()).item() for i, g in enumerate((q, k, v))]\n"
         "eo = ((o.permute(0, 2, 1, 3).float() - ref).norm() / ref.norm()).item()\n"
         "assert eo < 6e-3 and max(e) < 1.2e-2, (eo, e)\n"
-        "print('ok')\n" % (sys.path[:3],))
+        "print('ok')\n" % ([os.path.dirname(os.path.abspath(L.__file__ )) + "/..", os.path.dirname(os.path.abspath(__file__))],))
     env = dict(os.environ, VAW_ATTN_LEGACY=legacy)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

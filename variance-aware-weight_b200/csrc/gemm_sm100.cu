@@ -29,7 +29,8 @@ namespace {
 
 constexpr int BK = 64;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kEpiParts = kEpiWarps / 4;      // warps sharing one TMEM lane quarter; chunk c belongs to part c % kEpiParts
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + epilogue warps
 constexpr int kABytes = 128 * BK * 2;          // 16 KB per stage per CTA
 
 // epilogue selectors (mirrored in include/vaw_b200.h)
@@ -64,7 +65,8 @@ struct EpiParams {
   // work decomposition (see decode_work): full tiles, then the remaining tiles split along K
   int num_work, full_tiles, tail_splits, kb_per_split;
   float* split_ws;
-  int dbg;  // debug knobs (env VAW_DBG): 1 = ring of 2 stages, 2 = skip MMA issue, 4 = skip TMA issue
+  int dbg;  // debug knobs (env VAW_DBG): 1 = ring of 2 stages, 2 = skip MMA issue, 4 = skip TMA issue,
+            // 8 = epilogue drains TMEM only, 16 = epilogue drains TMEM + shared-memory transpose, no global traffic
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -203,8 +205,9 @@ struct EpiPre {  // global operands of the epilogue, fetched for a whole chunk b
   uint2 a;       // saved pre-activation (D-activation epilogues)
 };
 template <int EPI>
-__device__ __forceinline__ void epilogue_load(const EpiParams& p, int row, int col, long long gate_off, EpiPre& pre) {
-  if (row >= p.M || col >= p.N) return;
+__device__ __forceinline__ void epilogue_load(const EpiParams& p, int row, int col, long long gate_off, bool interior,
+                                              EpiPre& pre) {
+  if (!interior && (row >= p.M || col >= p.N)) return;
   const long long o = (long long)row * p.ldo + col;
   if constexpr (EPI == EPI_F32) {
     if (p.accumulate) pre.r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + o);
@@ -219,13 +222,11 @@ __device__ __forceinline__ void epilogue_load(const EpiParams& p, int row, int c
 }
 
 template <int EPI>
-__device__ __forceinline__ void epilogue_vec4(const EpiParams& p, int row, int col, float4 v, const EpiPre& pre) {
-  if (row >= p.M || col >= p.N) return;
+// (the bias is added by the caller: a lane's four columns are the same for all eight rows of a chunk)
+__device__ __forceinline__ void epilogue_vec4(const EpiParams& p, int row, int col, float4 v, bool interior,
+                                              const EpiPre& pre) {
+  if (!interior && (row >= p.M || col >= p.N)) return;
   const long long o = (long long)row * p.ldo + col;
-  if (p.bias) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-  }
   if constexpr (EPI == EPI_F32) {
     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
     if (p.accumulate) {
@@ -452,42 +453,49 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else {
-    // ===================== epilogue warps (2..9) =====================
-    // two warps per TMEM lane quarter, each draining half of the tile's columns
+    // ===================== epilogue warps =====================
+    // kEpiParts warps per TMEM lane quarter; 32-column chunk c of the tile is drained by part c % kEpiParts.
+    // (Sixteen warps, not eight: the per-element epilogue math is a long dependent chain and two warps per scheduler
+    //  left the issue slots ~70 % idle - the epilogue, not the MMA main loop, bounded the short-K GEMMs.)
     const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;    // 0: chunks [0, NCH/2), 1: chunks [NCH/2, NCH)
+    const int part = (warp - 2) >> 2;
     constexpr int NCH = BN / 32;
     float4* stg = reinterpret_cast<float4*>(smem + STAGES * C::kStageBytes + 256) + (warp - 2) * 256;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // after the transpose this lane owns rows {4i + lane/8} (i = 0..7) and column group lane%8 of every chunk
+    const int sub_r = lane >> 3, sub_c = lane & 7;
     for (int work = unit; work < num_work; work += num_units) {
       const Work wk = decode_work<TM, BN>(work, p, n_tiles, num_kb_total);
-      const int row0 = wk.m0 + (int)rank * 128;  // first global row held by this CTA's TMEM lanes
+      const int row0 = wk.m0 + (int)rank * 128 + q * 32 + sub_r;  // first global row of this lane (then +4 per i)
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      const int c_begin = half * (NCH / 2), c_end = c_begin + NCH / 2;
-      // after the transpose this lane owns rows {4i + lane/8} (i = 0..7) and column group lane%8 of every chunk
-      const int sub_r = lane >> 3, sub_c = lane & 7;
+      const bool interior = wk.m0 + TM <= p.M && wk.n0 + BN <= p.N;   // no bounds checks inside the tile
       long long gate_off[8];
       if constexpr (EPI == EPI_GATE_RES) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          gate_off[i] = (long long)((row0 + q * 32 + 4 * i + sub_r) / p.rows_per_sample) * p.ldg;
+        for (int i = 0; i < 8; ++i) gate_off[i] = (long long)((row0 + 4 * i) / p.rows_per_sample) * p.ldg;
       }
 #pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
+      for (int c = part; c < NCH; c += kEpiParts) {
+        const int col = wk.n0 + c * 32 + sub_c * 4;
         // issue the chunk's global operand loads first: their latency overlaps the TMEM load and the transpose
         EpiPre pre[8];
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!wk.partial) {
+          if (p.bias && col < p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            epilogue_load<EPI>(p, row0 + q * 32 + 4 * i + sub_r, wk.n0 + c * 32 + sub_c * 4,
-                               EPI == EPI_GATE_RES ? gate_off[i] : 0, pre[i]);
+            epilogue_load<EPI>(p, row0 + 4 * i, col, EPI == EPI_GATE_RES ? gate_off[i] : 0, interior, pre[i]);
         }
         uint32_t v[32];
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
         tmem_ld_wait();
+        if (p.dbg & 8) {   // experiment: no shared-memory transpose, no global traffic (results are wrong)
+          if (v[0] == 0x7fc12345u) stg[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
@@ -496,12 +504,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = 4 * i + sub_r;
-          const float4 a4 = stg[r * 8 + (sub_c ^ (r & 7))];
-          const int lrow = q * 32 + r;
-          const int lcol = c * 32 + sub_c * 4;
+          float4 a4 = stg[r * 8 + (sub_c ^ (r & 7))];
           if (!wk.partial) {
-            epilogue_vec4<EPI>(p, row0 + lrow, wk.n0 + lcol, a4, pre[i]);
+            a4.x += bias4.x; a4.y += bias4.y; a4.z += bias4.z; a4.w += bias4.w;
+            epilogue_vec4<EPI>(p, row0 + 4 * i, col, a4, interior, pre[i]);
           } else {
+            const int lrow = q * 32 + r, lcol = c * 32 + sub_c * 4;
             *reinterpret_cast<float4*>(p.split_ws + ((long long)wk.slab * TM + (int)rank * 128 + lrow) * BN + lcol) = a4;
           }
         }
