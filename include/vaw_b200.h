@@ -178,6 +178,12 @@ int vaw_finish_group(const float* part, int which, int groups, int chunks, int D
                      int accumulate, vaw_stream_t stream);
 int vaw_finish_all(const float* part, int which, int groups, int chunks, int D, const float* w, long long ld_w,
                    float* out, int accumulate, vaw_stream_t stream);
+/* All partial-sum buffers of one DiT block's backward in one launch: pA / pC = vaw_gate_bwd partials of the MLP /
+ * attention branch, pB / pD = vaw_ln_bwd partials of the MLP / attention LayerNorm.  Writes d mod[B, 6*D] (fp32 and a
+ * bf16 copy, row stride ldm) and (accumulate ? adds to : overwrites) the fc2.bias, proj.bias and adaLN-bias gradients. */
+int vaw_dit_block_finish(const float* pA, const float* pB, const float* pC, const float* pD, int B, int chunks, int D,
+                         const float* mod, long long ldm, float* dmod, void* dmod_b, float* g_fc2_b, float* g_proj_b,
+                         float* g_ada_b, int accumulate, vaw_stream_t stream);
 int vaw_colsum_bf16(const void* a, long long lda, int M, int N, float* part, int rows_per_chunk, float* out,
                     int accumulate, vaw_stream_t stream);
 int vaw_colsum_f32_small(const float* a, long long lda, int rows, int N, float* out, int accumulate,

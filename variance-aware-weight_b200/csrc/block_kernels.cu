@@ -24,7 +24,7 @@ constexpr int kMaxD = 2048;  // ln_fwd keeps a row in registers: KV = ceil(D / 1
 constexpr int kLnRowsPerWarp = 4;
 
 template <int KV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, KV <= 9 ? 4 : 2)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
               long long ld_mod, int rows_per_sample, const float* __restrict__ weight,
               const float* __restrict__ bias, bf16* __restrict__ y, float* __restrict__ mean_out,
@@ -438,6 +438,62 @@ finish_all_kernel(const float* __restrict__ part, int which, int groups, int chu
 }
 
 // ---------------------------------------------------------------------------------------------------
+// One launch that finishes every partial-sum buffer of a DiT block's backward (replaces 6 finish_group, 2 finish_all,
+// the fp32->bf16 cast of d mod and the adaLN-bias column sum: ten 3-7 us launches per block).
+//   pA = gate_bwd of the MLP branch   [B, ch, 2, D]: 0 = sum dx       1 = sum dx * y
+//   pB = ln_bwd  of the MLP LayerNorm               : 0 = sum dy       1 = sum dy * xhat
+//   pC = gate_bwd of the attention branch, pD = ln_bwd of the attention LayerNorm
+//   d mod[n, :] = [d shift_msa, d scale_msa, d gate_msa, d shift_mlp, d scale_mlp, d gate_mlp]  (fp32 + bf16 copy)
+//   g_fc2_b[col]  (+)= sum_n gate_mlp[n, col] * pA0[n, col]      g_proj_b[col] (+)= sum_n gate_msa[n, col] * pC0[n, col]
+//   g_ada_b[slot * D + col] (+)= sum_n d mod[n, slot, col]        (bias of adaLN_modulation.1, dit.py:139-141)
+// block = 32 columns x 16 sample lanes; every sum runs in a fixed order (deterministic).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+dit_block_finish_kernel(const float* __restrict__ pA, const float* __restrict__ pB, const float* __restrict__ pC,
+                        const float* __restrict__ pD, int B, int ch, int D, const float* __restrict__ mod,
+                        long long ldm, float* __restrict__ dmod, bf16* __restrict__ dmod_b,
+                        float* __restrict__ g_fc2_b, float* __restrict__ g_proj_b, float* __restrict__ g_ada_b,
+                        int accumulate) {
+  __shared__ float red[16][8][33];
+  const int cx = threadIdx.x & 31, ny = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  float tot[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 0..5: adaLN bias slots, 6: fc2.bias, 7: proj.bias
+  if (col < D) {
+    for (int n = ny; n < B; n += 16) {
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f, d0 = 0.f, d1 = 0.f;
+      for (int c = 0; c < ch; ++c) {
+        const long long o = (((long long)n * ch + c) * 2) * D + col;
+        a0 += pA[o]; a1 += pA[o + D];
+        b0 += pB[o]; b1 += pB[o + D];
+        c0 += pC[o]; c1 += pC[o + D];
+        d0 += pD[o]; d1 += pD[o + D];
+      }
+      const float v[6] = {d0, d1, c1, b0, b1, a1};
+      float* dm = dmod + (long long)n * ldm + col;
+      bf16* db = dmod_b + (long long)n * ldm + col;
+#pragma unroll
+      for (int sl = 0; sl < 6; ++sl) {
+        dm[(long long)sl * D] = v[sl];
+        db[(long long)sl * D] = __float2bfloat16(v[sl]);
+        tot[sl] += v[sl];
+      }
+      tot[6] += mod[(long long)n * ldm + 5 * D + col] * a0;
+      tot[7] += mod[(long long)n * ldm + 2 * D + col] * c0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[ny][k][cx] = tot[k];
+  __syncthreads();
+  if (ny < 8 && col < D) {   // sample-lane ny folds quantity ny over the 16 lanes, in order
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += red[i][ny][cx];
+    float* dst = ny < 6 ? g_ada_b + (long long)ny * D + col : (ny == 6 ? g_fc2_b + col : g_proj_b + col);
+    *dst = accumulate ? *dst + s : s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Column sum of a bf16 [M, N] matrix -> fp32 [N] (bias gradients of qkv / fc1): two deterministic stages.
 // stage 1: grid (N/64, row_chunks), 256 threads = 8 row groups x 32 lanes x 2 columns
 // ---------------------------------------------------------------------------------------------------
@@ -579,6 +635,18 @@ extern "C" int vaw_finish_all(const float* part, int which, int groups, int chun
   VAW_CHECK_ARG(part && out && (which == 0 || which == 1) && groups > 0 && chunks > 0 && D > 0,
                 "vaw_finish_all: bad arguments");
   finish_all_kernel<<<(D + 31) / 32, 1024, 0, stream>>>(part, which, groups, chunks, D, w, ld_w, out, accumulate);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+extern "C" int vaw_dit_block_finish(const float* pA, const float* pB, const float* pC, const float* pD, int B, int chunks,
+                                    int D, const float* mod, long long ldm, float* dmod, void* dmod_b, float* g_fc2_b,
+                                    float* g_proj_b, float* g_ada_b, int accumulate, cudaStream_t stream) {
+  VAW_CHECK_ARG(pA && pB && pC && pD && mod && dmod && dmod_b && g_fc2_b && g_proj_b && g_ada_b && B > 0 && chunks > 0 &&
+                    D > 0,
+                "vaw_dit_block_finish: bad arguments");
+  dit_block_finish_kernel<<<(D + 31) / 32, 512, 0, stream>>>(pA, pB, pC, pD, B, chunks, D, mod, ldm, dmod, (bf16*)dmod_b,
+                                                            g_fc2_b, g_proj_b, g_ada_b, accumulate);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }

@@ -72,6 +72,9 @@ int vaw_finish_group(const float* part, int which, int groups, int chunks, int D
                      int accumulate, cudaStream_t stream);
 int vaw_finish_all(const float* part, int which, int groups, int chunks, int D, const float* w, long long ld_w,
                    float* out, int accumulate, cudaStream_t stream);
+int vaw_dit_block_finish(const float* pA, const float* pB, const float* pC, const float* pD, int B, int chunks, int D,
+                         const float* mod, long long ldm, float* dmod, void* dmod_b, float* g_fc2_b, float* g_proj_b,
+                         float* g_ada_b, int accumulate, cudaStream_t stream);
 int vaw_colsum_bf16(const void* a, long long lda, int M, int N, float* part, int rows_per_chunk, float* out,
                     int accumulate, cudaStream_t stream);
 int vaw_patchify_in(const float* x, void* patches, int B, int C, int H, int W, int P, cudaStream_t stream);
