@@ -13,6 +13,8 @@
 //   4. O = P V  [128 x hd]: A operand read from TMEM (P), B = V from shared memory (MN-major), accumulator in the
 //      TMEM columns the softmax freed.
 //   5. epilogue: O / rowsum -> bf16 -> out[b, t, h, :]; L2[q] = max*c + log2(rowsum) (log2-domain, see attention.cu).
+//      (Direct 16-byte stores: a TMA-store epilogue was measured slower here - it keeps the CTA and its shared memory
+//       alive until the store engine has drained the tile, and the next CTA of the SM waits for that.)
 #include "vaw_common.cuh"
 #include "vaw_tc5.cuh"
 #include "vaw_internal.h"
@@ -99,7 +101,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
   float* s_max = reinterpret_cast<float*>(smem + S::kStat);
   float* s_sum = s_max + 2 * kTile;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
   const int nk = (T + 15) & ~15;                 // key columns of S (multiple of 16, <= 256)
   const int kboxes = (T + kTile - 1) / kTile;    // 128-row TMA boxes holding keys
@@ -196,19 +198,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
   __syncthreads();
   const float sum = s_sum[lane_row] + s_sum[kTile + lane_row];
 
-  // ---- O = P V ----
-  if (threadIdx.x == 0) {
+  // ---- O = P V ----  (warp 0 walks the loop with warp-uniform descriptors; lane 0 issues)
+  if (warp == 0) {
     mbar_wait(bar_v, 0);
     tc_fence_after();
+    const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t idm = idesc_bf16(64, 1), idt = idesc_bf16(16, 1);
-    const uint32_t av = smem_u32(smem + S::kVm), avt = smem_u32(smem + S::kVt);
+    const uint64_t dv = desc_sw128(smem_u32(smem + S::kVm)), dvt = desc_sw32(smem_u32(smem + S::kVt));
     const int ksteps = nk >> 4;
     for (int k = 0; k < ksteps; ++k) {
-      const uint32_t pa = tmem + (k < 8 ? k * 8 : kPHiCol + (k - 8) * 8);
-      tc_mma_ts(tmem + kOCol, pa, desc_sw128(av + k * 2048), idm, k ? 1u : 0u);
-      if (kTail) tc_mma_ts(tmem + kOTailCol, pa, desc_sw32(avt + k * 512), idt, k ? 1u : 0u);
+      const uint32_t pa = tm_u + (k < 8 ? k * 8 : kPHiCol + (k - 8) * 8);
+      if (lane == 0) {
+        tc_mma_ts(tm_u + kOCol, pa, dv + (uint32_t)(k * 128), idm, k ? 1u : 0u);
+        if (kTail) tc_mma_ts(tm_u + kOTailCol, pa, dvt + (uint32_t)(k * 32), idt, k ? 1u : 0u);
+      }
     }
-    tc_commit(bar_o);
+    if (lane == 0) tc_commit(bar_o);
   }
   __syncwarp();
   mbar_wait(bar_o, 0);

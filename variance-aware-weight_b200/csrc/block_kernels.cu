@@ -454,41 +454,50 @@ dit_block_finish_kernel(const float* __restrict__ pA, const float* __restrict__ 
                         long long ldm, float* __restrict__ dmod, bf16* __restrict__ dmod_b,
                         float* __restrict__ g_fc2_b, float* __restrict__ g_proj_b, float* __restrict__ g_ada_b,
                         int accumulate) {
-  __shared__ float red[16][8][33];
+  // blockIdx.y selects the partial buffer; each buffer feeds two of the eight outputs:
+  //   y = 0: pA -> fc2.bias (gate-weighted q0), d gate_mlp (slot 5, q1)      y = 1: pB -> slots 3, 4
+  //   y = 2: pC -> proj.bias (gate-weighted q0), d gate_msa (slot 2, q1)     y = 3: pD -> slots 0, 1
+  __shared__ float red[16][2][33];
   const int cx = threadIdx.x & 31, ny = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
-  float tot[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 0..5: adaLN bias slots, 6: fc2.bias, 7: proj.bias
+  const int which = blockIdx.y;
+  const float* part = which == 0 ? pA : which == 1 ? pB : which == 2 ? pC : pD;
+  const int slot0 = which == 1 ? 3 : which == 3 ? 0 : -1;            // d mod slot fed by q0 (-1: q0 feeds a bias grad)
+  const int slot1 = which == 0 ? 5 : which == 1 ? 4 : which == 2 ? 2 : 1;
+  const int gate_slot = which == 0 ? 5 : 2;
+  float t0 = 0.f, t1 = 0.f;
   if (col < D) {
     for (int n = ny; n < B; n += 16) {
-      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f, d0 = 0.f, d1 = 0.f;
+      float q0 = 0.f, q1 = 0.f;
       for (int c = 0; c < ch; ++c) {
         const long long o = (((long long)n * ch + c) * 2) * D + col;
-        a0 += pA[o]; a1 += pA[o + D];
-        b0 += pB[o]; b1 += pB[o + D];
-        c0 += pC[o]; c1 += pC[o + D];
-        d0 += pD[o]; d1 += pD[o + D];
+        q0 += part[o];
+        q1 += part[o + D];
       }
-      const float v[6] = {d0, d1, c1, b0, b1, a1};
-      float* dm = dmod + (long long)n * ldm + col;
-      bf16* db = dmod_b + (long long)n * ldm + col;
-#pragma unroll
-      for (int sl = 0; sl < 6; ++sl) {
-        dm[(long long)sl * D] = v[sl];
-        db[(long long)sl * D] = __float2bfloat16(v[sl]);
-        tot[sl] += v[sl];
+      const long long mo = (long long)n * ldm + col;
+      dmod[mo + (long long)slot1 * D] = q1;
+      dmod_b[mo + (long long)slot1 * D] = __float2bfloat16(q1);
+      t1 += q1;
+      if (slot0 >= 0) {
+        dmod[mo + (long long)slot0 * D] = q0;
+        dmod_b[mo + (long long)slot0 * D] = __float2bfloat16(q0);
+        t0 += q0;
+      } else {
+        t0 += mod[mo + (long long)gate_slot * D] * q0;
       }
-      tot[6] += mod[(long long)n * ldm + 5 * D + col] * a0;
-      tot[7] += mod[(long long)n * ldm + 2 * D + col] * c0;
     }
   }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) red[ny][k][cx] = tot[k];
+  red[ny][0][cx] = t0;
+  red[ny][1][cx] = t1;
   __syncthreads();
-  if (ny < 8 && col < D) {   // sample-lane ny folds quantity ny over the 16 lanes, in order
+  if (ny < 2 && col < D) {   // sample-lane ny folds quantity ny over the 16 lanes, in order
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) s += red[i][ny][cx];
-    float* dst = ny < 6 ? g_ada_b + (long long)ny * D + col : (ny == 6 ? g_fc2_b + col : g_proj_b + col);
+    float* dst;
+    if (ny == 1) dst = g_ada_b + (long long)slot1 * D + col;
+    else if (slot0 >= 0) dst = g_ada_b + (long long)slot0 * D + col;
+    else dst = (which == 0 ? g_fc2_b : g_proj_b) + col;
     *dst = accumulate ? *dst + s : s;
   }
 }
@@ -645,7 +654,7 @@ extern "C" int vaw_dit_block_finish(const float* pA, const float* pB, const floa
   VAW_CHECK_ARG(pA && pB && pC && pD && mod && dmod && dmod_b && g_fc2_b && g_proj_b && g_ada_b && B > 0 && chunks > 0 &&
                     D > 0,
                 "vaw_dit_block_finish: bad arguments");
-  dit_block_finish_kernel<<<(D + 31) / 32, 512, 0, stream>>>(pA, pB, pC, pD, B, chunks, D, mod, ldm, dmod, (bf16*)dmod_b,
+  dit_block_finish_kernel<<<dim3((D + 31) / 32, 4), 512, 0, stream>>>(pA, pB, pC, pD, B, chunks, D, mod, ldm, dmod, (bf16*)dmod_b,
                                                             g_fc2_b, g_proj_b, g_ada_b, accumulate);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
