@@ -63,6 +63,10 @@ int vaw_device_check(void); /* 0 iff the current device is compute capability 10
  * path.  t != NULL: tab_* are [T] fp32 tables gathered by t[n] (int64).  t == NULL: tab_* are per-sample [N]
  * arrays (FlowMatching.q_sample, :1273-1277).  tab_c0/tab_c1: posterior_mean_coef1/2 (PREVIOUS_X) or
  * d_alpha/d_sigma (VECTOR); may be NULL otherwise.  target may be NULL (EPSILON / START_X need no tensor). */
+/* sample_from_latent (tools/trainer.py:21-25), the step before the path: latent [N, 2C, H, W] holds
+ * (mean | std) along channels; out[N, C, H, W] = (mean + std * eps) * scale, bit-exact with the reference's fp32 ops. */
+int vaw_sample_from_latent(const float* latent, const float* eps, float* out, long long N, long long chw, float scale,
+                           vaw_stream_t stream);
 int vaw_qsample_target(const float* x0, const float* noise, const long long* t, const float* tab_alpha,
                        const float* tab_sigma, const float* tab_c0, const float* tab_c1, float* x_t, float* target,
                        int mean_type, long long N, long long chw, vaw_stream_t stream);
@@ -214,7 +218,12 @@ int vaw_align_mse(const void* zs, int zs_dtype, const void* feat, int feat_dtype
  * One pass: p, m, v updated in place from g * grad_scale; p_bf16 (nullable) refreshed; ema (nullable) updated.        */
 int vaw_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, float* ema, long long n, double lr,
                    double beta1, double beta2, double eps, double weight_decay, long long step, double grad_scale,
-                   double ema_decay, vaw_stream_t stream);
+                   double ema_decay, const float* clip_coef, vaw_stream_t stream);
+/* Global L2 norm of the flat gradient buffer and the clip_grad_norm_ coefficient (tools/trainer.py:60-62), kept on the
+ * device: out[0] = ||grad_scale * g||, out[1] = min(1, max_norm / (out[0] + 1e-6)); pass out + 1 as clip_coef above.
+ * part: 1024 floats of scratch. */
+int vaw_grad_clip_coef(const float* g, long long n, double grad_scale, double max_norm, float* part, float* out,
+                       vaw_stream_t stream);
 
 /* ---- DiT engine: forward / backward of the whole denoiser as one call each (models/dit.py:157-280) ----------------- */
 typedef struct vaw_dit_cfg {

@@ -143,6 +143,15 @@ def weight_lut(tb, mean_type, weight_type, p2_k=1.0, p2_gamma=1.0):
     return loss_weight(mean_type, weight_type, a, s, p2_k, p2_gamma)
 
 
+def sample_from_latent(latent, eps, latent_scale=1.0):
+    """tools/trainer.py:21-25 with the draw made explicit: latent [N, 2C, ...] = (mean | std) -> (mean + std*eps)*scale,
+    every fp32 operation rounded separately (torch elementwise order)."""
+    latent = np.asarray(latent, dtype=np.float32)
+    c = latent.shape[1] // 2
+    mean, std = latent[:, :c], latent[:, c:]
+    return ((mean + std * np.asarray(eps, dtype=np.float32)).astype(np.float32) * np.float32(latent_scale)).astype(np.float32)
+
+
 def mean_flat(x):
     return x.reshape(x.shape[0], -1).mean(axis=1, dtype=np.float32)
 

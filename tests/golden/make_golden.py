@@ -88,6 +88,18 @@ def diffusion_golden():
         terms["loss"].mean().backward()
         out[f"mse_{mean}_{wt}"] = terms["mse"].detach().float().numpy()
         out[f"grad_{mean}_{wt}"] = mo.grad.numpy()
+    # sample_from_latent (tools/trainer.py:21-25) with its randn_like pinned to a recorded tensor
+    import tools.trainer as rtr   # noqa: E402  (reference)
+    latent = torch.randn(5, 8, 4, 4, generator=g)
+    latent[:, 4:] = latent[:, 4:].abs() * 0.3
+    lat_eps = torch.randn(5, 4, 4, 4, generator=g)
+    orig = torch.randn_like
+    torch.randn_like = lambda *a, **k: lat_eps.clone()
+    try:
+        lat_out = rtr.sample_from_latent(latent, 0.18215)
+    finally:
+        torch.randn_like = orig
+    out.update(latent=latent.numpy(), latent_eps=lat_eps.numpy(), latent_out=lat_out.numpy())
     np.savez_compressed(os.path.join(HERE, "diffusion_golden.npz"), **out)
     print("diffusion_golden.npz", len(out), "arrays")
 
@@ -236,6 +248,9 @@ def unet_golden():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "diffusion":
+        diffusion_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "unet":
         unet_golden()
         sys.exit(0)

@@ -134,3 +134,27 @@ def test_align_loss_kernel_vs_torch():
     assert ((zs.grad.float() - z2.grad).norm() / z2.grad.norm()).item() < 5e-3
     with pytest.raises(ValueError):
         gd.compute_align_loss(feat, zs, "nope")
+
+
+def test_sample_from_latent_bit_exact_and_seeded():
+    """tools/trainer.py:21-25: the kernel against the reference golden (bit-exact, explicit noise through the C ABI) and
+    the Python mirror against the same formula in torch with the same generator state."""
+    import ctypes as C
+    from vaw_b200 import _lib as L
+    from vaw_b200.tools import trainer as vtr
+    g = np.load(os.path.join(G, "diffusion_golden.npz"))
+    lat, eps = torch.from_numpy(g["latent"]).to(DEV), torch.from_numpy(g["latent_eps"]).to(DEV)
+    out = torch.empty_like(eps)
+    L.call("vaw_sample_from_latent", lat.data_ptr(), eps.data_ptr(), out.data_ptr(), lat.shape[0], eps[0].numel(),
+           0.18215, L.stream_ptr())
+    assert np.array_equal(out.cpu().numpy(), g["latent_out"])
+    big = torch.randn(64, 8, 32, 32, device=DEV)
+    torch.manual_seed(123)
+    got = vtr.sample_from_latent(big, 0.18215)
+    torch.manual_seed(123)
+    mean, std = torch.chunk(big, 2, dim=1)
+    want = (mean + std * torch.randn_like(mean)) * 0.18215
+    assert torch.equal(got, want)
+    assert vtr.sample_from_latent(big[:0], 1.0).shape == (0, 4, 32, 32)
+    with pytest.raises(L.VawError):
+        vtr.sample_from_latent(big.cpu())

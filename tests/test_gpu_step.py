@@ -74,3 +74,41 @@ def test_three_steps_vs_oracle_trainer():
         num += float(((got - want) ** 2).sum())
         den += float(((want - init) ** 2).sum())
     assert (num / den) ** 0.5 < 0.15, (num / den) ** 0.5
+
+
+def test_fused_adamw_clip_and_ema_vs_torch():
+    """FusedAdamW(step(max_grad_norm), ema_decay) against torch.optim.AdamW + clip_grad_norm_ + the reference's ema()
+    (tools/trainer.py:12-18,60-62) on the same gradients: same update, same EMA, no host sync in the fused path."""
+    import copy
+    from vaw_b200.models.dit import DiT
+    from vaw_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+    m = DiT(image_size=16, patch_size=2, in_channels=4, hidden_size=128, depth=2, num_heads=2, class_dropout_prob=0.0,
+            num_classes=10).to("cuda")
+    dezero(m)
+    x = torch.randn(4, 4, 16, 16, device="cuda"); t = torch.rand(4, device="cuda") * 999
+    y = torch.randint(0, 10, (4,), device="cuda")
+    opt = FusedAdamW(m, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.01, ema_decay=0.99)
+    ref_p = {k: p.detach().clone() for k, p in m.named_parameters()}
+    ref_params = [torch.nn.Parameter(v.clone()) for v in ref_p.values()]
+    ref_opt = torch.optim.AdamW(ref_params, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.01, eps=1e-8)
+    ema_ref = [v.clone() for v in ref_p.values()]
+    for it in range(3):
+        out, _ = m(x, t, y)
+        (out.float() ** 2).sum().backward()          # large gradients: the clip is active
+        for rp, p in zip(ref_params, m.parameters()):   # frozen tensors (pos_embed) have no gradient on either side
+            rp.grad = None if p.grad is None else p.grad.detach().clone()
+        total = torch.nn.utils.clip_grad_norm_(ref_params, 0.5)
+        ref_opt.step()
+        with torch.no_grad():
+            for e, rp in zip(ema_ref, ref_params):
+                e.copy_(e * 0.99 + rp.detach() * 0.01)
+        opt.step(max_grad_norm=0.5)
+        opt.zero_grad()
+        norm, coef = opt.grad_norm.tolist()
+        assert abs(norm - float(total)) <= 1e-4 * float(total)
+        assert coef < 1.0 and abs(coef - 0.5 / (float(total) + 1e-6)) < 1e-5
+    ema_sd = opt.ema_state_dict()
+    for (k, p), rp, e in zip(m.named_parameters(), ref_params, ema_ref):
+        torch.testing.assert_close(p.detach(), rp.detach(), rtol=2e-5, atol=2e-6, msg=k)
+        torch.testing.assert_close(ema_sd[k], e, rtol=2e-5, atol=2e-6, msg=k)

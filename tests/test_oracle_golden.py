@@ -71,6 +71,10 @@ def test_qsample_target_bit_exact(dg, mean):
     assert np.array_equal(odiff.target(tb, mean, dg["x0"], dg["t"], dg["eps"]), dg[f"target_{mean}"])
 
 
+def test_sample_from_latent_bit_exact(dg):
+    assert np.array_equal(odiff.sample_from_latent(dg["latent"], dg["latent_eps"], 0.18215), dg["latent_out"])
+
+
 @pytest.mark.parametrize("mean,wt", [("EPSILON", "lambda"), ("START_X", "lambda"), ("VELOCITY", "min_snr_5"),
                                      ("PREVIOUS_X", "constant"), ("EPSILON", "min_snr_5")])
 def test_training_losses_mse_and_grad(dg, mean, wt):

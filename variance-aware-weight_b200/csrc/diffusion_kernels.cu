@@ -205,11 +205,37 @@ scale_rows_kernel(const T* __restrict__ x, const float* __restrict__ s, T* __res
   }
 }
 
+// sample_from_latent (tools/trainer.py:21-25): latent [N, 2C, H, W] = (mean | std) along channels;
+// out = (mean + std * eps) * scale with every product / sum rounded separately (torch's elementwise sequence).
+__global__ void __launch_bounds__(256)
+sample_from_latent_kernel(const float* __restrict__ latent, const float* __restrict__ eps, float* __restrict__ out,
+                          long long N, long long chw, float scale) {
+  const long long total = N * chw;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long n = i / chw, r = i - n * chw;
+    const float mean = latent[n * 2 * chw + r], sd = latent[n * 2 * chw + chw + r];
+    out[i] = __fmul_rn(__fadd_rn(mean, __fmul_rn(sd, eps[i])), scale);
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
+extern "C" int vaw_sample_from_latent(const float* latent, const float* eps, float* out, long long N, long long chw,
+                                      float scale, cudaStream_t stream) {
+  VAW_CHECK_ARG(latent && eps && out && N >= 0 && chw >= 0, "vaw_sample_from_latent: bad arguments");
+  if (N * chw == 0) return VAW_OK;
+  long long blocks = (N * chw + 255) / 256;
+  const long long cap = (long long)vaw_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  sample_from_latent_kernel<<<(unsigned)blocks, 256, 0, stream>>>(latent, eps, out, N, chw, scale);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
 extern "C" int vaw_qsample_target(const float* x0, const float* noise, const long long* t, const float* tab_alpha,
                                   const float* tab_sigma, const float* tab_c0, const float* tab_c1, float* x_t,
                                   float* target, int mean_type, long long N, long long chw, cudaStream_t stream) {

@@ -148,7 +148,9 @@ __global__ void colsum_f32_small_kernel(const float* __restrict__ a, long long l
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              bf16* __restrict__ p_bf16, float* __restrict__ ema, long long n, float lr, float beta1, float beta2,
-             float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, float ema_decay) {
+             float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, float ema_decay,
+             const float* __restrict__ clip_coef) {
+  if (clip_coef) grad_scale *= __ldg(clip_coef);   // device-side clip_grad_norm_ coefficient (vaw_grad_clip_coef)
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -185,6 +187,52 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
       e.w = e.w * ema_decay + pa[3] * (1.f - ema_decay);
       reinterpret_cast<float4*>(ema)[i] = e;
     }
+  }
+}
+
+// Global gradient norm of the flat gradient buffer and the clip_grad_norm_ coefficient (trainer.py:60-62 ->
+// torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (||g||_2 + 1e-6))), kept on the device so that the optimizer
+// step needs no host synchronisation.  Two deterministic stages (fixed grid, fixed reduction tree).
+constexpr int kNormBlocks = 1024;
+__global__ void __launch_bounds__(256)
+grad_sqnorm_stage1(const float* __restrict__ g, long long n, float scale, float* __restrict__ part) {
+  __shared__ float red[8];
+  const long long n4 = n >> 2;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)kNormBlocks * 256) {
+    const float4 v = ldg_stream_f4(reinterpret_cast<const float4*>(g) + i);
+    const float a = v.x * scale, b = v.y * scale, c = v.z * scale, d = v.w * scale;
+    acc += (a * a + b * b) + (c * c + d * d);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float a = g[(n4 << 2) + threadIdx.x] * scale;
+    acc += a * a;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i];
+    part[blockIdx.x] = s;
+  }
+}
+__global__ void __launch_bounds__(256)
+grad_sqnorm_stage2(const float* __restrict__ part, float max_norm, float* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < kNormBlocks; i += 256) s += (double)part[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float norm = (float)sqrt(red[0]);
+    out[0] = norm;
+    out[1] = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
   }
 }
 
@@ -330,14 +378,27 @@ extern "C" int vaw_colsum_f32_small(const float* a, long long lda, int rows, int
 // step: 1-based optimizer step (bias corrections are computed on the host in double like torch does)
 extern "C" int vaw_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, float* ema, long long n,
                               double lr, double beta1, double beta2, double eps, double weight_decay, long long step,
-                              double grad_scale, double ema_decay, cudaStream_t stream) {
+                              double grad_scale, double ema_decay, const float* clip_coef, cudaStream_t stream) {
   VAW_CHECK_ARG(p && g && m && v && n >= 0 && n % 4 == 0 && step >= 1, "vaw_adamw_step: bad arguments (n %% 4 == 0)");
   if (n == 0) return VAW_OK;
   const double bc1 = 1.0 - pow(beta1, (double)step);
   const double bc2 = 1.0 - pow(beta2, (double)step);
   adamw_kernel<<<grid_for(n / 4), 256, 0, stream>>>(p, g, m, v, (bf16*)p_bf16, ema, n, (float)lr, (float)beta1,
                                                     (float)beta2, (float)eps, (float)weight_decay, (float)bc1,
-                                                    (float)sqrt(bc2), (float)grad_scale, (float)ema_decay);
+                                                    (float)sqrt(bc2), (float)grad_scale, (float)ema_decay, clip_coef);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+// out[0] = ||grad_scale * g||_2, out[1] = clip coefficient min(1, max_norm / (out[0] + 1e-6)) (1 if max_norm <= 0);
+// part: scratch of 1024 floats.
+extern "C" int vaw_grad_clip_coef(const float* g, long long n, double grad_scale, double max_norm, float* part,
+                                  float* out, cudaStream_t stream) {
+  VAW_CHECK_ARG(g && part && out && n >= 0, "vaw_grad_clip_coef: bad arguments");
+  VAW_CHECK_ARG((reinterpret_cast<uintptr_t>(g) & 15) == 0, "vaw_grad_clip_coef: g must be 16-byte aligned");
+  grad_sqnorm_stage1<<<kNormBlocks, 256, 0, stream>>>(g, n, (float)grad_scale, part);
+  VAW_LAUNCH_CHECK();
+  grad_sqnorm_stage2<<<1, 256, 0, stream>>>(part, (float)max_norm, out);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }

@@ -17,7 +17,8 @@ from . import _lib as L
 from .parallel import FlatGradSync, dist_ready
 
 L.register("vaw_adamw_step", [C.c_void_p] * 6 + [C.c_longlong] + [C.c_double] * 5 + [C.c_longlong, C.c_double, C.c_double,
-                                                                                      C.c_void_p])
+                                                                                      C.c_void_p, C.c_void_p])
+L.register("vaw_grad_clip_coef", [C.c_void_p, C.c_longlong, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p])
 
 
 class FusedAdamW:
@@ -27,6 +28,8 @@ class FusedAdamW:
         self.ema_decay = ema_decay
         self.step_count = 0
         self.m = self.v = self.ema = None
+        self.grad_norm = self._norm_ws = None
+        self._ranges = []
         self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)]  # LambdaLR-style access
 
     def _ensure_state(self):
@@ -38,19 +41,55 @@ class FusedAdamW:
             self.v = torch.zeros_like(flat, requires_grad=False)
             if self.ema_decay is not None:
                 self.ema = flat.detach().clone()
+            # contiguous element ranges of the TRAINABLE tensors (frozen ones - DiT's pos_embed - get no update and no
+            # weight decay, like torch.optim.AdamW skipping parameters without a gradient); padding rides along
+            slots = sorted(((o, p.numel(), p.requires_grad) for p, o in self.model._slot_cache), key=lambda x: x[0])
+            ranges = []
+            for i, (o, n, train) in enumerate(slots):
+                end = slots[i + 1][0] if i + 1 < len(slots) else flat.numel()
+                if not train:
+                    continue
+                if ranges and ranges[-1][1] == o:
+                    ranges[-1][1] = end
+                else:
+                    ranges.append([o, end])
+            self._ranges = [(a, b - a) for a, b in ranges]
         return flat, gflat, shadow
 
     @torch.no_grad()
-    def step(self, grad_scale: float = 1.0):
+    def step(self, grad_scale: float = 1.0, max_grad_norm: float | None = None):
+        """One AdamW step.  `grad_scale` multiplies the gradients (GradScaler unscale / accumulation average);
+        `max_grad_norm` applies torch.nn.utils.clip_grad_norm_ semantics (trainer.py:60-62) without a host sync: the
+        norm and the clip coefficient stay on the device (`self.grad_norm` holds [norm, coef] after the call)."""
         flat, gflat, shadow = self._ensure_state()
         self.step_count += 1
         g = self.param_groups[0]
-        L.call("vaw_adamw_step", flat.data_ptr(), gflat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-               shadow.data_ptr(), L.ptr(self.ema), flat.numel(), float(g["lr"]), float(g["betas"][0]),
-               float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self.step_count, float(grad_scale),
-               float(self.ema_decay if self.ema_decay is not None else 0.0), L.stream_ptr())
+        clip = None
+        if max_grad_norm:
+            if self.grad_norm is None or self.grad_norm.device != flat.device:
+                self.grad_norm = torch.zeros(2, device=flat.device)
+                self._norm_ws = torch.empty(1024, device=flat.device)
+            L.call("vaw_grad_clip_coef", gflat.data_ptr(), gflat.numel(), float(grad_scale), float(max_grad_norm),
+                   self._norm_ws.data_ptr(), self.grad_norm.data_ptr(), L.stream_ptr())
+            clip = self.grad_norm.data_ptr() + 4
+        for off, n in self._ranges:
+            L.call("vaw_adamw_step", flat.data_ptr() + 4 * off, gflat.data_ptr() + 4 * off, self.m.data_ptr() + 4 * off,
+                   self.v.data_ptr() + 4 * off, shadow.data_ptr() + 2 * off,
+                   self.ema.data_ptr() + 4 * off if self.ema is not None else None, n, float(g["lr"]),
+                   float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
+                   self.step_count, float(grad_scale), float(self.ema_decay if self.ema_decay is not None else 0.0),
+                   clip, L.stream_ptr())
         # the kernel refreshed the bf16 shadow itself: mark it current so the next forward skips the cast pass
         self.model._shadow_version = sum(p._version for p, _ in self.model._slot_cache)
+
+    def ema_state_dict(self):
+        """The EMA weights (trainer.py:12-18 keeps them in a second model) under the model's parameter names, as views
+        of the flat EMA buffer; load them into a model copy with load_state_dict(..., strict=False)."""
+        if self.ema is None:
+            raise L.VawError("FusedAdamW was built without ema_decay")
+        by_id = {id(p): o for p, o in self.model._slot_cache}
+        return {k: self.ema[by_id[id(p)]:by_id[id(p)] + p.numel()].view(p.shape)
+                for k, p in self.model.named_parameters() if id(p) in by_id}
 
     def zero_grad(self, set_to_none: bool = True):
         for p in self.model.parameters():
