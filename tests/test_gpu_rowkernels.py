@@ -114,3 +114,21 @@ def test_gate_bwd(B, T, D, chunks, gated):
     assert relerr(part[:, :, 0].sum(1), dx.view(B, T, D).sum(1)) < 1e-5
     if gated:
         assert relerr(part[:, :, 1].sum(1), (dx * y.float()).view(B, T, D).sum(1)) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,rows", [(16384, 3456, 1496), (1000, 4608, 256), (777, 130, 64), (64, 72, 8), (4096, 2050, 512)])
+@pytest.mark.parametrize("acc", [0, 1])
+def test_colsum_bf16(M, N, rows, acc):
+    """Bias-gradient column sums (16-byte-load kernel for N % 8 == 0, 4-byte fallback otherwise), deterministic."""
+    L.register("vaw_colsum_bf16", [P, C.c_longlong, C.c_int, C.c_int, P, C.c_int, P, C.c_int, P])
+    torch.manual_seed(N)
+    a = torch.randn(M, N, device=DEV).bfloat16()
+    chunks = -(-M // rows)
+    part = torch.empty(chunks * N + 1024, device=DEV)
+    out = torch.ones(N, device=DEV)
+    L.call("vaw_colsum_bf16", a.data_ptr(), N, M, N, part.data_ptr(), rows, out.data_ptr(), acc, L.stream_ptr())
+    want = a.float().sum(0) + (1.0 if acc else 0.0)
+    assert relerr(out, want) < 1e-5
+    out2 = torch.ones(N, device=DEV)
+    L.call("vaw_colsum_bf16", a.data_ptr(), N, M, N, part.data_ptr(), rows, out2.data_ptr(), acc, L.stream_ptr())
+    assert torch.equal(out, out2)

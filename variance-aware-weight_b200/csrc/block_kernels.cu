@@ -534,6 +534,45 @@ colsum_bf16_stage1(const bf16* __restrict__ a, long long lda, int M, int N, int 
     if (c < N) part[(long long)blockIdx.y * N + c] = s;
   }
 }
+// 16-byte loads: a warp covers 4 rows x 64 columns per instruction (lane = row l/8, 8 columns (l%8)*8); the four row
+// sub-lanes are folded with shuffles, the eight warps through shared memory, both in fixed order.
+__global__ void __launch_bounds__(256)
+colsum_bf16_stage1_v8(const bf16* __restrict__ a, long long lda, int M, int N, int rows_per_chunk,
+                      float* __restrict__ part) {
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int sub = lane >> 3, cl = (lane & 7) * 8;
+  const int col = blockIdx.x * 64 + cl;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(r0 + rows_per_chunk, M);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < N) {
+#pragma unroll 4
+    for (int r = r0 + rg * 4 + sub; r < r1; r += 32) {
+      const uint4 v = ldg_stream_u4(reinterpret_cast<const uint4*>(a + (long long)r * lda + col));
+      const float2 f0 = unpack_bf16(v.x), f1 = unpack_bf16(v.y), f2 = unpack_bf16(v.z), f3 = unpack_bf16(v.w);
+      s[0] += f0.x; s[1] += f0.y; s[2] += f1.x; s[3] += f1.y;
+      s[4] += f2.x; s[5] += f2.y; s[6] += f3.x; s[7] += f3.y;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    s[k] += __shfl_xor_sync(0xffffffffu, s[k], 8);
+    s[k] += __shfl_xor_sync(0xffffffffu, s[k], 16);
+  }
+  __shared__ float red[8][64];
+  if (sub == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[rg][cl + k] = s[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < N) part[(long long)blockIdx.y * N + c] = t;
+  }
+}
 __global__ void __launch_bounds__(256)
 colsum_stage2(const float* __restrict__ part, int chunks, int N, float* __restrict__ out, int accumulate) {
   const int c = blockIdx.x * 256 + threadIdx.x;
@@ -665,7 +704,10 @@ extern "C" int vaw_colsum_bf16(const void* a, long long lda, int M, int N, float
                                float* out, int accumulate, cudaStream_t stream) {
   VAW_CHECK_ARG(a && part && out && M > 0 && N > 0 && N % 2 == 0 && rows_per_chunk > 0, "vaw_colsum_bf16: bad arguments");
   const int chunks = (M + rows_per_chunk - 1) / rows_per_chunk;
-  colsum_bf16_stage1<<<dim3((N + 63) / 64, chunks), 256, 0, stream>>>((const bf16*)a, lda, M, N, rows_per_chunk, part);
+  if (N % 8 == 0 && lda % 8 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0)
+    colsum_bf16_stage1_v8<<<dim3((N + 63) / 64, chunks), 256, 0, stream>>>((const bf16*)a, lda, M, N, rows_per_chunk, part);
+  else
+    colsum_bf16_stage1<<<dim3((N + 63) / 64, chunks), 256, 0, stream>>>((const bf16*)a, lda, M, N, rows_per_chunk, part);
   VAW_LAUNCH_CHECK();
   colsum_stage2<<<(N + 255) / 256, 256, 0, stream>>>(part, chunks, N, out, accumulate);
   VAW_LAUNCH_CHECK();

@@ -724,6 +724,11 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
       const int tm = cand_pair[i] ? 256 : 128;
       const int units = cand_pair[i] ? sms / 2 : sms;
       const long long tiles = (long long)((a->M + tm - 1) / tm) * ((a->N + cand_bn[i] - 1) / cand_bn[i]);
+      // measured exceptions to the model (scripts/dev_perf.py): the 10-byte-per-element residual epilogues on a short
+      // K loop (proj: 74 vs 86 us) and weight gradients with less than one wave of pair tiles (wgrad proj: 61 vs 72 us)
+      // are faster on single CTAs
+      if (cand_pair[i] && (epi == EPI_GATE_RES || epi == EPI_RES) && nkb <= 24) continue;
+      if (cand_pair[i] && tail_ok && tiles < units) continue;
       const long long fullw = tiles / units, rem = tiles % units;
       double waves = (double)fullw;
       if (rem) {
