@@ -432,6 +432,46 @@ attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, floa
   delta[(b * H + h) * T + t] = acc;
 }
 
+// Coalesced version for 256 % H == 0: a CTA owns 256 consecutive (token, head) segments = a contiguous range of
+// 256 * HD / 8 16-byte chunks.  Thread i takes chunks i, i + 256, ... of O and dO (fully coalesced), leaves their partial
+// dot products in shared memory, then thread j folds the HD / 8 partials of segment j (stride HD / 8 is odd for hd 72:
+// conflict-free) and the results are written head-major, 256 / H consecutive tokens per head.
+template <int HD>
+__global__ void __launch_bounds__(256)
+attn_delta_coalesced_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta, int T,
+                            int H, long long n_seg) {
+  constexpr int CPS = HD / 8;   // 16-byte chunks per segment
+  __shared__ float partial[256 * CPS];
+  __shared__ float seg[256];
+  const long long seg0 = (long long)blockIdx.x * 256;
+  const long long nseg_here = min((long long)256, n_seg - seg0);
+  const uint4* po = reinterpret_cast<const uint4*>(o) + seg0 * CPS;
+  const uint4* pd = reinterpret_cast<const uint4*>(d_o) + seg0 * CPS;
+  const int nchunks = (int)nseg_here * CPS;
+#pragma unroll
+  for (int k = 0; k < CPS; ++k) {
+    const int i = threadIdx.x + 256 * k;
+    if (i < nchunks) partial[i] = dot8(__ldg(po + i), __ldg(pd + i));
+  }
+  __syncthreads();
+  if (threadIdx.x < nseg_here) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPS; ++k) acc += partial[threadIdx.x * CPS + k];
+    seg[threadIdx.x] = acc;
+  }
+  __syncthreads();
+  // segment s = token * H + head (within the CTA: tokens_per_cta = 256 / H whole tokens); write head-major
+  const int tpc = 256 / H;
+  const int hh = threadIdx.x / tpc, tl = threadIdx.x % tpc;
+  const long long token = seg0 / H + tl;          // global token index b * T + t
+  if (tl * H + hh < nseg_here) {
+    const long long b = token / T;
+    const int t = (int)(token - b * T);
+    delta[(b * H + hh) * T + t] = seg[tl * H + hh];
+  }
+}
+
 unsigned long long* g_attn_trace = nullptr;   // debug: device buffer of 128 stamps (vaw_attn_set_trace)
 
 template <int HD>
@@ -454,8 +494,12 @@ int launch_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* 
   }
   if (delta_ws) {
     const long long n = (long long)B * T * H;
-    attn_delta_kernel<HD><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const bf16*)o, (const bf16*)d_o, delta_ws, T, H,
-                                                                         n);
+    if (256 % H == 0)
+      attn_delta_coalesced_kernel<HD><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const bf16*)o, (const bf16*)d_o,
+                                                                                     delta_ws, T, H, n);
+    else
+      attn_delta_kernel<HD><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const bf16*)o, (const bf16*)d_o, delta_ws, T,
+                                                                           H, n);
     VAW_LAUNCH_CHECK();
   }
   const float scale = 1.0f / sqrtf((float)HD);

@@ -93,7 +93,17 @@ int ln_chunks(const vaw_dit_cfg& c) {
   // over at high occupancy, few enough that the per-CTA partial sums stay small
   int ch = (c.T + 31) / 32;
   while ((c.T + ch - 1) / ch > 64) ++ch;
-  return ch;
+  // wave quantisation: the staged LayerNorm backward runs 2 CTAs per SM; prefer a chunk count whose grid (B x chunks)
+  // nearly fills whole waves (B = 64, T = 256: 9 chunks -> 576 CTAs = 1.95 waves instead of 8 -> 1.73)
+  const int slots = 2 * vaw_num_sms();
+  int best = ch;
+  double best_eff = 0.0;
+  for (int k = ch; k <= 2 * ch + 2 && k <= c.T; ++k) {
+    const long long ctas = (long long)c.B * k;
+    const double eff = (double)ctas / (double)(((ctas + slots - 1) / slots) * slots);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = k; }
+  }
+  return best;
 }
 
 void carve(const vaw_dit_cfg& c, void* base, Ws& w) {
