@@ -176,6 +176,12 @@ int vaw_ln_fwd(const float* x, const float* shift, const float* scale, long long
 int vaw_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
                long long ld_mod, const float* weight, float* dx_io, int add_into, float* part, int rows_per_group,
                int groups, int chunks, int M, int D, vaw_stream_t stream);
+/* vaw_ln_bwd fused with the vaw_gate_bwd of the branch that follows in the backward pass (saves re-reading the residual
+ * gradient): afterwards dx_io = dx', dy_next = bf16(dx' * gate_next[group]), part_gate = (sum dx', sum dx' * y_next). */
+int vaw_ln_bwd_gate(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
+                    long long ld_mod, const float* weight, float* dx_io, int add_into, float* part, const void* y_next,
+                    const float* gate_next, long long ld_gate, void* dy_next, float* part_gate, int rows_per_group,
+                    int groups, int chunks, int M, int D, vaw_stream_t stream);
 int vaw_gate_bwd(const float* dx, const void* y, const float* gate, long long ld_gate, void* dy, float* part,
                  int rows_per_group, int groups, int chunks, int M, int D, vaw_stream_t stream);
 int vaw_finish_group(const float* part, int which, int groups, int chunks, int D, float* out, long long ld_out,

@@ -77,6 +77,14 @@ for ch in (4, 8, 16):
     dyo = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
     us = timeit(lambda: L.call("vaw_gate_bwd", dx.data_ptr(), dy.data_ptr(), mod.data_ptr(), 6 * D, dyo.data_ptr(), part.data_ptr(), T, B, ch, M, D, st()))
     print(f"gate_bwd chunks={ch}: {us:.1f} us  {M*D*8/us/1e3:.0f} GB/s")
+L.register("vaw_ln_bwd_gate", [C.c_void_p] * 5 + [C.c_longlong] + [C.c_void_p] * 2 + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p])
+for ch in (8, 9, 16):
+    part = torch.empty(B * ch * 2 * D, device=dev); part2 = torch.empty_like(part)
+    dyo = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    us = timeit(lambda: L.call("vaw_ln_bwd_gate", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), mod[:, D:].data_ptr(), 6 * D, None, dx.data_ptr(), 1, part.data_ptr(), dy.data_ptr(), mod.data_ptr(), 6 * D, dyo.data_ptr(), part2.data_ptr(), T, B, ch, M, D, st()))
+    print(f"ln_bwd_gate fused chunks={ch}: {us:.1f} us  {M*D*18/us/1e3:.0f} GB/s")
+    us = timeit(lambda: L.call("vaw_ln_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), mod[:, D:].data_ptr(), 6 * D, None, dx.data_ptr(), 1, part.data_ptr(), T, B, ch, M, D, st()))
+    print(f"ln_bwd chunks={ch}: {us:.1f} us")
 hd = D // H
 qkv = bf(B, T, 3, H, hd); o = torch.empty(B, T, H, hd, device=dev, dtype=torch.bfloat16); lse = torch.empty(B, H, T, device=dev)
 us = timeit(lambda: L.call("vaw_attn_fwd", qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, H, hd, st()))

@@ -15,6 +15,7 @@ P = C.c_void_p
 L.register("vaw_ln_fwd", [P] * 3 + [C.c_longlong, C.c_int] + [P] * 5 + [C.c_int, C.c_int, C.c_float, P])
 L.register("vaw_ln_bwd", [P] * 5 + [C.c_longlong] + [P] * 2 + [C.c_int, P] + [C.c_int] * 5 + [P])
 L.register("vaw_gate_bwd", [P] * 3 + [C.c_longlong] + [P] * 2 + [C.c_int] * 5 + [P])
+L.register("vaw_ln_bwd_gate", [P] * 5 + [C.c_longlong] + [P] * 2 + [C.c_int, P, P, P, C.c_longlong, P, P] + [C.c_int] * 5 + [P])
 L.register("vaw_finish_group", [P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_longlong, C.c_int, P])
 L.register("vaw_finish_all", [P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_longlong, P, C.c_int, P])
 
@@ -132,3 +133,41 @@ def test_colsum_bf16(M, N, rows, acc):
     out2 = torch.ones(N, device=DEV)
     L.call("vaw_colsum_bf16", a.data_ptr(), N, M, N, part.data_ptr(), rows, out2.data_ptr(), acc, L.stream_ptr())
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("B,T,D,chunks", [(4, 256, 1152, 9), (3, 64, 384, 2), (2, 100, 132, 4), (2, 257, 1536, 5)])
+@pytest.mark.parametrize("gated", [True, False])
+def test_ln_bwd_fused_with_next_gate_bwd(B, T, D, chunks, gated):
+    """vaw_ln_bwd_gate == vaw_ln_bwd followed by vaw_gate_bwd on the updated residual gradient (bit-identical dx and
+    LayerNorm partials; dy / gate partials to rounding), for the fused kernel (D <= 1280, D % 8 == 0) and its fallbacks."""
+    torch.manual_seed(D + chunks)
+    M = B * T
+    x = torch.randn(M, D, device=DEV); mod = torch.randn(B, 3 * D, device=DEV) * 0.3
+    scale, gate = mod[:, D:2 * D], mod[:, 2 * D:]
+    y = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    st = L.stream_ptr()
+    L.call("vaw_ln_fwd", x.data_ptr(), mod.data_ptr(), scale.data_ptr(), 3 * D, T, None, None, y.data_ptr(),
+           mean.data_ptr(), rstd.data_ptr(), M, D, 1e-6, st)
+    dy = torch.randn(M, D, device=DEV).bfloat16()
+    y_next = torch.randn(M, D, device=DEV).bfloat16()
+    dx0 = torch.randn(M, D, device=DEV)
+    # reference: two launches
+    dx_a = dx0.clone(); part_a = torch.empty(B, chunks, 2, D, device=DEV); pg_a = torch.empty_like(part_a)
+    dyn_a = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    L.call("vaw_ln_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), scale.data_ptr(), 3 * D, None,
+           dx_a.data_ptr(), 1, part_a.data_ptr(), T, B, chunks, M, D, st)
+    L.call("vaw_gate_bwd", dx_a.data_ptr(), y_next.data_ptr() if gated else None, gate.data_ptr() if gated else None,
+           3 * D, dyn_a.data_ptr(), pg_a.data_ptr(), T, B, chunks, M, D, st)
+    # fused
+    dx_b = dx0.clone(); part_b = torch.empty_like(part_a); pg_b = torch.full_like(part_a, float("nan"))
+    dyn_b = torch.empty_like(dyn_a)
+    L.call("vaw_ln_bwd_gate", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), scale.data_ptr(), 3 * D, None,
+           dx_b.data_ptr(), 1, part_b.data_ptr(), y_next.data_ptr() if gated else None, gate.data_ptr() if gated else None,
+           3 * D, dyn_b.data_ptr(), pg_b.data_ptr(), T, B, chunks, M, D, st)
+    assert relerr(dx_b, dx_a) < 1e-6
+    assert relerr(part_b.sum(1), part_a.sum(1)) < 1e-5
+    assert relerr(dyn_b, dyn_a) < 4e-3
+    assert relerr(pg_b[:, :, 0].sum(1), pg_a[:, :, 0].sum(1)) < 1e-5
+    if gated:
+        assert relerr(pg_b[:, :, 1].sum(1), pg_a[:, :, 1].sum(1)) < 1e-5

@@ -199,11 +199,23 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const fl
 // ---------------------------------------------------------------------------------------------------
 constexpr int kStagedBudget = 110592;  // bytes of staged rows per CTA (2 stages of x fp32 + dy bf16): 2 x 8 rows at D = 1152
 
-__global__ void __launch_bounds__(576, 2)
+// FUSE: the residual-branch backward of the NEXT branch rides along (vaw_ln_bwd_gate): with dx' the updated residual
+// gradient, dy_next = bf16(dx' * gate_next), part_gate = (sum dx', sum dx' * y_next) - exactly gate_bwd_kernel's outputs,
+// without re-reading dx' (75 MB per call at DiT-XL/2 B=64).  That variant runs fewer threads with more registers.
+struct GateFuse {
+  const bf16* y;       // [M, D] output of the next branch (saved in forward), null: plain residual
+  const float* gate;   // [groups, ld_gate] gate rows, null: plain residual
+  long long ld_gate;
+  bf16* dy;            // [M, D] out
+  float* part;         // [groups, chunks, 2, D] out
+};
+template <int MAXT, bool FUSE>
+__global__ void __launch_bounds__(MAXT, 2)
 ln_bwd_staged_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, const float* __restrict__ scale, long long ld_mod,
                      const float* __restrict__ weight, float* __restrict__ dx_io, int add_into,
-                     float* __restrict__ part, int rows_per_group, int chunks, int M, int D, int R, int nvp) {
+                     float* __restrict__ part, int rows_per_group, int chunks, int M, int D, int R, int nvp,
+                     GateFuse gf) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   // stage s: x [R, D] fp32 | dy [R, D] bf16 ; then per stage [4, R] floats (m1, m2, mean, rstd) ; then 2 mbarriers
   const size_t stage_bytes = (size_t)R * D * 6;
@@ -250,6 +262,8 @@ ln_bwd_staged_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, c
     A = make_float4(a.x + add1, a.y + add1, a.z + add1, a.w + add1);
   }
   float4 accB = make_float4(0.f, 0.f, 0.f, 0.f), accA = accB;
+  float4 accS = accB, accG = accB, gt = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (FUSE && gf.gate && owner) gt = __ldg(reinterpret_cast<const float4*>(gf.gate + (long long)group * gf.ld_gate) + cg);
 
   for (int sub = 0; sub < nsub; ++sub) {
     const int r0 = c_begin + sub * R;
@@ -298,12 +312,16 @@ ln_bwd_staged_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, c
     if (owner) {
       for (int rb = half; rb < nrows; rb += 4 * halves) {
         float4 prev[4];
+        uint2 yv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int r = rb + j * halves;
           prev[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          yv[j] = make_uint2(0u, 0u);
           if (add_into && r < nrows)
             prev[j] = ldg_stream_f4(reinterpret_cast<const float4*>(dx_io + (long long)(r0 + r) * D) + cg);
+          if (FUSE && gf.y && r < nrows)
+            yv[j] = ldg_stream_u2(reinterpret_cast<const uint2*>(gf.y + (long long)(r0 + r) * D) + cg);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -323,6 +341,15 @@ ln_bwd_staged_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, c
             *(reinterpret_cast<float4*>(dx_io + (long long)(r0 + r) * D) + cg) = out;
             accB.x += d0.x; accB.y += d0.y; accB.z += d1.x; accB.w += d1.y;
             accA.x += d0.x * h0; accA.y += d0.y * h1; accA.z += d1.x * h2; accA.w += d1.y * h3;
+            if (FUSE) {
+              uint2 ov;
+              ov.x = pack_bf16(out.x * gt.x, out.y * gt.y);
+              ov.y = pack_bf16(out.z * gt.z, out.w * gt.w);
+              *(reinterpret_cast<uint2*>(gf.dy + (long long)(r0 + r) * D) + cg) = ov;
+              const float2 y0 = unpack_bf16(yv[j].x), y1 = unpack_bf16(yv[j].y);
+              accS.x += out.x; accS.y += out.y; accS.z += out.z; accS.w += out.w;
+              accG.x += out.x * y0.x; accG.y += out.y * y0.y; accG.z += out.z * y1.x; accG.w += out.w * y1.y;
+            }
           }
         }
       }
@@ -331,23 +358,40 @@ ln_bwd_staged_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, c
     if (threadIdx.x == 0 && sub + 2 < nsub) issue(sub + 2);
   }
 
-  if (!part) return;
+  if (!part && !FUSE) return;
   // fold the halves in fixed order through shared memory (the staged rows are dead now)
-  float4* red = reinterpret_cast<float4*>(ln_smem);   // [halves - 1, 2, nvp] float4
+  constexpr int NACC = FUSE ? 4 : 2;
+  float4* red = reinterpret_cast<float4*>(ln_smem);   // [halves - 1, NACC, nvp] float4
   if (half > 0 && owner) {
-    red[((half - 1) * 2 + 0) * nvp + cg] = accB;
-    red[((half - 1) * 2 + 1) * nvp + cg] = accA;
+    red[((half - 1) * NACC + 0) * nvp + cg] = accB;
+    red[((half - 1) * NACC + 1) * nvp + cg] = accA;
+    if (FUSE) {
+      red[((half - 1) * NACC + 2) * nvp + cg] = accS;
+      red[((half - 1) * NACC + 3) * nvp + cg] = accG;
+    }
   }
   __syncthreads();
   if (half == 0 && owner) {
     for (int h = 1; h < halves; ++h) {
-      const float4 b = red[((h - 1) * 2 + 0) * nvp + cg], a = red[((h - 1) * 2 + 1) * nvp + cg];
+      const float4 b = red[((h - 1) * NACC + 0) * nvp + cg], a = red[((h - 1) * NACC + 1) * nvp + cg];
       accB.x += b.x; accB.y += b.y; accB.z += b.z; accB.w += b.w;
       accA.x += a.x; accA.y += a.y; accA.z += a.z; accA.w += a.w;
+      if (FUSE) {
+        const float4 c = red[((h - 1) * NACC + 2) * nvp + cg], g = red[((h - 1) * NACC + 3) * nvp + cg];
+        accS.x += c.x; accS.y += c.y; accS.z += c.z; accS.w += c.w;
+        accG.x += g.x; accG.y += g.y; accG.z += g.z; accG.w += g.w;
+      }
     }
-    float* dst = part + ((long long)group * chunks + chunk) * 2 * D;
-    *(reinterpret_cast<float4*>(dst) + cg) = accB;
-    *(reinterpret_cast<float4*>(dst + D) + cg) = accA;
+    if (part) {
+      float* dst = part + ((long long)group * chunks + chunk) * 2 * D;
+      *(reinterpret_cast<float4*>(dst) + cg) = accB;
+      *(reinterpret_cast<float4*>(dst + D) + cg) = accA;
+    }
+    if (FUSE) {
+      float* dst = gf.part + ((long long)group * chunks + chunk) * 2 * D;
+      *(reinterpret_cast<float4*>(dst) + cg) = accS;
+      *(reinterpret_cast<float4*>(dst + D) + cg) = accG;
+    }
   }
 }
 
@@ -618,9 +662,11 @@ extern "C" int vaw_ln_fwd(const float* x, const float* shift, const float* scale
 
 // chunks: number of partial rows per group (ceil(rows_per_group / chunks) must be <= 64); part must hold
 // groups * chunks * 2 * D floats (may be NULL when neither dA nor dB is wanted).  groups * rows_per_group covers M.
-extern "C" int vaw_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
-                          long long ld_mod, const float* weight, float* dx_io, int add_into, float* part,
-                          int rows_per_group, int groups, int chunks, int M, int D, cudaStream_t stream) {
+namespace {
+// common launcher: fuse == nullptr -> plain LayerNorm backward
+int launch_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
+                  long long ld_mod, const float* weight, float* dx_io, int add_into, float* part, int rows_per_group,
+                  int groups, int chunks, int M, int D, const GateFuse* fuse, cudaStream_t stream) {
   VAW_CHECK_ARG(dy && x && mean && rstd && dx_io && M > 0, "vaw_ln_bwd: bad arguments");
   VAW_CHECK_ARG(D % 4 == 0, "vaw_ln_bwd: D=%d must be a multiple of 4", D);
   VAW_CHECK_ARG(rows_per_group > 0 && groups > 0 && chunks > 0 && (long long)groups * rows_per_group >= M,
@@ -629,19 +675,27 @@ extern "C" int vaw_ln_bwd(const void* dy, const float* x, const float* mean, con
   int R = kStagedBudget / (12 * D);   // rows per stage, two stages
   if (R > 32) R = 32;
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0;
-  if (D % 8 == 0 && R >= 4 && nvp <= 576 && aligned) {
+  const int max_threads = fuse ? 320 : 576;
+  if (D % 8 == 0 && R >= 4 && nvp <= max_threads && aligned) {
     int halves = 1;
-    while (halves * 2 * nvp <= 576 && halves * 2 * 4 <= R) halves *= 2;
+    while (halves * 2 * nvp <= max_threads && halves * 2 * 4 <= R) halves *= 2;
     const size_t smem = 2 * (size_t)R * D * 6 + (size_t)R * 32 + 16;
     static bool configured = false;
     if (!configured) {
-      VAW_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      VAW_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_staged_kernel<576, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kStagedBudget + 32 * 32 + 16));
+      VAW_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_staged_kernel<320, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kStagedBudget + 32 * 32 + 16));
       configured = true;
     }
-    ln_bwd_staged_kernel<<<dim3(chunks, groups), halves * nvp, smem, stream>>>(
-        (const bf16*)dy, x, mean, rstd, scale, ld_mod, weight, dx_io, add_into, part, rows_per_group, chunks, M, D, R,
-        nvp);
+    if (fuse)
+      ln_bwd_staged_kernel<320, true><<<dim3(chunks, groups), halves * nvp, smem, stream>>>(
+          (const bf16*)dy, x, mean, rstd, scale, ld_mod, weight, dx_io, add_into, part, rows_per_group, chunks, M, D, R,
+          nvp, *fuse);
+    else
+      ln_bwd_staged_kernel<576, false><<<dim3(chunks, groups), halves * nvp, smem, stream>>>(
+          (const bf16*)dy, x, mean, rstd, scale, ld_mod, weight, dx_io, add_into, part, rows_per_group, chunks, M, D, R,
+          nvp, GateFuse{});
     VAW_LAUNCH_CHECK();
     return VAW_OK;
   }
@@ -651,7 +705,40 @@ extern "C" int vaw_ln_bwd(const void* dy, const float* x, const float* mean, con
   ln_bwd_kernel<<<dim3(chunks, groups), threads_for_columns(D), 0, stream>>>(
       (const bf16*)dy, x, mean, rstd, scale, ld_mod, weight, dx_io, add_into, part, rows_per_group, chunks, M, D);
   VAW_LAUNCH_CHECK();
+  if (fuse) {   // shapes outside the fused kernel's range: the two-kernel sequence it replaces
+    gate_bwd_kernel<<<dim3(chunks, groups), threads_for_columns(D), 0, stream>>>(dx_io, fuse->y, fuse->gate, fuse->ld_gate,
+                                                                                fuse->dy, fuse->part, rows_per_group,
+                                                                                chunks, M, D);
+    VAW_LAUNCH_CHECK();
+  }
   return VAW_OK;
+}
+}  // namespace
+
+extern "C" int vaw_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
+                          long long ld_mod, const float* weight, float* dx_io, int add_into, float* part,
+                          int rows_per_group, int groups, int chunks, int M, int D, cudaStream_t stream) {
+  return launch_ln_bwd(dy, x, mean, rstd, scale, ld_mod, weight, dx_io, add_into, part, rows_per_group, groups, chunks, M,
+                       D, nullptr, stream);
+}
+
+// LayerNorm backward fused with the residual-branch backward of the branch that follows in the backward pass:
+// afterwards dx_io holds the updated residual gradient dx', dy_next = bf16(dx' * gate_next[group]) and part_gate holds
+// (sum dx', sum dx' * y_next) per chunk - what vaw_ln_bwd followed by vaw_gate_bwd(dx_io, y_next, gate_next, ...) give.
+extern "C" int vaw_ln_bwd_gate(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
+                               long long ld_mod, const float* weight, float* dx_io, int add_into, float* part,
+                               const void* y_next, const float* gate_next, long long ld_gate, void* dy_next,
+                               float* part_gate, int rows_per_group, int groups, int chunks, int M, int D,
+                               cudaStream_t stream) {
+  VAW_CHECK_ARG(dy_next && part_gate, "vaw_ln_bwd_gate: dy_next and part_gate are required");
+  GateFuse gf;
+  gf.y = reinterpret_cast<const bf16*>(y_next);
+  gf.gate = gate_next;
+  gf.ld_gate = ld_gate;
+  gf.dy = reinterpret_cast<bf16*>(dy_next);
+  gf.part = part_gate;
+  return launch_ln_bwd(dy, x, mean, rstd, scale, ld_mod, weight, dx_io, add_into, part, rows_per_group, groups, chunks, M,
+                       D, &gf, stream);
 }
 
 extern "C" int vaw_gate_bwd(const float* dx, const void* y, const float* gate, long long ld_gate, void* dy,

@@ -80,7 +80,7 @@ struct Ws {
   float* dx;
   bf16 *dy, *dh, *dqkv, *d_o, *dxn, *dtok, *dz, *dxa;
   float* attn_delta;   // [B*H*T] rowsum(dO*O) scratch of the attention backward
-  float *part, *part_b, *part_c, *part_d, *cpart, *dmod_all, *dmod_final, *dcs, *dc;
+  float *part, *part_a2, *part_b, *part_c, *part_d, *cpart, *dmod_all, *dmod_final, *dcs, *dc;
   bf16 *dmod_all_b, *dmod_final_b, *dc_b, *dth;
   float* split_ws;
   long long split_elems;
@@ -147,6 +147,7 @@ void carve(const vaw_dit_cfg& c, void* base, Ws& w) {
   w.dz = k.take<bf16>(2 * M * pd);
   w.dxa = k.take<bf16>(c.learn_align ? M * D : 0);
   w.part = k.take<float>(B * ln_chunks(c) * 2 * D);
+  w.part_a2 = k.take<float>(B * ln_chunks(c) * 2 * D);
   w.part_b = k.take<float>(B * ln_chunks(c) * 2 * D);
   w.part_c = k.take<float>(B * ln_chunks(c) * 2 * D);
   w.part_d = k.take<float>(B * ln_chunks(c) * 2 * D);
@@ -308,10 +309,27 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
   TRY(G(w.dtok, PPC, 1, w.xnf, D, 1, PPC, D, M, VAW_EPI_F32).out(Gd + L.off[P_FLIN_W]).acc(acc)
           .autosplit(w.split_ws, w.split_elems).run(s));
   TRY(G(w.dtok, PPC, 0, Pb + L.off[P_FLIN_W], D, 1, M, D, PPC, VAW_EPI_BF16).out(w.dxn).run(s));
-  TRY(vaw_ln_bwd(w.dxn, w.x[2 * c.depth], w.meanf, w.rstdf, w.mod_final + D, 2LL * D, nullptr, w.dx, 0, w.part, T, B,
-                 ch, M, D, s));
-  TRY(vaw_finish_group(w.part, 0, B, ch, D, w.dmod_final, 2LL * D, 0, s));      // d shift
-  TRY(vaw_finish_group(w.part, 1, B, ch, D, w.dmod_final + D, 2LL * D, 0, s));  // d scale
+  // Every LayerNorm backward also runs the gate * branch backward of the branch that FOLLOWS it in the backward pass
+  // (vaw_ln_bwd_gate): the updated residual gradient is used while it is still in registers instead of being re-read.
+  // pa(i) = partial buffer of block i's MLP-branch gate backward; two buffers alternate because block i's buffer is
+  // still unread (vaw_dit_block_finish at the end of block i) when block i-1's is produced.
+  auto pa = [&](int i) { return (i & 1) ? w.part_a2 : w.part; };
+  // the REPA projector injects an extra gradient into dx at the top of one block: that block's MLP gate backward must
+  // see it, so it cannot ride on the previous LayerNorm backward
+  auto injects = [&](int i) { return c.learn_align && i + 1 == c.encoder_depth && dzs != nullptr; };
+  {
+    const int i = c.depth - 1;
+    const float* mod = w.mod_all + (long long)i * 6 * D;
+    if (!injects(i)) {
+      TRY(vaw_ln_bwd_gate(w.dxn, w.x[2 * c.depth], w.meanf, w.rstdf, w.mod_final + D, 2LL * D, nullptr, w.dx, 0, w.part_d,
+                          w.blk[i].y_mlp, mod + 5 * D, ldm, w.dy, pa(i), T, B, ch, M, D, s));
+    } else {
+      TRY(vaw_ln_bwd(w.dxn, w.x[2 * c.depth], w.meanf, w.rstdf, w.mod_final + D, 2LL * D, nullptr, w.dx, 0, w.part_d, T,
+                     B, ch, M, D, s));
+    }
+  }
+  TRY(vaw_finish_group(w.part_d, 0, B, ch, D, w.dmod_final, 2LL * D, 0, s));      // d shift
+  TRY(vaw_finish_group(w.part_d, 1, B, ch, D, w.dmod_final + D, 2LL * D, 0, s));  // d scale
 
   for (int i = c.depth - 1; i >= 0; --i) {
     BlockWs& b = w.blk[i];
@@ -339,7 +357,8 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
     }
     // ---- MLP branch: x_out = x_mid + gate_mlp * fc2(gelu(fc1(modulate(LN(x_mid))))) ----
     // (the partial sums of the four row kernels below are folded by one vaw_dit_block_finish at the end of the block)
-    TRY(vaw_gate_bwd(w.dx, b.y_mlp, mod + 5 * D, ldm, w.dy, w.part, T, B, ch, M, D, s));
+    if (injects(i)) TRY(vaw_gate_bwd(w.dx, b.y_mlp, mod + 5 * D, ldm, w.dy, pa(i), T, B, ch, M, D, s));
+    // else: w.dy and pa(i) were produced by the LayerNorm backward that precedes this block in the backward pass
     TRY(G(w.dy, D, 1, b.h_act, Hd, 1, D, Hd, M, VAW_EPI_F32).out(Gd + L.off[pb + B_FC2_W]).acc(acc)
             .autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dy, D, 0, Pb + L.off[pb + B_FC2_W], Hd, 1, M, Hd, D, VAW_EPI_DGELU_TANH).out(w.dh).aux(b.h_pre).run(s));
@@ -347,10 +366,10 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
     TRY(G(w.dh, Hd, 1, b.xn2, D, 1, Hd, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_FC1_W]).acc(acc)
             .autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dh, Hd, 0, Pb + L.off[pb + B_FC1_W], D, 1, M, D, Hd, VAW_EPI_BF16).out(w.dxn).run(s));
-    TRY(vaw_ln_bwd(w.dxn, w.x[2 * i + 1], b.mean2, b.rstd2, mod + 4 * D, ldm, nullptr, w.dx, 1, w.part_b, T, B, ch, M, D,
-                   s));
     // ---- attention branch: x_mid = x_in + gate_msa * proj(attn(qkv(modulate(LN(x_in))))) ----
-    TRY(vaw_gate_bwd(w.dx, b.y_attn, mod + 2 * D, ldm, w.dy, w.part_c, T, B, ch, M, D, s));
+    // (its gate backward is fused into the MLP LayerNorm backward)
+    TRY(vaw_ln_bwd_gate(w.dxn, w.x[2 * i + 1], b.mean2, b.rstd2, mod + 4 * D, ldm, nullptr, w.dx, 1, w.part_b, b.y_attn,
+                        mod + 2 * D, ldm, w.dy, w.part_c, T, B, ch, M, D, s));
     TRY(G(w.dy, D, 1, b.attn_o, D, 1, D, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_PROJ_W]).acc(acc)
             .autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dy, D, 0, Pb + L.off[pb + B_PROJ_W], D, 1, M, D, D, VAW_EPI_BF16).out(w.d_o).run(s));
@@ -359,13 +378,18 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
     TRY(G(w.dqkv, 3LL * D, 1, b.xn1, D, 1, 3 * D, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_QKV_W]).acc(acc)
             .autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dqkv, 3LL * D, 0, Pb + L.off[pb + B_QKV_W], D, 1, M, D, 3 * D, VAW_EPI_BF16).out(w.dxn).run(s));
-    TRY(vaw_ln_bwd(w.dxn, w.x[2 * i], b.mean1, b.rstd1, mod + D, ldm, nullptr, w.dx, 1, w.part_d, T, B, ch, M, D, s));
+    if (i > 0 && !injects(i - 1)) {   // + the MLP-branch gate backward of block i-1
+      TRY(vaw_ln_bwd_gate(w.dxn, w.x[2 * i], b.mean1, b.rstd1, mod + D, ldm, nullptr, w.dx, 1, w.part_d,
+                          w.blk[i - 1].y_mlp, mod - 6 * D + 5 * D, ldm, w.dy, pa(i - 1), T, B, ch, M, D, s));
+    } else {
+      TRY(vaw_ln_bwd(w.dxn, w.x[2 * i], b.mean1, b.rstd1, mod + D, ldm, nullptr, w.dx, 1, w.part_d, T, B, ch, M, D, s));
+    }
     // adaLN_modulation.1 of this block: mod_i = silu(c) W_i^T + b_i.  Its gradient is final here, so the block's
     // whole parameter set can be all-reduced while the remaining blocks are still in backward.
     {
       bf16* dmod_b = w.dmod_all_b + (long long)i * 6 * D;
       // d mod (fp32 + bf16), d fc2.bias, d proj.bias and the adaLN bias gradient from the four partial buffers
-      TRY(vaw_dit_block_finish(w.part, w.part_b, w.part_c, w.part_d, B, ch, D, mod, ldm, dmod, dmod_b,
+      TRY(vaw_dit_block_finish(pa(i), w.part_b, w.part_c, w.part_d, B, ch, D, mod, ldm, dmod, dmod_b,
                                Gd + L.off[pb + B_FC2_B], Gd + L.off[pb + B_PROJ_B],
                                Gd + L.off[P_ADA_B] + (long long)i * 6 * D, acc, s));
       TRY(G(dmod_b, ldm, 1, w.c_silu, D, 1, 6 * D, D, B, VAW_EPI_F32)

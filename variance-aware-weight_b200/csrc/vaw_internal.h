@@ -66,6 +66,10 @@ int vaw_ln_fwd(const float* x, const float* shift, const float* scale, long long
 int vaw_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
                long long ld_mod, const float* weight, float* dx_io, int add_into, float* part, int rows_per_group,
                int groups, int chunks, int M, int D, cudaStream_t stream);
+int vaw_ln_bwd_gate(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
+                    long long ld_mod, const float* weight, float* dx_io, int add_into, float* part, const void* y_next,
+                    const float* gate_next, long long ld_gate, void* dy_next, float* part_gate, int rows_per_group,
+                    int groups, int chunks, int M, int D, cudaStream_t stream);
 int vaw_gate_bwd(const float* dx, const void* y, const float* gate, long long ld_gate, void* dy, float* part,
                  int rows_per_group, int groups, int chunks, int M, int D, cudaStream_t stream);
 int vaw_finish_group(const float* part, int which, int groups, int chunks, int D, float* out, long long ld_out,
