@@ -217,10 +217,11 @@ ln_bwd_staged_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, c
                      float* __restrict__ part, int rows_per_group, int chunks, int M, int D, int R, int nvp,
                      GateFuse gf) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
-  // stage s: x [R, D] fp32 | dy [R, D] bf16 ; then per stage [4, R] floats (m1, m2, mean, rstd) ; then 2 mbarriers
+  // stage s: x [R, D] fp32 | dy [R, D] bf16 ; then per stage [6, R] floats (two half-row sums of g and g*xhat, mean,
+  // rstd) ; then 2 mbarriers
   const size_t stage_bytes = (size_t)R * D * 6;
   float* s_stat_all = reinterpret_cast<float*>(ln_smem + 2 * stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + 2 * stage_bytes + (size_t)R * 32);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + 2 * stage_bytes + (size_t)R * 48);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int halves = blockDim.x / nvp;
@@ -271,7 +272,7 @@ ln_bwd_staged_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, c
     const int stg = sub & 1;
     const float* sx = reinterpret_cast<const float*>(ln_smem + (size_t)stg * stage_bytes);
     const bf16* sdy = reinterpret_cast<const bf16*>(ln_smem + (size_t)stg * stage_bytes + (size_t)R * D * 4);
-    float* s_m1 = s_stat_all + stg * 4 * R, *s_m2 = s_m1 + R, *s_mean = s_m1 + 2 * R, *s_rstd = s_m1 + 3 * R;
+    float* s_h1 = s_stat_all + stg * 6 * R, *s_h2 = s_h1 + 2 * R, *s_mean = s_h1 + 4 * R, *s_rstd = s_h1 + 5 * R;
     if (threadIdx.x < nrows) {   // row statistics of the forward pass ride along
       s_mean[threadIdx.x] = mean_in[r0 + threadIdx.x];
       s_rstd[threadIdx.x] = rstd_in[r0 + threadIdx.x];
@@ -279,36 +280,46 @@ ln_bwd_staged_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, c
     mbar_wait(&bars[stg], (uint32_t)(sub >> 1) & 1u);
     __syncthreads();
 
-    // ---- row statistics: mean(g), mean(g * xhat), one warp per row ----
-    for (int r = warp; r < nrows; r += nwarps) {
-      const float4* xr = reinterpret_cast<const float4*>(sx + (size_t)r * D);
-      const uint2* dyr = reinterpret_cast<const uint2*>(sdy + (size_t)r * D);
-      const float mean = s_mean[r], rstd = s_rstd[r];
-      float s1 = 0.f, s2 = 0.f;
-      for (int idx = lane; idx < nv; idx += 32) {
-        const float4 xv = xr[idx];
-        const uint2 du = dyr[idx];
-        const float2 d0 = unpack_bf16(du.x), d1 = unpack_bf16(du.y);
-        float4 Aw = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (Ap) {
-          const float4 a = __ldg(Ap + idx);
-          Aw = make_float4(a.x + add1, a.y + add1, a.z + add1, a.w + add1);
+    // ---- row statistics: sum(g), sum(g * xhat) with g = dy * A; two warps per row (each half of the columns), so that
+    //      16 of the 18 warps work; the two halves meet in shared memory in fixed order ----
+    {
+      const int nv_half = (nv + 1) >> 1;
+      for (int job = warp; job < 2 * nrows; job += nwarps) {
+        const int r = job >> 1, hf = job & 1;
+        const float4* xr = reinterpret_cast<const float4*>(sx + (size_t)r * D);
+        const uint2* dyr = reinterpret_cast<const uint2*>(sdy + (size_t)r * D);
+        const float rstd = s_rstd[r], nmr = -s_mean[r] * rstd;   // xhat = fma(x, rstd, -mean * rstd)
+        float s1 = 0.f, s2 = 0.f;
+        const int i_end = min(nv, (hf + 1) * nv_half);
+        for (int idx = hf * nv_half + lane; idx < i_end; idx += 32) {
+          const float4 xv = xr[idx];
+          const uint2 du = dyr[idx];
+          const float2 d0 = unpack_bf16(du.x), d1 = unpack_bf16(du.y);
+          float4 Aw = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (Ap) {
+            const float4 a = __ldg(Ap + idx);
+            Aw = make_float4(a.x + add1, a.y + add1, a.z + add1, a.w + add1);
+          }
+          const float g0 = d0.x * Aw.x, g1 = d0.y * Aw.y, g2 = d1.x * Aw.z, g3 = d1.y * Aw.w;
+          s1 += (g0 + g1) + (g2 + g3);
+          s2 = fmaf(g0, fmaf(xv.x, rstd, nmr), s2);
+          s2 = fmaf(g1, fmaf(xv.y, rstd, nmr), s2);
+          s2 = fmaf(g2, fmaf(xv.z, rstd, nmr), s2);
+          s2 = fmaf(g3, fmaf(xv.w, rstd, nmr), s2);
         }
-        const float g0 = d0.x * Aw.x, g1 = d0.y * Aw.y, g2 = d1.x * Aw.z, g3 = d1.y * Aw.w;
-        s1 += (g0 + g1) + (g2 + g3);
-        s2 += (g0 * ((xv.x - mean) * rstd) + g1 * ((xv.y - mean) * rstd)) +
-              (g2 * ((xv.z - mean) * rstd) + g3 * ((xv.w - mean) * rstd));
-      }
-      s1 = warp_sum(s1);
-      s2 = warp_sum(s2);
-      if (lane == 0) {
-        s_m1[r] = s1 * inv_d;
-        s_m2[r] = s2 * inv_d;
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+          s_h1[hf * R + r] = s1;
+          s_h2[hf * R + r] = s2;
+        }
       }
     }
     __syncthreads();
 
-    // ---- column owners: dx and the column sums, 4 rows per step (dx_io loads issued before the math) ----
+    // ---- column owners: dx and the column sums, 4 rows per step (dx_io loads issued before the math).
+    //      dx = rstd * (A dy - m1 - xhat m2) is evaluated as P dy + Q x + Rr with the per-row constants
+    //      Q = -rstd^2 m2, Rr = -rstd m1 - Q mean and P = rstd A (per row and column): 2 FMA + 1 MUL per element ----
     if (owner) {
       for (int rb = half; rb < nrows; rb += 4 * halves) {
         float4 prev[4];
@@ -330,17 +341,21 @@ ln_bwd_staged_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, c
             const float4 xv = *(reinterpret_cast<const float4*>(sx + (size_t)r * D) + cg);
             const uint2 du = *(reinterpret_cast<const uint2*>(sdy + (size_t)r * D) + cg);
             const float2 d0 = unpack_bf16(du.x), d1 = unpack_bf16(du.y);
-            const float mean = s_mean[r], rstd = s_rstd[r], m1 = s_m1[r], m2 = s_m2[r];
-            const float h0 = (xv.x - mean) * rstd, h1 = (xv.y - mean) * rstd, h2 = (xv.z - mean) * rstd,
-                        h3 = (xv.w - mean) * rstd;
+            const float mean = s_mean[r], rstd = s_rstd[r];
+            const float m1 = (s_h1[r] + s_h1[R + r]) * inv_d, m2 = (s_h2[r] + s_h2[R + r]) * inv_d;
+            const float nmr = -mean * rstd;
+            const float Q = -rstd * rstd * m2, Rr = -rstd * m1 - Q * mean;
             float4 out;
-            out.x = rstd * (d0.x * A.x - m1 - h0 * m2) + prev[j].x;
-            out.y = rstd * (d0.y * A.y - m1 - h1 * m2) + prev[j].y;
-            out.z = rstd * (d1.x * A.z - m1 - h2 * m2) + prev[j].z;
-            out.w = rstd * (d1.y * A.w - m1 - h3 * m2) + prev[j].w;
+            out.x = fmaf(rstd * A.x, d0.x, fmaf(Q, xv.x, Rr + prev[j].x));
+            out.y = fmaf(rstd * A.y, d0.y, fmaf(Q, xv.y, Rr + prev[j].y));
+            out.z = fmaf(rstd * A.z, d1.x, fmaf(Q, xv.z, Rr + prev[j].z));
+            out.w = fmaf(rstd * A.w, d1.y, fmaf(Q, xv.w, Rr + prev[j].w));
             *(reinterpret_cast<float4*>(dx_io + (long long)(r0 + r) * D) + cg) = out;
             accB.x += d0.x; accB.y += d0.y; accB.z += d1.x; accB.w += d1.y;
-            accA.x += d0.x * h0; accA.y += d0.y * h1; accA.z += d1.x * h2; accA.w += d1.y * h3;
+            accA.x = fmaf(d0.x, fmaf(xv.x, rstd, nmr), accA.x);
+            accA.y = fmaf(d0.y, fmaf(xv.y, rstd, nmr), accA.y);
+            accA.z = fmaf(d1.x, fmaf(xv.z, rstd, nmr), accA.z);
+            accA.w = fmaf(d1.y, fmaf(xv.w, rstd, nmr), accA.w);
             if (FUSE) {
               uint2 ov;
               ov.x = pack_bf16(out.x * gt.x, out.y * gt.y);
@@ -348,7 +363,8 @@ ln_bwd_staged_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, c
               *(reinterpret_cast<uint2*>(gf.dy + (long long)(r0 + r) * D) + cg) = ov;
               const float2 y0 = unpack_bf16(yv[j].x), y1 = unpack_bf16(yv[j].y);
               accS.x += out.x; accS.y += out.y; accS.z += out.z; accS.w += out.w;
-              accG.x += out.x * y0.x; accG.y += out.y * y0.y; accG.z += out.z * y1.x; accG.w += out.w * y1.y;
+              accG.x = fmaf(out.x, y0.x, accG.x); accG.y = fmaf(out.y, y0.y, accG.y);
+              accG.z = fmaf(out.z, y1.x, accG.z); accG.w = fmaf(out.w, y1.y, accG.w);
             }
           }
         }
@@ -679,13 +695,13 @@ int launch_ln_bwd(const void* dy, const float* x, const float* mean, const float
   if (D % 8 == 0 && R >= 4 && nvp <= max_threads && aligned) {
     int halves = 1;
     while (halves * 2 * nvp <= max_threads && halves * 2 * 4 <= R) halves *= 2;
-    const size_t smem = 2 * (size_t)R * D * 6 + (size_t)R * 32 + 16;
+    const size_t smem = 2 * (size_t)R * D * 6 + (size_t)R * 48 + 16;
     static bool configured = false;
     if (!configured) {
       VAW_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_staged_kernel<576, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kStagedBudget + 32 * 32 + 16));
+                                        kStagedBudget + 32 * 48 + 16));
       VAW_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_staged_kernel<320, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kStagedBudget + 32 * 32 + 16));
+                                        kStagedBudget + 32 * 48 + 16));
       configured = true;
     }
     if (fuse)
