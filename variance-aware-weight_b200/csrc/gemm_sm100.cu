@@ -469,7 +469,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     for (int work = unit; work < num_work; work += num_units) {
       const Work wk = decode_work<TM, BN>(work, p, n_tiles, num_kb_total);
       const int row0 = wk.m0 + (int)rank * 128 + q * 32 + sub_r;  // first global row of this lane (then +4 per i)
-      mbar_wait(&tfull[acc], acc_phase);
+      mbar_wait_sleep(&tfull[acc], acc_phase, 128);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       const bool interior = wk.m0 + TM <= p.M && wk.n0 + BN <= p.N;   // no bounds checks inside the tile

@@ -38,6 +38,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, for waits that can tolerate ~100 ns of extra latency (epilogue warps waiting for an accumulator, the TMA
+// producer waiting for a free stage): the waiting warp sleeps between polls instead of competing for issue slots with
+// the single-thread MMA / TMA roles - and it stops burning power on a power-capped part.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (globaltimer_ns() - t0 > 4000000000ull) __trap();
+  }
+}
+
 // 1-D bulk copy global -> shared (TMA engine, no tensor map); bytes % 16 == 0, both addresses 16-byte aligned.
 // Completion is credited (complete_tx) to the mbarrier.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
