@@ -243,7 +243,9 @@ __device__ __forceinline__ void epilogue_vec4(const EpiParams& p, int row, int c
     if constexpr (EPI == EPI_DGELU_TANH || EPI == EPI_DGELU_ERF || EPI == EPI_DSILU) {
       const float2 h0 = unpack_bf16(pre.a.x), h1 = unpack_bf16(pre.a.y);
       if constexpr (EPI == EPI_DGELU_TANH) {
-        v.x *= gelu_tanh_grad_f(h0.x); v.y *= gelu_tanh_grad_f(h0.y); v.z *= gelu_tanh_grad_f(h1.x); v.w *= gelu_tanh_grad_f(h1.y);
+        const float2 g0 = gelu_tanh_grad_f2(h0), g1 = gelu_tanh_grad_f2(h1);
+        const float2 r0 = __fmul2_rn(make_float2(v.x, v.y), g0), r1 = __fmul2_rn(make_float2(v.z, v.w), g1);
+        v = make_float4(r0.x, r0.y, r1.x, r1.y);
       } else if constexpr (EPI == EPI_DGELU_ERF) {
         v.x *= gelu_erf_grad_f(h0.x); v.y *= gelu_erf_grad_f(h0.y); v.z *= gelu_erf_grad_f(h1.x); v.w *= gelu_erf_grad_f(h1.y);
       } else {
@@ -260,7 +262,8 @@ __device__ __forceinline__ void epilogue_vec4(const EpiParams& p, int row, int c
       const float2 h0 = unpack_bf16(pk.x), h1 = unpack_bf16(pk.y);
       uint2 ak;
       if constexpr (EPI == EPI_GELU_TANH) {
-        ak.x = pack_bf16(gelu_tanh_f(h0.x), gelu_tanh_f(h0.y)); ak.y = pack_bf16(gelu_tanh_f(h1.x), gelu_tanh_f(h1.y));
+        const float2 a0 = gelu_tanh_f2(h0), a1 = gelu_tanh_f2(h1);
+        ak.x = pack_bf16(a0.x, a0.y); ak.y = pack_bf16(a1.x, a1.y);
       } else if constexpr (EPI == EPI_GELU_ERF) {
         ak.x = pack_bf16(gelu_erf_f(h0.x), gelu_erf_f(h0.y)); ak.y = pack_bf16(gelu_erf_f(h1.x), gelu_erf_f(h1.y));
       } else {
@@ -272,8 +275,9 @@ __device__ __forceinline__ void epilogue_vec4(const EpiParams& p, int row, int c
       const float2 y0 = unpack_bf16(pk.x), y1 = unpack_bf16(pk.y);
       const float4 g = pre.g;
       const float4 r = pre.r;
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out2) + o) =
-          make_float4(fmaf(g.x, y0.x, r.x), fmaf(g.y, y0.y, r.y), fmaf(g.z, y1.x, r.z), fmaf(g.w, y1.y, r.w));
+      const float2 o0 = __ffma2_rn(make_float2(g.x, g.y), y0, make_float2(r.x, r.y));
+      const float2 o1 = __ffma2_rn(make_float2(g.z, g.w), y1, make_float2(r.z, r.w));
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out2) + o) = make_float4(o0.x, o0.y, o1.x, o1.y);
     }
   }
 }
@@ -507,7 +511,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const int r = 4 * i + sub_r;
           float4 a4 = stg[r * 8 + (sub_c ^ (r & 7))];
           if (!wk.partial) {
-            a4.x += bias4.x; a4.y += bias4.y; a4.z += bias4.z; a4.w += bias4.w;
+            {
+              const float2 lo = __fadd2_rn(make_float2(a4.x, a4.y), make_float2(bias4.x, bias4.y));
+              const float2 hi = __fadd2_rn(make_float2(a4.z, a4.w), make_float2(bias4.z, bias4.w));
+              a4 = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
             epilogue_vec4<EPI>(p, row0 + 4 * i, col, a4, interior, pre[i]);
           } else {
             const int lrow = q * 32 + r, lcol = c * 32 + sub_c * 4;

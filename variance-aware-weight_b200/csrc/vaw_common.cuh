@@ -127,6 +127,27 @@ __device__ __forceinline__ float gelu_tanh_grad_f(float x) {
   const float du = k0 * fmaf(3.f * k1, x2, 1.f);
   return 0.5f * (1.f + th) + 0.5f * x * (1.f - th * th) * du;
 }
+// Two elements per instruction (Blackwell FFMA2 / FMUL2): same formulas, half the issue slots.  Used by the GEMM
+// epilogues, where the per-element math - not the main loop - bounded the short-K GEMMs.
+__device__ __forceinline__ float2 gelu_tanh_f2(float2 x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 u = __fmul2_rn(x, __ffma2_rn(x2, make_float2(k0 * k1, k0 * k1), make_float2(k0, k0)));
+  const float2 t = make_float2(tanh_fast(u.x), tanh_fast(u.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, t, hx);
+}
+__device__ __forceinline__ float2 gelu_tanh_grad_f2(float2 x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 u = __fmul2_rn(x, __ffma2_rn(x2, make_float2(k0 * k1, k0 * k1), make_float2(k0, k0)));
+  const float2 t = make_float2(tanh_fast(u.x), tanh_fast(u.y));
+  const float2 omt2 = __ffma2_rn(make_float2(-t.x, -t.y), t, make_float2(1.f, 1.f));
+  const float2 du = __ffma2_rn(x2, make_float2(3.f * k0 * k1, 3.f * k0 * k1), make_float2(k0, k0));
+  const float2 a = __fmul2_rn(__fmul2_rn(x, make_float2(0.5f, 0.5f)), omt2);
+  const float2 b = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+  return __ffma2_rn(a, du, b);
+}
 // exact-GELU via erf(z) ~ 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p|z|)  (Abramowitz-Stegun 7.1.26, |err| < 1.5e-7)
 __device__ __forceinline__ float erf_fast(float z) {
   const float az = fabsf(z);
