@@ -580,6 +580,18 @@ splitk_fixup_kernel(const float* __restrict__ ws, int first_tile, int splits, in
   }
 }
 
+// SMs the persistent GEMM grids may occupy.  Experiment knob (env VAW_GEMM_SMS): with a collective running next to the
+// backward pass, NCCL's CTAs hold some SMs and a statically scheduled 148-CTA grid then runs in two waves.
+int gemm_sms() {
+  static int n = 0;
+  if (n == 0) {
+    n = vaw_num_sms();
+    const char* e = getenv("VAW_GEMM_SMS");
+    if (e && atoi(e) >= 2 && atoi(e) < n) n = atoi(e) & ~1;
+  }
+  return n;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side: tensor maps + dispatch
 // ---------------------------------------------------------------------------------------------------
@@ -631,7 +643,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams&
     VAW_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
-  const int sms = vaw_num_sms();
+  const int sms = gemm_sms();
   if constexpr (!PAIR) {
     const int grid = p.num_work < sms ? p.num_work : sms;
     kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
@@ -720,7 +732,7 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
   bool pair = a->cta_group == 2;
   int bn = a->tile_n;
   if (bn == 0 && a->cta_group == 0) {
-    const int sms = vaw_num_sms();
+    const int sms = gemm_sms();
     const int nkb = (a->K + BK - 1) / BK;
     const bool tail_ok = (a->k_splits == -1);
     double best = 1e30;
@@ -791,7 +803,7 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
   const int num_kb = (a->K + BK - 1) / BK;
   const int m_tiles = (a->M + tile_m - 1) / tile_m, n_tiles = (a->N + bn - 1) / bn;
   const int tiles = m_tiles * n_tiles;
-  const int G = pair ? vaw_num_sms() / 2 : vaw_num_sms();
+  const int G = pair ? gemm_sms() / 2 : gemm_sms();
   int full = tiles, splits = 1, kb_per = num_kb;
   if (a->k_splits != 0 && a->k_splits != 1) {
     VAW_CHECK_ARG(epi == EPI_F32 && a->split_ws, "vaw_gemm_bf16: split-K needs the F32 epilogue and split_ws");

@@ -13,6 +13,7 @@ world_size=2 CPU tests exercise it); the kernels it feeds are CUDA-only.
 """
 from __future__ import annotations
 
+import os
 from contextlib import contextmanager
 
 import torch
@@ -92,6 +93,8 @@ class FlatGradSync:
 
     def launch(self, events=None):
         if not self.enabled or self.world == 1:
+            return
+        if os.environ.get("VAW_DP_NOSYNC") == "1":   # measurement knob: data-parallel step without the gradient all-reduce
             return
         if self.stream is None:
             for ranges in self.buckets:
