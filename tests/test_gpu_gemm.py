@@ -5,6 +5,7 @@ import torch
 import torch.nn.functional as F
 
 from gpu_util import relerr, run_gemm
+from gpu_util import run_gemm as _rg
 from vaw_b200 import _lib as L
 
 pytestmark = pytest.mark.gpu
@@ -126,3 +127,22 @@ def test_rejects_bad_arguments():
         run_gemm(A, A, 0, 0, 128, 100, 64, L.EPI_F32, out=torch.zeros(128, 100, device=DEV))  # N % 8
     with pytest.raises(L.VawError):
         run_gemm(A, A, 0, 0, 128, 128, 64, L.EPI_GATE_RES, out=A)  # missing out2/resid/gate
+
+
+@pytest.mark.parametrize("tile_n,cta_group", [(128, 1), (192, 1), (256, 1), (128, 2), (192, 2), (256, 2)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 200, 136), (512, 1152, 384)])
+def test_tma_store_epilogues_every_tile_config(tile_n, cta_group, M, N, K):
+    """The bf16 epilogues leave through swizzled shared-memory boxes + TMA stores; the staging area's alignment (and with
+    it the swizzle phase) depends on the tile configuration, so every configuration is checked, ragged shapes included."""
+    torch.manual_seed(M + N)
+    A = torch.randn(M, K, device=DEV).bfloat16(); B = (torch.randn(N, K, device=DEV) * 0.1).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    acc = A.float() @ B.float().t() + bias
+    pre = acc.bfloat16().float()
+    o = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16); o2 = torch.full_like(o, float("nan"))
+    _rg(A, B, 0, 0, M, N, K, L.EPI_BF16, out=o, bias=bias, tile_n=tile_n, cta_group=cta_group)
+    assert relerr(o, acc) < 3e-3
+    for epi, fn in ((L.EPI_GELU_TANH, lambda x: F.gelu(x, approximate="tanh")), (L.EPI_GELU_ERF, F.gelu), (L.EPI_SILU, F.silu)):
+        o.fill_(float("nan")); o2.fill_(float("nan"))
+        _rg(A, B, 0, 0, M, N, K, epi, out=o, out2=o2, bias=bias, tile_n=tile_n, cta_group=cta_group)
+        assert relerr(o, acc) < 3e-3 and relerr(o2, fn(pre)) < 4e-3, epi

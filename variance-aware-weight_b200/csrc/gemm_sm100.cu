@@ -332,10 +332,30 @@ __device__ __forceinline__ Work decode_work(int w, const EpiParams& p, int n_til
   return k;
 }
 
+// Tensor maps of the bf16 outputs for the TMA-store epilogue ([32 rows x 32 columns] boxes, SWIZZLE_64B).
+struct OutMaps {
+  CUtensorMap c, c2;
+};
+// Epilogues whose only per-element input is the accumulator (plus a per-column bias) and whose outputs are bf16 take the
+// TMA-store path: the math runs in the TMEM row layout (thread = row, 32 consecutive columns), the bf16 results go
+// into a swizzled shared-memory box and leave through the bulk-store engine - no fp32 transpose, no per-thread global
+// stores or address arithmetic.  (Sustained runs are power-capped, so the epilogue's instruction and data-movement
+// energy, not its latency, is what it costs: scripts/dev_gemm_power.py.)
+template <int EPI>
+struct TmaEpi {
+  static constexpr bool value = (EPI == EPI_BF16 || EPI == EPI_GELU_TANH || EPI == EPI_GELU_ERF || EPI == EPI_SILU);
+  static constexpr bool two = (EPI != EPI_BF16);
+};
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 template <int BN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const EpiParams p) {
+                         const __grid_constant__ OutMaps om, const EpiParams p) {
   using C = Cfg<BN, PAIR>;
   constexpr int STAGES = C::kStages;
   constexpr int TM = C::kTileM;
@@ -419,14 +439,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       // ===================== MMA issuer (leader CTA only) =====================
+      // The whole warp walks the loop so that barriers, descriptors and TMEM addresses stay warp-uniform (uniform
+      // datapath); only lane 0 issues.  With everything under `if (lane == 0)` every MMA dragged ~20 vector instructions
+      // of descriptor arithmetic along.
       // instruction descriptor: D=f32, A=B=bf16, majorness bits, N>>3, M>>4
+      const bool leader = lane == 0;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
                              ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(TM >> 4) << 24);
-      const uint32_t a_kstep = p.a_mn ? 2048u : 32u;  // bytes per UMMA_K=16 step
-      const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
+      const uint32_t a_kstep = (p.a_mn ? 2048u : 32u) >> 4;  // descriptor units (16 B) per UMMA_K=16 step
+      const uint32_t b_kstep = (p.b_mn ? 2048u : 32u) >> 4;
+      const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -438,22 +463,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int num_kb = wk.kb1 - wk.kb0;
         mbar_wait(&tempty[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tm_u + (uint32_t)(acc * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + stage * kABytes);
-          const uint32_t b_base = smem_u32(sB + stage * C::kBBytes);
+          const uint64_t ad0 = umma_desc(smem_u32(sA + stage * kABytes), p.a_mn);
+          const uint64_t bd0 = umma_desc(smem_u32(sB + stage * C::kBBytes), p.b_mn);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = umma_desc(a_base + k * a_kstep, p.a_mn);
-            const uint64_t bd = umma_desc(b_base + k * b_kstep, p.b_mn);
-            if (!skip_mma) tc_mma_f16<PAIR>(d_tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              if (!skip_mma) tc_mma_f16<PAIR>(d_tmem, ad0 + k * a_kstep, bd0 + k * b_kstep, idesc, (kb | k) ? 1u : 0u);
+            tc_commit<PAIR>(&empty[stage]);  // frees the smem slot (in both CTAs) once these MMAs have read it
           }
-          tc_commit<PAIR>(&empty[stage]);  // frees the smem slot (in both CTAs) once these MMAs have read it
+          __syncwarp();
           if (++stage == ring) { stage = 0; phase ^= 1u; }
         }
-        tc_commit<PAIR>(&tfull[acc]);  // accumulator complete -> epilogue warps (of both CTAs)
+        if (leader) tc_commit<PAIR>(&tfull[acc]);  // accumulator complete -> epilogue warps (of both CTAs)
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -478,6 +504,75 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       const bool interior = wk.m0 + TM <= p.M && wk.n0 + BN <= p.N;   // no bounds checks inside the tile
+      if constexpr (TmaEpi<EPI>::value) {
+        // ---- TMA-store epilogue: thread = accumulator row, one 32-column chunk at a time ----
+        uint8_t* stg_b = reinterpret_cast<uint8_t*>(stg);          // 2 slots of [32 rows x 64 B], SWIZZLE_64B
+        const int grow = wk.m0 + (int)rank * 128 + q * 32;            // first global row of this warp's 32 rows
+        // SWIZZLE_64B is a function of the absolute shared-memory address (bits 4-5 ^= bits 7-8); the staging area is
+        // only 256-byte aligned, so the row's swizzle term comes from its address, not from its index.  Both slots are
+        // 2048 B apart, i.e. share the term.
+        const int sw = (int)(((smem_u32(stg_b) + (uint32_t)lane * 64u) >> 7) & 3u);   // 16-byte chunk c lives at c ^ sw
+        int slot = 0;
+#pragma unroll 1
+        for (int c = part; c < NCH; c += kEpiParts) {
+          // the slot(s) written below must have been read by the store engine (at most one older group may be in flight
+          // for the single-output epilogue, none for the two-output ones)
+          if (lane == 0) {
+            if (TmaEpi<EPI>::two) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          }
+          __syncwarp();   // reconverge before the warp-collective TMEM load
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+          const int col0 = wk.n0 + c * 32;
+          uint32_t pk[16], ak[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias && col0 + 4 * j < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);  // warp-uniform
+            const float2 lo = __fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                                         make_float2(b.x, b.y));
+            const float2 hi = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])),
+                                         make_float2(b.z, b.w));
+            pk[2 * j] = pack_bf16(lo.x, lo.y);
+            pk[2 * j + 1] = pack_bf16(hi.x, hi.y);
+            if constexpr (TmaEpi<EPI>::two) {
+              // activation of the bf16-rounded pre-activation (what the next Linear sees in the reference)
+              const float2 h0 = unpack_bf16(pk[2 * j]), h1 = unpack_bf16(pk[2 * j + 1]);
+              if constexpr (EPI == EPI_GELU_TANH) {
+                const float2 a0 = gelu_tanh_f2(h0), a1 = gelu_tanh_f2(h1);
+                ak[2 * j] = pack_bf16(a0.x, a0.y);
+                ak[2 * j + 1] = pack_bf16(a1.x, a1.y);
+              } else if constexpr (EPI == EPI_GELU_ERF) {
+                ak[2 * j] = pack_bf16(gelu_erf_f(h0.x), gelu_erf_f(h0.y));
+                ak[2 * j + 1] = pack_bf16(gelu_erf_f(h1.x), gelu_erf_f(h1.y));
+              } else {
+                ak[2 * j] = pack_bf16(silu_f(h0.x), silu_f(h0.y));
+                ak[2 * j + 1] = pack_bf16(silu_f(h1.x), silu_f(h1.y));
+              }
+            }
+          }
+          uint8_t* s0 = stg_b + (TmaEpi<EPI>::two ? 0 : slot * 2048) + lane * 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(s0 + ((k ^ sw) * 16)) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          if constexpr (TmaEpi<EPI>::two) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<uint4*>(s0 + 2048 + ((k ^ sw) * 16)) =
+                  make_uint4(ak[4 * k], ak[4 * k + 1], ak[4 * k + 2], ak[4 * k + 3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&om.c, stg_b + (TmaEpi<EPI>::two ? 0 : slot * 2048), col0, grow);
+            if (TmaEpi<EPI>::two) tma_store_2d(&om.c2, stg_b + 2048, col0, grow);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          slot ^= 1;
+        }
+      } else {
       long long gate_off[8];
       if constexpr (EPI == EPI_GATE_RES) {
 #pragma unroll
@@ -538,6 +633,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         __syncwarp();
       }
+      }  // generic (transposing) epilogue
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -546,6 +642,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+    }
+    if constexpr (TmaEpi<EPI>::value) {   // shared memory must outlive the store engine's reads
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
   }
 
@@ -648,8 +747,31 @@ int make_tmap(CUtensorMap* map, const void* base, long long rows, long long cols
   return VAW_OK;
 }
 
+// bf16 output [rows, cols] with leading dimension ld: boxes of 32 columns (64 B, SWIZZLE_64B) x 32 rows
+int make_out_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) {
+    vaw_set_error("cuTensorMapEncodeTiled entry point not available");
+    return VAW_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    vaw_set_error("cuTensorMapEncodeTiled (output) failed (%d) rows=%lld cols=%lld ld=%lld base=%p", (int)r, rows, cols,
+                  ld, base);
+    return VAW_ERR_CUDA;
+  }
+  return VAW_OK;
+}
+
 template <int BN, int EPI, bool PAIR>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& p, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& om, const EpiParams& p,
+                cudaStream_t stream) {
   using C = Cfg<BN, PAIR>;
   static bool configured = false;
   auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, PAIR>;
@@ -660,7 +782,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams&
   const int sms = gemm_sms();
   if constexpr (!PAIR) {
     const int grid = p.num_work < sms ? p.num_work : sms;
-    kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
+    kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, om, p);
   } else {
     const int pairs = p.num_work < sms / 2 ? p.num_work : sms / 2;
     cudaLaunchConfig_t cfg = {};
@@ -675,43 +797,44 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams&
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VAW_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+    VAW_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, om, p));
   }
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }
 
 template <int BN, bool PAIR>
-int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& p, cudaStream_t s) {
+int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& om, const EpiParams& p,
+                 cudaStream_t s) {
   switch (epi) {
-    case EPI_BF16: return launch_gemm<BN, EPI_BF16, PAIR>(tmA, tmB, p, s);
-    case EPI_F32: return launch_gemm<BN, EPI_F32, PAIR>(tmA, tmB, p, s);
-    case EPI_GELU_TANH: return launch_gemm<BN, EPI_GELU_TANH, PAIR>(tmA, tmB, p, s);
-    case EPI_GELU_ERF: return launch_gemm<BN, EPI_GELU_ERF, PAIR>(tmA, tmB, p, s);
-    case EPI_GATE_RES: return launch_gemm<BN, EPI_GATE_RES, PAIR>(tmA, tmB, p, s);
-    case EPI_RES: return launch_gemm<BN, EPI_RES, PAIR>(tmA, tmB, p, s);
-    case EPI_DGELU_TANH: return launch_gemm<BN, EPI_DGELU_TANH, PAIR>(tmA, tmB, p, s);
-    case EPI_DGELU_ERF: return launch_gemm<BN, EPI_DGELU_ERF, PAIR>(tmA, tmB, p, s);
-    case EPI_SILU: return launch_gemm<BN, EPI_SILU, PAIR>(tmA, tmB, p, s);
-    case EPI_DSILU: return launch_gemm<BN, EPI_DSILU, PAIR>(tmA, tmB, p, s);
+    case EPI_BF16: return launch_gemm<BN, EPI_BF16, PAIR>(tmA, tmB, om, p, s);
+    case EPI_F32: return launch_gemm<BN, EPI_F32, PAIR>(tmA, tmB, om, p, s);
+    case EPI_GELU_TANH: return launch_gemm<BN, EPI_GELU_TANH, PAIR>(tmA, tmB, om, p, s);
+    case EPI_GELU_ERF: return launch_gemm<BN, EPI_GELU_ERF, PAIR>(tmA, tmB, om, p, s);
+    case EPI_GATE_RES: return launch_gemm<BN, EPI_GATE_RES, PAIR>(tmA, tmB, om, p, s);
+    case EPI_RES: return launch_gemm<BN, EPI_RES, PAIR>(tmA, tmB, om, p, s);
+    case EPI_DGELU_TANH: return launch_gemm<BN, EPI_DGELU_TANH, PAIR>(tmA, tmB, om, p, s);
+    case EPI_DGELU_ERF: return launch_gemm<BN, EPI_DGELU_ERF, PAIR>(tmA, tmB, om, p, s);
+    case EPI_SILU: return launch_gemm<BN, EPI_SILU, PAIR>(tmA, tmB, om, p, s);
+    case EPI_DSILU: return launch_gemm<BN, EPI_DSILU, PAIR>(tmA, tmB, om, p, s);
   }
   vaw_set_error("vaw_gemm_bf16: unknown epilogue %d", epi);
   return VAW_ERR_INVALID;
 }
 
-int dispatch_tile(int bn, bool pair, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& p,
-                  cudaStream_t s) {
+int dispatch_tile(int bn, bool pair, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& om,
+                  const EpiParams& p, cudaStream_t s) {
   if (pair) {
     switch (bn) {
-      case 128: return dispatch_epi<128, true>(epi, tmA, tmB, p, s);
-      case 192: return dispatch_epi<192, true>(epi, tmA, tmB, p, s);
-      default: return dispatch_epi<256, true>(epi, tmA, tmB, p, s);
+      case 128: return dispatch_epi<128, true>(epi, tmA, tmB, om, p, s);
+      case 192: return dispatch_epi<192, true>(epi, tmA, tmB, om, p, s);
+      default: return dispatch_epi<256, true>(epi, tmA, tmB, om, p, s);
     }
   }
   switch (bn) {
-    case 128: return dispatch_epi<128, false>(epi, tmA, tmB, p, s);
-    case 192: return dispatch_epi<192, false>(epi, tmA, tmB, p, s);
-    default: return dispatch_epi<256, false>(epi, tmA, tmB, p, s);
+    case 128: return dispatch_epi<128, false>(epi, tmA, tmB, om, p, s);
+    case 192: return dispatch_epi<192, false>(epi, tmA, tmB, om, p, s);
+    default: return dispatch_epi<256, false>(epi, tmA, tmB, om, p, s);
   }
 }
 
@@ -846,7 +969,21 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
     p.dbg = e ? atoi(e) : 0;
   }
 
-  rc = dispatch_tile(bn, pair, epi, tmA, tmB, p, stream);
+  OutMaps om;
+  om.c = tmA;   // placeholders for the epilogues that do not store through TMA
+  om.c2 = tmA;
+  if (epi == EPI_BF16 || epi == EPI_GELU_TANH || epi == EPI_GELU_ERF || epi == EPI_SILU) {
+    VAW_CHECK_ARG((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "vaw_gemm_bf16: out must be 16-byte aligned");
+    rc = make_out_tmap(&om.c, a->out, a->M, a->N, ldo);
+    if (rc) return rc;
+    if (epi != EPI_BF16) {
+      VAW_CHECK_ARG(a->out2 && (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0,
+                    "vaw_gemm_bf16: this epilogue needs a 16-byte aligned out2");
+      rc = make_out_tmap(&om.c2, a->out2, a->M, a->N, ldo);
+      if (rc) return rc;
+    }
+  }
+  rc = dispatch_tile(bn, pair, epi, tmA, tmB, om, p, stream);
   if (rc || splits == 1) return rc;
   {
     const int rem = tiles - full;
