@@ -146,3 +146,11 @@ def test_tma_store_epilogues_every_tile_config(tile_n, cta_group, M, N, K):
         o.fill_(float("nan")); o2.fill_(float("nan"))
         _rg(A, B, 0, 0, M, N, K, epi, out=o, out2=o2, bias=bias, tile_n=tile_n, cta_group=cta_group)
         assert relerr(o, acc) < 3e-3 and relerr(o2, fn(pre)) < 4e-3, epi
+    # d-activation epilogues: the saved pre-activation tile arrives by TMA as well
+    aux = torch.randn(M, N, device=DEV).bfloat16()
+    for epi, fn in ((L.EPI_DGELU_TANH, lambda x: F.gelu(x, approximate="tanh")), (L.EPI_DGELU_ERF, F.gelu), (L.EPI_DSILU, F.silu)):
+        h = aux.float().requires_grad_(True)
+        fn(h).sum().backward()
+        o.fill_(float("nan"))
+        _rg(A, B, 0, 0, M, N, K, epi, out=o, aux=aux, tile_n=tile_n, cta_group=cta_group)
+        assert relerr(o, (acc - bias) * h.grad) < 4e-3, epi

@@ -343,8 +343,12 @@ struct OutMaps {
 // energy, not its latency, is what it costs: scripts/dev_gemm_power.py.)
 template <int EPI>
 struct TmaEpi {
-  static constexpr bool value = (EPI == EPI_BF16 || EPI == EPI_GELU_TANH || EPI == EPI_GELU_ERF || EPI == EPI_SILU);
-  static constexpr bool two = (EPI != EPI_BF16);
+  // aux: the d-activation epilogues also READ a bf16 tile (the saved pre-activation); it arrives by TMA in the same box
+  // geometry, one chunk ahead of the math (om.c2 is then the map of that input)
+  static constexpr bool aux = (EPI == EPI_DGELU_TANH || EPI == EPI_DGELU_ERF || EPI == EPI_DSILU);
+  static constexpr bool value =
+      (EPI == EPI_BF16 || EPI == EPI_GELU_TANH || EPI == EPI_GELU_ERF || EPI == EPI_SILU) || aux;
+  static constexpr bool two = (EPI == EPI_GELU_TANH || EPI == EPI_GELU_ERF || EPI == EPI_SILU);
 };
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
@@ -369,6 +373,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* abar = bars + 2 * STAGES + 5;   // [kEpiWarps] per-warp barriers of the TMA-loaded aux tiles
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -392,6 +397,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], PAIR ? 2 * kEpiWarps : kEpiWarps);
     }
+    for (int w = 0; w < kEpiWarps; ++w) mbar_init(&abar[w], 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -494,12 +500,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr int NCH = BN / 32;
     float4* stg = reinterpret_cast<float4*>(smem + STAGES * C::kStageBytes + 256) + (warp - 2) * 256;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, aux_phase = 0;
     // after the transpose this lane owns rows {4i + lane/8} (i = 0..7) and column group lane%8 of every chunk
     const int sub_r = lane >> 3, sub_c = lane & 7;
     for (int work = unit; work < num_work; work += num_units) {
       const Work wk = decode_work<TM, BN>(work, p, n_tiles, num_kb_total);
       const int row0 = wk.m0 + (int)rank * 128 + q * 32 + sub_r;  // first global row of this lane (then +4 per i)
+      if constexpr (TmaEpi<EPI>::aux) {
+        // the first aux tile of this work item does not depend on the accumulator: fetch it before waiting for the MMAs
+        // (slot 0 is free: the previous tile's last aux tile was consumed into registers)
+        if (lane == 0 && part < NCH) {
+          mbar_expect_tx(&abar[warp - 2], 2048);
+          tma_load_2d<false>(reinterpret_cast<uint8_t*>(stg), &om.c2, &abar[warp - 2], wk.n0 + part * 32,
+                             wk.m0 + (int)rank * 128 + q * 32);
+        }
+        __syncwarp();
+      }
       mbar_wait_sleep(&tfull[acc], acc_phase, 128);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -513,12 +529,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // 2048 B apart, i.e. share the term.
         const int sw = (int)(((smem_u32(stg_b) + (uint32_t)lane * 64u) >> 7) & 3u);   // 16-byte chunk c lives at c ^ sw
         int slot = 0;
+        // aux variant: slot 0 receives the aux tile (TMA load, per-warp mbarrier), slot 1 stages the output
+        uint64_t* my_bar = &abar[warp - 2];
+        auto aux_load = [&](int c) {   // lane 0
+          mbar_expect_tx(my_bar, 2048);
+          tma_load_2d<false>(stg_b, &om.c2, my_bar, wk.n0 + c * 32, grow);
+        };
 #pragma unroll 1
         for (int c = part; c < NCH; c += kEpiParts) {
+          uint32_t ax[16];
+          if constexpr (TmaEpi<EPI>::aux) {
+            mbar_wait(my_bar, aux_phase);
+            aux_phase ^= 1u;
+            const uint8_t* a0 = stg_b + lane * 64;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint4 t = *reinterpret_cast<const uint4*>(a0 + ((k ^ sw) * 16));
+              ax[4 * k] = t.x; ax[4 * k + 1] = t.y; ax[4 * k + 2] = t.z; ax[4 * k + 3] = t.w;
+            }
+            __syncwarp();   // every lane has its row: the next chunk's tile may overwrite the slot
+            if (lane == 0 && c + kEpiParts < NCH) aux_load(c + kEpiParts);
+          }
           // the slot(s) written below must have been read by the store engine (at most one older group may be in flight
-          // for the single-output epilogue, none for the two-output ones)
+          // for the alternating single-output epilogue, none otherwise)
           if (lane == 0) {
-            if (TmaEpi<EPI>::two) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (TmaEpi<EPI>::two || TmaEpi<EPI>::aux) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           }
           __syncwarp();   // reconverge before the warp-collective TMEM load
@@ -531,10 +566,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int j = 0; j < 8; ++j) {
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias && col0 + 4 * j < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);  // warp-uniform
-            const float2 lo = __fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
-                                         make_float2(b.x, b.y));
-            const float2 hi = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])),
-                                         make_float2(b.z, b.w));
+            float2 lo = __fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                                   make_float2(b.x, b.y));
+            float2 hi = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])),
+                                   make_float2(b.z, b.w));
+            if constexpr (TmaEpi<EPI>::aux) {   // dX = dY * act'(saved pre-activation)
+              const float2 h0 = unpack_bf16(ax[2 * j]), h1 = unpack_bf16(ax[2 * j + 1]);
+              if constexpr (EPI == EPI_DGELU_TANH) {
+                lo = __fmul2_rn(lo, gelu_tanh_grad_f2(h0));
+                hi = __fmul2_rn(hi, gelu_tanh_grad_f2(h1));
+              } else if constexpr (EPI == EPI_DGELU_ERF) {
+                lo = __fmul2_rn(lo, make_float2(gelu_erf_grad_f(h0.x), gelu_erf_grad_f(h0.y)));
+                hi = __fmul2_rn(hi, make_float2(gelu_erf_grad_f(h1.x), gelu_erf_grad_f(h1.y)));
+              } else {
+                lo = __fmul2_rn(lo, make_float2(silu_grad_f(h0.x), silu_grad_f(h0.y)));
+                hi = __fmul2_rn(hi, make_float2(silu_grad_f(h1.x), silu_grad_f(h1.y)));
+              }
+            }
             pk[2 * j] = pack_bf16(lo.x, lo.y);
             pk[2 * j + 1] = pack_bf16(hi.x, hi.y);
             if constexpr (TmaEpi<EPI>::two) {
@@ -553,6 +601,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               }
             }
           }
+          if constexpr (TmaEpi<EPI>::aux) slot = 1;
           uint8_t* s0 = stg_b + (TmaEpi<EPI>::two ? 0 : slot * 2048) + lane * 64;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -972,6 +1021,15 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
   OutMaps om;
   om.c = tmA;   // placeholders for the epilogues that do not store through TMA
   om.c2 = tmA;
+  const bool aux_epi = (epi == EPI_DGELU_TANH || epi == EPI_DGELU_ERF || epi == EPI_DSILU);
+  if (aux_epi) {
+    VAW_CHECK_ARG(a->aux && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0 && a->out &&
+                      (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
+                  "vaw_gemm_bf16: d-activation epilogues need 16-byte aligned out and aux");
+    rc = make_out_tmap(&om.c, a->out, a->M, a->N, ldo);
+    if (!rc) rc = make_out_tmap(&om.c2, a->aux, a->M, a->N, ldo);
+    if (rc) return rc;
+  }
   if (epi == EPI_BF16 || epi == EPI_GELU_TANH || epi == EPI_GELU_ERF || epi == EPI_SILU) {
     VAW_CHECK_ARG((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "vaw_gemm_bf16: out must be 16-byte aligned");
     rc = make_out_tmap(&om.c, a->out, a->M, a->N, ldo);
