@@ -146,6 +146,20 @@ def test_tma_store_epilogues_every_tile_config(tile_n, cta_group, M, N, K):
         o.fill_(float("nan")); o2.fill_(float("nan"))
         _rg(A, B, 0, 0, M, N, K, epi, out=o, out2=o2, bias=bias, tile_n=tile_n, cta_group=cta_group)
         assert relerr(o, acc) < 3e-3 and relerr(o2, fn(pre)) < 4e-3, epi
+    # residual epilogues: resid in / out2 + y out through TMA in 16-column halves (ragged sample boundaries included)
+    rps = {128: 64, 300: 100, 512: 256}[M]
+    resid = torch.randn(M, N, device=DEV); gate = torch.randn(M // rps, N, device=DEV)
+    xo = torch.full((M, N), float("nan"), device=DEV)
+    o.fill_(float("nan"))
+    _rg(A, B, 0, 0, M, N, K, L.EPI_GATE_RES, out=o, out2=xo, bias=bias, resid=resid, gate=gate, rows_per_sample=rps,
+        tile_n=tile_n, cta_group=cta_group)
+    assert relerr(o, acc) < 3e-3 and relerr(xo, resid + gate.repeat_interleave(rps, 0) * pre) < 2e-3
+    xo.fill_(float("nan"))
+    _rg(A, B, 0, 0, M, N, K, L.EPI_RES, out2=xo, bias=bias, resid=resid, tile_n=tile_n, cta_group=cta_group)
+    assert relerr(xo, resid + pre) < 2e-3
+    xo2 = resid.clone()    # in place: out2 aliases resid (the U-ViT residual stream is updated in place)
+    _rg(A, B, 0, 0, M, N, K, L.EPI_RES, out2=xo2, bias=bias, resid=xo2, tile_n=tile_n, cta_group=cta_group)
+    assert relerr(xo2, resid + pre) < 2e-3
     # d-activation epilogues: the saved pre-activation tile arrives by TMA as well
     aux = torch.randn(M, N, device=DEV).bfloat16()
     for epi, fn in ((L.EPI_DGELU_TANH, lambda x: F.gelu(x, approximate="tanh")), (L.EPI_DGELU_ERF, F.gelu), (L.EPI_DSILU, F.silu)):

@@ -65,6 +65,7 @@ struct EpiParams {
   // work decomposition (see decode_work): full tiles, then the remaining tiles split along K
   int num_work, full_tiles, tail_splits, kb_per_split;
   float* split_ws;
+  int tma_res;  // residual epilogues: resid / out2 / out move through TMA (set by the host when the layout allows)
   int dbg;  // debug knobs (env VAW_DBG): 1 = ring of 2 stages, 2 = skip MMA issue, 4 = skip TMA issue,
             // 8 = epilogue drains TMEM only (| 64: plus (dbg >> 8) x 32 FFMAs of pure ALU work per chunk),
             // 32 = bf16 epilogues do all their math but skip the global stores
@@ -334,7 +335,7 @@ __device__ __forceinline__ Work decode_work(int w, const EpiParams& p, int n_til
 
 // Tensor maps of the bf16 outputs for the TMA-store epilogue ([32 rows x 32 columns] boxes, SWIZZLE_64B).
 struct OutMaps {
-  CUtensorMap c, c2;
+  CUtensorMap c, c2, c3;   // bf16 out | bf16 out2 or aux, fp32 out2 of the residual epilogues | fp32 resid
 };
 // Epilogues whose only per-element input is the accumulator (plus a per-column bias) and whose outputs are bf16 take the
 // TMA-store path: the math runs in the TMEM row layout (thread = row, 32 consecutive columns), the bf16 results go
@@ -516,6 +517,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         __syncwarp();
       }
+      constexpr bool kResEpi = (EPI == EPI_GATE_RES || EPI == EPI_RES);
+      if constexpr (kResEpi) {
+        if (p.tma_res && lane == 0 && part < NCH) {   // first 16-column residual tile of this work item
+          mbar_expect_tx(&abar[warp - 2], 2048);
+          tma_load_2d<false>(reinterpret_cast<uint8_t*>(stg), &om.c3, &abar[warp - 2], wk.n0 + part * 32,
+                             wk.m0 + (int)rank * 128 + q * 32);
+        }
+        __syncwarp();
+      }
       mbar_wait_sleep(&tfull[acc], acc_phase, 128);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -621,6 +631,90 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           slot ^= 1;
         }
+      } else if (kResEpi && p.tma_res) {
+        // ---- residual epilogues through TMA: out2 = resid + gate * y (fp32), y = bf16(acc + bias) ----
+        // 16-column halves (64-byte fp32 rows): slot 0 receives the residual tile one half ahead (per-warp mbarrier),
+        // slot 1 stages out2 of each half and finally the bf16 y tile of the whole 32-column chunk.
+        uint8_t* stg_b = reinterpret_cast<uint8_t*>(stg);
+        const int grow = wk.m0 + (int)rank * 128 + q * 32;
+        const int sw = (int)(((smem_u32(stg_b) + (uint32_t)lane * 64u) >> 7) & 3u);
+        uint64_t* my_bar = &abar[warp - 2];
+        const int my_row = min(grow + lane, p.M - 1);
+        const float* gate_row = EPI == EPI_GATE_RES ? p.gate + (long long)(my_row / p.rows_per_sample) * p.ldg : nullptr;
+        auto wait_slot1 = [&]() {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        };
+#pragma unroll 1
+        for (int c = part; c < NCH; c += kEpiParts) {
+          const int col0 = wk.n0 + c * 32;
+          uint32_t v[32], ypk[16];
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            mbar_wait(my_bar, aux_phase);
+            aux_phase ^= 1u;
+            float4 r[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r[k] = *reinterpret_cast<const float4*>(stg_b + lane * 64 + ((k ^ sw) * 16));
+            __syncwarp();   // slot 0 consumed: fetch the next residual tile (other half, or the next chunk's first half)
+            if (lane == 0) {
+              const int nc = hf == 0 ? c : c + kEpiParts;
+              if (nc < NCH) {
+                mbar_expect_tx(my_bar, 2048);
+                tma_load_2d<false>(stg_b, &om.c3, my_bar, wk.n0 + nc * 32 + (hf == 0 ? 16 : 0), grow);
+              }
+            }
+            __syncwarp();
+            if (hf == 0) {
+              tmem_ld32(t_row + (uint32_t)(c * 32), v);
+              tmem_ld_wait();
+            }
+            float4 o4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int col = col0 + hf * 16 + 4 * k;
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f), g = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (col < p.N) {
+                if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                if (EPI == EPI_GATE_RES) g = __ldg(reinterpret_cast<const float4*>(gate_row + col));
+              }
+              const int j = hf * 4 + k;
+              const float2 lo = __fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                                           make_float2(b.x, b.y));
+              const float2 hi = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])),
+                                           make_float2(b.z, b.w));
+              // the linear output is a bf16 tensor in the reference's autocast path: round before the residual add
+              ypk[2 * j] = pack_bf16(lo.x, lo.y);
+              ypk[2 * j + 1] = pack_bf16(hi.x, hi.y);
+              const float2 y0 = unpack_bf16(ypk[2 * j]), y1 = unpack_bf16(ypk[2 * j + 1]);
+              const float2 a0 = __ffma2_rn(make_float2(g.x, g.y), y0, make_float2(r[k].x, r[k].y));
+              const float2 a1 = __ffma2_rn(make_float2(g.z, g.w), y1, make_float2(r[k].z, r[k].w));
+              o4[k] = make_float4(a0.x, a0.y, a1.x, a1.y);
+            }
+            wait_slot1();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(stg_b + 2048 + lane * 64 + ((k ^ sw) * 16)) = o4[k];
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&om.c2, stg_b + 2048, col0 + hf * 16, grow);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          if (p.out) {   // y (bf16) of the whole chunk, needed by the backward pass of the gated branch
+            wait_slot1();
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<uint4*>(stg_b + 2048 + lane * 64 + ((k ^ sw) * 16)) =
+                  make_uint4(ypk[4 * k], ypk[4 * k + 1], ypk[4 * k + 2], ypk[4 * k + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&om.c, stg_b + 2048, col0, grow);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+        }
       } else {
       long long gate_off[8];
       if constexpr (EPI == EPI_GATE_RES) {
@@ -692,7 +786,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if constexpr (TmaEpi<EPI>::value) {   // shared memory must outlive the store engine's reads
+    if constexpr (TmaEpi<EPI>::value || EPI == EPI_GATE_RES || EPI == EPI_RES) {
+      // shared memory must outlive the store engine's reads
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
   }
@@ -797,19 +892,20 @@ int make_tmap(CUtensorMap* map, const void* base, long long rows, long long cols
 }
 
 // bf16 output [rows, cols] with leading dimension ld: boxes of 32 columns (64 B, SWIZZLE_64B) x 32 rows
-int make_out_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld) {
+// (fp32 = true: boxes of 16 fp32 columns - the same 64-byte rows)
+int make_out_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, bool fp32 = false) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) {
     vaw_set_error("cuTensorMapEncodeTiled entry point not available");
     return VAW_ERR_CUDA;
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {32u, 32u};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (fp32 ? 4 : 2)};
+  cuuint32_t box[2] = {fp32 ? 16u : 32u, 32u};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     vaw_set_error("cuTensorMapEncodeTiled (output) failed (%d) rows=%lld cols=%lld ld=%lld base=%p", (int)r, rows, cols,
                   ld, base);
@@ -1021,6 +1117,18 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
   OutMaps om;
   om.c = tmA;   // placeholders for the epilogues that do not store through TMA
   om.c2 = tmA;
+  om.c3 = tmA;
+  p.tma_res = 0;
+  if ((epi == EPI_GATE_RES || epi == EPI_RES) && a->resid_mod == 0 && a->resid && a->out2 &&
+      ((reinterpret_cast<uintptr_t>(a->resid) | reinterpret_cast<uintptr_t>(a->out2) |
+        reinterpret_cast<uintptr_t>(a->out)) & 15) == 0 &&
+      (epi == EPI_RES || a->gate)) {
+    rc = make_out_tmap(&om.c2, a->out2, a->M, a->N, ldo, true);
+    if (!rc) rc = make_out_tmap(&om.c3, a->resid, a->M, a->N, ldo, true);
+    if (!rc && a->out) rc = make_out_tmap(&om.c, a->out, a->M, a->N, ldo);
+    if (rc) return rc;
+    p.tma_res = 1;
+  }
   const bool aux_epi = (epi == EPI_DGELU_TANH || epi == EPI_DGELU_ERF || epi == EPI_DSILU);
   if (aux_epi) {
     VAW_CHECK_ARG(a->aux && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0 && a->out &&
