@@ -289,7 +289,9 @@ ln_bwd_staged_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, c
         const float4* xr = reinterpret_cast<const float4*>(sx + (size_t)r * D);
         const uint2* dyr = reinterpret_cast<const uint2*>(sdy + (size_t)r * D);
         const float rstd = s_rstd[r], nmr = -s_mean[r] * rstd;   // xhat = fma(x, rstd, -mean * rstd)
-        float s1 = 0.f, s2 = 0.f;
+        const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(nmr, nmr);
+        float2 s1v = make_float2(0.f, 0.f), s2v = s1v;
+        float s1, s2;
         const int i_end = min(nv, (hf + 1) * nv_half);
         for (int idx = hf * nv_half + lane; idx < i_end; idx += 32) {
           const float4 xv = xr[idx];
@@ -300,15 +302,14 @@ ln_bwd_staged_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, c
             const float4 a = __ldg(Ap + idx);
             Aw = make_float4(a.x + add1, a.y + add1, a.z + add1, a.w + add1);
           }
-          const float g0 = d0.x * Aw.x, g1 = d0.y * Aw.y, g2 = d1.x * Aw.z, g3 = d1.y * Aw.w;
-          s1 += (g0 + g1) + (g2 + g3);
-          s2 = fmaf(g0, fmaf(xv.x, rstd, nmr), s2);
-          s2 = fmaf(g1, fmaf(xv.y, rstd, nmr), s2);
-          s2 = fmaf(g2, fmaf(xv.z, rstd, nmr), s2);
-          s2 = fmaf(g3, fmaf(xv.w, rstd, nmr), s2);
+          // packed fp32 (FFMA2 / FMUL2 / FADD2): the kernel is issue-bound, two elements per instruction
+          const float2 ga = __fmul2_rn(d0, make_float2(Aw.x, Aw.y)), gb = __fmul2_rn(d1, make_float2(Aw.z, Aw.w));
+          s1v = __fadd2_rn(s1v, __fadd2_rn(ga, gb));
+          s2v = __ffma2_rn(ga, __ffma2_rn(make_float2(xv.x, xv.y), rs2, nm2), s2v);
+          s2v = __ffma2_rn(gb, __ffma2_rn(make_float2(xv.z, xv.w), rs2, nm2), s2v);
         }
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
+        s1 = warp_sum(s1v.x + s1v.y);
+        s2 = warp_sum(s2v.x + s2v.y);
         if (lane == 0) {
           s_h1[hf * R + r] = s1;
           s_h2[hf * R + r] = s2;
@@ -345,26 +346,34 @@ ln_bwd_staged_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, c
             const float m1 = (s_h1[r] + s_h1[R + r]) * inv_d, m2 = (s_h2[r] + s_h2[R + r]) * inv_d;
             const float nmr = -mean * rstd;
             const float Q = -rstd * rstd * m2, Rr = -rstd * m1 - Q * mean;
-            float4 out;
-            out.x = fmaf(rstd * A.x, d0.x, fmaf(Q, xv.x, Rr + prev[j].x));
-            out.y = fmaf(rstd * A.y, d0.y, fmaf(Q, xv.y, Rr + prev[j].y));
-            out.z = fmaf(rstd * A.z, d1.x, fmaf(Q, xv.z, Rr + prev[j].z));
-            out.w = fmaf(rstd * A.w, d1.y, fmaf(Q, xv.w, Rr + prev[j].w));
+            const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(nmr, nmr), Q2 = make_float2(Q, Q),
+                         R2 = make_float2(Rr, Rr);
+            const float2 xa = make_float2(xv.x, xv.y), xb = make_float2(xv.z, xv.w);
+            const float2 oa = __ffma2_rn(__fmul2_rn(rs2, make_float2(A.x, A.y)), d0,
+                                         __ffma2_rn(Q2, xa, __fadd2_rn(R2, make_float2(prev[j].x, prev[j].y))));
+            const float2 ob = __ffma2_rn(__fmul2_rn(rs2, make_float2(A.z, A.w)), d1,
+                                         __ffma2_rn(Q2, xb, __fadd2_rn(R2, make_float2(prev[j].z, prev[j].w))));
+            const float4 out = make_float4(oa.x, oa.y, ob.x, ob.y);
             *(reinterpret_cast<float4*>(dx_io + (long long)(r0 + r) * D) + cg) = out;
-            accB.x += d0.x; accB.y += d0.y; accB.z += d1.x; accB.w += d1.y;
-            accA.x = fmaf(d0.x, fmaf(xv.x, rstd, nmr), accA.x);
-            accA.y = fmaf(d0.y, fmaf(xv.y, rstd, nmr), accA.y);
-            accA.z = fmaf(d1.x, fmaf(xv.z, rstd, nmr), accA.z);
-            accA.w = fmaf(d1.y, fmaf(xv.w, rstd, nmr), accA.w);
+            {
+              const float2 ba = __fadd2_rn(make_float2(accB.x, accB.y), d0), bb = __fadd2_rn(make_float2(accB.z, accB.w), d1);
+              accB = make_float4(ba.x, ba.y, bb.x, bb.y);
+              const float2 aa = __ffma2_rn(d0, __ffma2_rn(xa, rs2, nm2), make_float2(accA.x, accA.y));
+              const float2 ab = __ffma2_rn(d1, __ffma2_rn(xb, rs2, nm2), make_float2(accA.z, accA.w));
+              accA = make_float4(aa.x, aa.y, ab.x, ab.y);
+            }
             if (FUSE) {
+              const float2 ga = __fmul2_rn(oa, make_float2(gt.x, gt.y)), gb = __fmul2_rn(ob, make_float2(gt.z, gt.w));
               uint2 ov;
-              ov.x = pack_bf16(out.x * gt.x, out.y * gt.y);
-              ov.y = pack_bf16(out.z * gt.z, out.w * gt.w);
+              ov.x = pack_bf16(ga.x, ga.y);
+              ov.y = pack_bf16(gb.x, gb.y);
               *(reinterpret_cast<uint2*>(gf.dy + (long long)(r0 + r) * D) + cg) = ov;
               const float2 y0 = unpack_bf16(yv[j].x), y1 = unpack_bf16(yv[j].y);
-              accS.x += out.x; accS.y += out.y; accS.z += out.z; accS.w += out.w;
-              accG.x = fmaf(out.x, y0.x, accG.x); accG.y = fmaf(out.y, y0.y, accG.y);
-              accG.z = fmaf(out.z, y1.x, accG.z); accG.w = fmaf(out.w, y1.y, accG.w);
+              const float2 sa = __fadd2_rn(make_float2(accS.x, accS.y), oa), sb = __fadd2_rn(make_float2(accS.z, accS.w), ob);
+              accS = make_float4(sa.x, sa.y, sb.x, sb.y);
+              const float2 qa = __ffma2_rn(oa, y0, make_float2(accG.x, accG.y));
+              const float2 qb = __ffma2_rn(ob, y1, make_float2(accG.z, accG.w));
+              accG = make_float4(qa.x, qa.y, qb.x, qb.y);
             }
           }
         }
@@ -528,11 +537,27 @@ dit_block_finish_kernel(const float* __restrict__ pA, const float* __restrict__ 
   float t0 = 0.f, t1 = 0.f;
   if (col < D) {
     for (int n = ny; n < B; n += 16) {
+      // loads of four chunks are issued before they are folded (the kernel is latency-bound: 21 MB in 72-element strides);
+      // the sums still run in chunk order
       float q0 = 0.f, q1 = 0.f;
-      for (int c = 0; c < ch; ++c) {
-        const long long o = (((long long)n * ch + c) * 2) * D + col;
-        q0 += part[o];
-        q1 += part[o + D];
+      const float* pn = part + ((long long)n * ch * 2) * D + col;
+      int c = 0;
+      for (; c + 4 <= ch; c += 4) {
+        float a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a[u] = __ldg(pn + (long long)(c + u) * 2 * D);
+          b[u] = __ldg(pn + (long long)(c + u) * 2 * D + D);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          q0 += a[u];
+          q1 += b[u];
+        }
+      }
+      for (; c < ch; ++c) {
+        q0 += __ldg(pn + (long long)c * 2 * D);
+        q1 += __ldg(pn + (long long)c * 2 * D + D);
       }
       const long long mo = (long long)n * ldm + col;
       dmod[mo + (long long)slot1 * D] = q1;
