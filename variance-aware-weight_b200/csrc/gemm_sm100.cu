@@ -357,6 +357,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                : "memory");
 }
 
+// Columns of a tile that exist (the last tile of a row of tiles may be ragged: N = 1152 = 4.5 x 256).  The MMAs of such
+// a tile run with N = tile_cols() instead of BN, and the epilogue skips the missing 32-column chunks: a tenth of the
+// tensor-core work (and energy) of every N = 1152 GEMM was spent on zero padding.  Multiple of 32 so that each CTA of a
+// pair holds a multiple of 16 columns of B.
+__device__ __forceinline__ int tile_cols(int N, int n0, int BN_) {
+  const int left = (N - n0 + 31) & ~31;
+  return left < BN_ ? left : BN_;
+}
+
 template <int BN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -420,7 +429,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int work = unit; work < num_work; work += num_units) {
         const Work wk = decode_work<TM, BN>(work, p, n_tiles, num_kb_total);
         const int am0 = wk.m0 + (int)rank * 128;
-        const int bn0 = wk.n0 + (int)rank * C::kBRows;
+        // a CTA pair splits the tile's columns of B in two; on a ragged tile the split point moves with it
+        const int bn0 = wk.n0 + (PAIR ? (int)rank * (tile_cols(p.N, wk.n0, BN) >> 1) : 0);
         for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
           if (rank == 0) mbar_expect_tx(&full[stage], skip_tma ? 0u : (PAIR ? 2u : 1u) * (kABytes + bbytes));
@@ -471,6 +481,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         mbar_wait(&tempty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tm_u + (uint32_t)(acc * BN);
+        const uint32_t idesc_t = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(tile_cols(p.N, wk.n0, BN) >> 3) << 17);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -479,7 +490,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (leader) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              if (!skip_mma) tc_mma_f16<PAIR>(d_tmem, ad0 + k * a_kstep, bd0 + k * b_kstep, idesc, (kb | k) ? 1u : 0u);
+              if (!skip_mma) tc_mma_f16<PAIR>(d_tmem, ad0 + k * a_kstep, bd0 + k * b_kstep, idesc_t, (kb | k) ? 1u : 0u);
             tc_commit<PAIR>(&empty[stage]);  // frees the smem slot (in both CTAs) once these MMAs have read it
           }
           __syncwarp();
@@ -498,7 +509,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     //  left the issue slots ~70 % idle - the epilogue, not the MMA main loop, bounded the short-K GEMMs.)
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int part = (warp - 2) >> 2;
-    constexpr int NCH = BN / 32;
+    constexpr int NCH_MAX = BN / 32;
     float4* stg = reinterpret_cast<float4*>(smem + STAGES * C::kStageBytes + 256) + (warp - 2) * 256;
     int acc = 0;
     uint32_t acc_phase = 0, aux_phase = 0;
@@ -506,6 +517,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int sub_r = lane >> 3, sub_c = lane & 7;
     for (int work = unit; work < num_work; work += num_units) {
       const Work wk = decode_work<TM, BN>(work, p, n_tiles, num_kb_total);
+      const int NCH = tile_cols(p.N, wk.n0, BN) >> 5;              // 32-column chunks that exist in this tile
       const int row0 = wk.m0 + (int)rank * 128 + q * 32 + sub_r;  // first global row of this lane (then +4 per i)
       if constexpr (TmaEpi<EPI>::aux) {
         // the first aux tile of this work item does not depend on the accumulator: fetch it before waiting for the MMAs
