@@ -175,14 +175,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const uint64_t ak = dK + (uint32_t)(kt * (16384 >> 4)), av = dV + (uint32_t)(kt * (16384 >> 4));
       const uint64_t bq = dQ + (uint32_t)(qs * (8192 >> 4)), bo = dDO + (uint32_t)(qs * (8192 >> 4));
       if (leader) {
+        // consecutive MMAs alternate between the two accumulators.  (Measured: no faster than accumulator-by-accumulator
+        // order - the ~55 ns per small MMA is a per-instruction cost, not accumulate latency.)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_ss(tmem + cS, ak + 2 * k, bq + 2 * k, id_kk, k ? 1u : 0u);
-        if (kTail)
+        for (int k = 0; k < 4; ++k) {
+          tc_mma_ss(tmem + cS, ak + 2 * k, bq + 2 * k, id_kk, k ? 1u : 0u);
+          tc_mma_ss(tmem + cDP, av + 2 * k, bo + 2 * k, id_kk, k ? 1u : 0u);
+        }
+        if (kTail) {
           tc_mma_ss(tmem + cS, dKt + (uint32_t)(kt * (4096 >> 4)), dQt + (uint32_t)(qs * (2048 >> 4)), id_kk, 1u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_ss(tmem + cDP, av + 2 * k, bo + 2 * k, id_kk, k ? 1u : 0u);
-        if (kTail)
           tc_mma_ss(tmem + cDP, dVt + (uint32_t)(kt * (4096 >> 4)), dDOt + (uint32_t)(qs * (2048 >> 4)), id_kk, 1u);
+        }
         tc_commit(sdp_full);
       }
       __syncwarp();
@@ -204,14 +207,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const uint32_t acc0 = qs ? 1u : 0u;
       if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {   // dV[kt] += P^T dO[qs]
+        for (int k = 0; k < 4; ++k) {   // dV[kt] += P^T dO[qs], dK[kt] += dS^T Q[qs]: four accumulators round-robin
           tc_mma_ts(tmem + cDV, tmem + cPt + k * 8, bo + 128 * k, id_m, k ? 1u : acc0);
-          if (kTail) tc_mma_ts(tmem + cDV + 64, tmem + cPt + k * 8, bot + 32 * k, id_t, k ? 1u : acc0);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {   // dK[kt] += dS^T Q[qs]
           tc_mma_ts(tmem + cDK, tmem + cDSt + k * 8, bq + 128 * k, id_m, k ? 1u : acc0);
-          if (kTail) tc_mma_ts(tmem + cDK + 64, tmem + cDSt + k * 8, bqt + 32 * k, id_t, k ? 1u : acc0);
+          if (kTail) {
+            tc_mma_ts(tmem + cDV + 64, tmem + cPt + k * 8, bot + 32 * k, id_t, k ? 1u : acc0);
+            tc_mma_ts(tmem + cDK + 64, tmem + cDSt + k * 8, bqt + 32 * k, id_t, k ? 1u : acc0);
+          }
         }
         tc_commit(p_free);
       }
