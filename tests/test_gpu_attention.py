@@ -81,3 +81,28 @@ def test_unsupported_head_dim_fails_loudly():
     x = torch.zeros(1, 16, 3, 1, 48, device=DEV, dtype=torch.bfloat16)
     with pytest.raises(L.VawError):
         L.call("vaw_attn_fwd", x.data_ptr(), x.data_ptr(), x.data_ptr(), 1, 16, 1, 48, L.stream_ptr())
+
+
+@pytest.mark.parametrize("B,T,H,hd", [(2, 100, 2, 72), (1, 256, 3, 64), (2, 37, 1, 72)])
+def test_attention_outputs_stay_inside_their_buffers(B, T, H, hd):
+    """Guard bands around o, lse and dqkv (TMA stores clip at the tensor bounds; ragged T exercises the clipping)."""
+    torch.manual_seed(3)
+    pad = 4096
+    qkv = (torch.randn(B, T, 3, H, hd, device=DEV) * 0.7).bfloat16()
+
+    def guarded(n, dtype):
+        buf = torch.full((n + 2 * pad,), 7.0, device=DEV, dtype=dtype)
+        return buf, buf[pad:pad + n]
+
+    bo, o = guarded(B * T * H * hd, torch.bfloat16)
+    bl, lse = guarded(B * H * T, torch.float32)
+    L.call("vaw_attn_fwd", qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, H, hd, L.stream_ptr())
+    bd, dqkv = guarded(qkv.numel(), torch.bfloat16)
+    bw, ws = guarded(B * H * T, torch.float32)
+    do = torch.randn(B, T, H, hd, device=DEV).bfloat16()
+    L.call("vaw_attn_bwd_ws", qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), ws.data_ptr(),
+           B, T, H, hd, L.stream_ptr())
+    torch.cuda.synchronize()
+    for buf in (bo, bl, bd, bw):
+        assert bool((buf[:pad] == 7.0).all()) and bool((buf[-pad:] == 7.0).all())
+    assert not torch.isnan(o.float()).any() and not torch.isnan(dqkv.float()).any()

@@ -168,3 +168,46 @@ def test_tma_store_epilogues_every_tile_config(tile_n, cta_group, M, N, K):
         o.fill_(float("nan"))
         _rg(A, B, 0, 0, M, N, K, epi, out=o, aux=aux, tile_n=tile_n, cta_group=cta_group)
         assert relerr(o, (acc - bias) * h.grad) < 4e-3, epi
+
+
+@pytest.mark.parametrize("epi", ["bf16", "gelu", "dgelu", "gate_res", "f32"])
+def test_outputs_stay_inside_their_buffers(epi):
+    """Guard bands around every output: ragged shapes (M, N not multiples of the tile), TMA stores and direct stores
+    must not touch a byte outside [M, N]."""
+    torch.manual_seed(7)
+    M, N, K, rps = 300, 200, 136, 100
+    A = torch.randn(M, K, device=DEV).bfloat16(); B = (torch.randn(N, K, device=DEV) * 0.1).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    pad = 4096
+
+    def guarded(dtype):
+        buf = torch.full((M * N + 2 * pad,), 7.0, device=DEV, dtype=dtype)
+        return buf, buf[pad:pad + M * N].view(M, N)
+
+    def check(buf):
+        assert bool((buf[:pad] == 7.0).all()) and bool((buf[-pad:] == 7.0).all())
+
+    if epi == "bf16":
+        b1, o = guarded(torch.bfloat16)
+        _rg(A, B, 0, 0, M, N, K, L.EPI_BF16, out=o, bias=bias)
+        check(b1)
+    elif epi == "gelu":
+        b1, o = guarded(torch.bfloat16); b2, o2 = guarded(torch.bfloat16)
+        _rg(A, B, 0, 0, M, N, K, L.EPI_GELU_TANH, out=o, out2=o2, bias=bias)
+        check(b1); check(b2)
+    elif epi == "dgelu":
+        b1, o = guarded(torch.bfloat16)
+        aux = torch.randn(M, N, device=DEV).bfloat16()
+        _rg(A, B, 0, 0, M, N, K, L.EPI_DGELU_TANH, out=o, aux=aux)
+        check(b1)
+    elif epi == "gate_res":
+        b1, o = guarded(torch.bfloat16); b2, xo = guarded(torch.float32)
+        resid = torch.randn(M, N, device=DEV); gate = torch.randn(M // rps, N, device=DEV)
+        _rg(A, B, 0, 0, M, N, K, L.EPI_GATE_RES, out=o, out2=xo, bias=bias, resid=resid, gate=gate, rows_per_sample=rps)
+        check(b1); check(b2)
+        assert relerr(xo, resid + gate.repeat_interleave(rps, 0) * (A.float() @ B.float().t() + bias).bfloat16().float()) < 2e-3
+    else:
+        b1, o = guarded(torch.float32)
+        _rg(A, B, 0, 0, M, N, K, L.EPI_F32, out=o, bias=bias)
+        check(b1)
+        assert relerr(o, A.float() @ B.float().t() + bias) < 1e-5
