@@ -44,16 +44,20 @@ __device__ __forceinline__ void row_max_chunk(const uint32_t (&v)[32], int key0,
 __device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], uint32_t (&pk)[16], int key0, int T, float c,
                                               float mneg, float& s0, float& s1, float& s2, float& s3) {
   if (key0 + 32 <= T) {
+    const float2 c2 = make_float2(c, c), m2 = make_float2(mneg, mneg);
+    float2 sa = make_float2(s0, s1), sb = make_float2(s2, s3);
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), c, mneg));
-      const float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), c, mneg));
-      const float p2 = ex2_approx(fmaf(__uint_as_float(v[j + 2]), c, mneg));
-      const float p3 = ex2_approx(fmaf(__uint_as_float(v[j + 3]), c, mneg));
-      s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-      pk[j >> 1] = pack_bf16(p0, p1);
-      pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+    for (int j = 0; j < 32; j += 4) {   // packed FFMA2 / FADD2: two elements per issue slot around the MUFU.EX2
+      const float2 xa = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), c2, m2);
+      const float2 xb = __ffma2_rn(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), c2, m2);
+      const float2 pa = make_float2(ex2_approx(xa.x), ex2_approx(xa.y));
+      const float2 pb = make_float2(ex2_approx(xb.x), ex2_approx(xb.y));
+      sa = __fadd2_rn(sa, pa);
+      sb = __fadd2_rn(sb, pb);
+      pk[j >> 1] = pack_bf16(pa.x, pa.y);
+      pk[(j >> 1) + 1] = pack_bf16(pb.x, pb.y);
     }
+    s0 = sa.x; s1 = sa.y; s2 = sb.x; s3 = sb.y;
   } else {
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
