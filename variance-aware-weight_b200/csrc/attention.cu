@@ -5,9 +5,11 @@
 // feature order (3, H, hd) — the order both references produce — so no q/k/v split or head transpose is ever
 // materialised.  head_dim 64 (DiT-S/B/L, U-ViT) and 72 (DiT-XL) are supported; T is arbitrary (258 for U-ViT).
 //
-// Round-1 implementation: warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate), whole K/V (and for the
-// backward Q/dO) of one (batch, head) resident in shared memory.  Attention is 3.6 % of DiT-XL's FLOPs; the
-// tcgen05 version is scheduled after the GEMM path.
+// This file holds the entry points and the general-shape kernels: warp-level mma.sync.m16n8k16 (bf16 in, fp32
+// accumulate), whole K/V (and for the backward Q/dO) of one (batch, head) resident in shared memory, any T.
+// Sequences of up to 256 tokens - every DiT configuration - are dispatched to the tcgen05 / TMEM kernels in
+// attention_sm100.cu and attention_bwd_sm100.cu; the kernels below serve T > 256 (U-ViT: 258 tokens) and A/B testing
+// (VAW_ATTN_LEGACY=1).
 //
 // Softmax statistics are kept in the log2 domain: L2[q] = max_k(s*c) + log2(sum_k 2^(s*c - max)), c = scale*log2(e),
 // so that P = exp2(s*c - L2) in the backward pass.

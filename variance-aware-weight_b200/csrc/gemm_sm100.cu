@@ -11,9 +11,13 @@
 //
 // Kernel shape (persistent, 320 threads per CTA):
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> STAGES x {A, B} ring, mbarrier full/empty)
-//   warp 1      MMA issuer     (one lane issues tcgen05.mma, commits to the ring / to the epilogue)
-//   warps 2-9   epilogue       (tcgen05.ld -> registers -> smem transpose -> fused epilogue, coalesced global I/O)
+//   warp 1      MMA issuer     (the warp walks the loop with uniform descriptors, lane 0 issues tcgen05.mma and commits)
+//   warps 2-9   epilogue       (tcgen05.ld -> registers -> fused math -> swizzled staging boxes -> TMA store for the
+//                               bf16 / residual epilogues, with TMA loads of their tile inputs; the fp32
+//                               weight-gradient and split-K paths transpose through smem for coalesced stores)
 // Two accumulator stages in TMEM (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// Sustained runs are power-capped (scripts/dev_gemm_power.py): the epilogues are written for few instructions and
+// little data movement, because under the cap kernel time follows energy, not the critical path.
 //
 // PAIR = true: two CTAs of one cluster (an SM pair) work on a 256 x BN tile with tcgen05.mma.cta_group::2:
 // each CTA stages its own 128 rows of A and HALF of the B tile, the leader CTA issues the MMAs for both, and the
@@ -505,8 +509,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else {
     // ===================== epilogue warps =====================
     // kEpiParts warps per TMEM lane quarter; 32-column chunk c of the tile is drained by part c % kEpiParts.
-    // (Sixteen warps, not eight: the per-element epilogue math is a long dependent chain and two warps per scheduler
-    //  left the issue slots ~70 % idle - the epilogue, not the MMA main loop, bounded the short-K GEMMs.)
+    // (Sixteen epilogue warps were measured too: no better than eight once the epilogue math was trimmed, and the
+    //  register cap then spills the residual epilogues.)
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int part = (warp - 2) >> 2;
     constexpr int NCH_MAX = BN / 32;
