@@ -71,6 +71,30 @@ int vaw_qsample_target(const float* x0, const float* noise, const long long* t, 
                        const float* tab_sigma, const float* tab_c0, const float* tab_c1, float* x_t, float* target,
                        int mean_type, long long N, long long chw, vaw_stream_t stream);
 
+/* ---- K8: fused reverse-process step ------------------------------------------------------------
+ * Replaces the elementwise tail of GaussianDiffusion.p_mean_variance (tools/gaussian_diffusion.py:278-384) followed
+ * by p_sample (:455-506), ddim_sample (:603-651) or ddim_reverse_sample (:653-689), and the 8 per-call table uploads
+ * of _extract_into_tensor (:1059-1072).  model_out is the denoiser output, fp32 or bf16, out_stride values per sample
+ * (chw, or 2*chw with the variance channels behind the mean channels for the LEARNED* variance types, :312-314).
+ * tab is a [VAW_RT_ROWS][T] fp32 table (each float64 schedule table rounded once to fp32, as the reference does).
+ * Outputs are fp32 [N, chw]; any of them may be NULL (at least one must not be).  mode VAW_RS_MOMENTS only
+ * evaluates p_mean_variance.  mean_type / var_type use the reference's enum values (:21-45).  Each fp32 operation
+ * is rounded separately in the reference's order: results are bit-identical to the eager path except where exp()
+ * is involved (device vs host libm, <= 1 ulp).  VELOCITY uses the per-sample coefficient the reference intends
+ * (its :392-397 broadcasts over the wrong axis and only runs for N == 1 or N == W). */
+enum { VAW_VT_LEARNED = 1, VAW_VT_FIXED_SMALL = 2, VAW_VT_FIXED_LARGE = 3, VAW_VT_LEARNED_RANGE = 4 };
+enum { VAW_RS_DDPM = 0, VAW_RS_DDIM = 1, VAW_RS_DDIM_REVERSE = 2, VAW_RS_MOMENTS = 3 };
+enum { VAW_RT_SQRT_RECIP_AC = 0, VAW_RT_SQRT_RECIPM1_AC, VAW_RT_SQRT_AC, VAW_RT_SQRT_1MAC, VAW_RT_INV_COEF1,
+       VAW_RT_COEF2_OVER_COEF1, VAW_RT_COEF1, VAW_RT_COEF2, VAW_RT_LOGVAR /* LEARNED_RANGE: min_log */,
+       VAW_RT_MAX_LOG, VAW_RT_VARIANCE, VAW_RT_AC, VAW_RT_AC_PREV, VAW_RT_AC_NEXT, VAW_RT_ROWS };
+int vaw_reverse_step(const void* model_out, int out_dtype, long long out_stride, const float* x, const float* noise,
+                     const long long* t, const float* tab, int T, float* sample, float* pred_xstart, float* mean,
+                     float* log_variance, float* variance, int mean_type, int var_type, int mode, float eta, int clip,
+                     long long N, long long chw, vaw_stream_t stream);
+/* IntervalCFG combine (tools/sampler.py:46-48): both = [cond | uncond] halves of a doubled batch (half values each),
+ * y = uncond + scale * (cond - uncond), every op rounded in the tensor's dtype like the eager expression. */
+int vaw_cfg_combine(const void* both, void* y, int dtype, float scale, long long half, vaw_stream_t stream);
+
 /* ---- K2: fused weighted-MSE forward + backward --------------------------------------------------------------
  * Replaces (target - out)**2 -> mean_flat (tools/nn.py:86-90) -> w * raw (tools/gaussian_diffusion.py:911-913)
  * and the autograd backward of that chain (seeded by trainer.py:107-108).  The target is rebuilt from x0/noise

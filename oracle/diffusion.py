@@ -9,6 +9,8 @@ Follows /root/reference/tools/gaussian_diffusion.py:
     loss weight        compute_mse_loss_weight :1092-1148 (table in SURVEY.md §A.1)
     training_losses    :834-930 (MSE branch, fixed variance) and FlowMatching.training_losses :1297-1340
     align loss         compute_align_loss :1007-1046
+    reverse step       p_mean_variance :278-384, p_sample :455-506, ddim_sample :603-651, ddim_reverse_sample :653-689
+                       and IntervalCFG.forward tools/sampler.py:32-48 (the guidance combine)
 and tools/nn.py:86-90 (mean_flat).
 
 numpy for the integer/fp32 elementwise arithmetic (bit-exact with torch's eager fp32 ops), torch only where a model
@@ -49,6 +51,10 @@ def tables(betas):
         sqrt_alphas_cumprod=np.sqrt(ac), sqrt_one_minus_alphas_cumprod=np.sqrt(1.0 - ac),
         posterior_mean_coef1=betas * np.sqrt(ac_prev) / (1.0 - ac),
         posterior_mean_coef2=(1.0 - ac_prev) * np.sqrt(alphas) / (1.0 - ac),
+        alphas_cumprod_next=np.append(ac[1:], 0.0),
+        sqrt_recip_alphas_cumprod=np.sqrt(1.0 / ac), sqrt_recipm1_alphas_cumprod=np.sqrt(1.0 / ac - 1),
+        posterior_variance=(pv := betas * (1.0 - ac_prev) / (1.0 - ac)),
+        posterior_log_variance_clipped=np.log(np.append(pv[1], pv[1:])),
     )
 
 
@@ -194,3 +200,128 @@ def training_losses_torch(tb, mean_type, weight_type, model_fn, x0, t, eps, *, n
     else:
         terms["loss"] = terms["mse"]
     return terms
+
+
+# ---- reverse process (inference path) ----------------------------------------------------------------
+def _bf16_round(a):
+    """Round-to-nearest-even to bfloat16, returned as float32 (what a bf16 torch op does to its fp32 result)."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    out = r.view(np.float32).copy()
+    nan = np.isnan(a)
+    out[nan] = np.nan
+    return out.reshape(np.shape(a))
+
+
+def p_mean_variance(tb, mean_type, var_type, model_output, x, t, clip_denoised=True, out_is_bf16=False):
+    """gaussian_diffusion.py:278-384.  model_output: [N, C or 2C, H, W] float32 values (already widened if the model
+    returned bf16: pass out_is_bf16=True so the variance branch keeps the reference's bf16 intermediates)."""
+    f = np.float32
+    x = np.asarray(x, dtype=f)
+    model_output = np.asarray(model_output, dtype=f)
+    C = x.shape[1]
+    rb = _bf16_round if out_is_bf16 else (lambda a: a)
+    if var_type in ("LEARNED", "LEARNED_RANGE"):
+        assert model_output.shape[1] == 2 * C
+        model_output, v = model_output[:, :C], model_output[:, C:]
+        if var_type == "LEARNED":
+            log_var = v
+            var = rb(np.exp(v).astype(f))
+        else:
+            min_log = extract(tb["posterior_log_variance_clipped"], t)
+            max_log = extract(np.log(tb["betas"]), t)
+            frac = rb((rb((v + f(1)).astype(f)) / f(2)).astype(f))
+            log_var = (frac * max_log).astype(f) + (rb((f(1) - frac).astype(f)) * min_log).astype(f)
+            var = np.exp(log_var).astype(f)
+    else:
+        pv = tb["posterior_variance"]
+        if var_type == "FIXED_LARGE":
+            vt = np.append(pv[1], tb["betas"][1:])
+            var_t, lv_t = vt, np.log(vt)
+        else:
+            var_t, lv_t = pv, tb["posterior_log_variance_clipped"]
+        var = np.broadcast_to(extract(var_t, t), x.shape)
+        log_var = np.broadcast_to(extract(lv_t, t), x.shape)
+
+    def proc(a):
+        return np.clip(a, f(-1), f(1)) if clip_denoised else a
+
+    if mean_type == "PREVIOUS_X":
+        c1, c2 = tb["posterior_mean_coef1"], tb["posterior_mean_coef2"]
+        xs = proc((extract(1.0 / c1, t) * model_output).astype(f) - (extract(c2 / c1, t) * x).astype(f))
+        mean = model_output
+    else:
+        if mean_type == "START_X":
+            xs = proc(model_output)
+        elif mean_type == "EPSILON":
+            xs = proc((extract(tb["sqrt_recip_alphas_cumprod"], t) * x).astype(f)
+                      - (extract(tb["sqrt_recipm1_alphas_cumprod"], t) * model_output).astype(f))
+        elif mean_type == "VELOCITY":   # per-sample coefficients (the reference's :392-397 only runs for N == 1)
+            xs = proc((extract(tb["sqrt_alphas_cumprod"], t) * x).astype(f)
+                      - (extract(tb["sqrt_one_minus_alphas_cumprod"], t) * model_output).astype(f))
+        else:
+            raise NotImplementedError(mean_type)
+        mean = (extract(tb["posterior_mean_coef1"], t) * xs).astype(f) + (extract(tb["posterior_mean_coef2"], t) * x).astype(f)
+    return dict(mean=mean, variance=var, log_variance=log_var, pred_xstart=xs)
+
+
+def _nonzero_mask(t):
+    return (np.asarray(t) != 0).astype(np.float32).reshape(-1, 1, 1, 1)
+
+
+def p_sample(tb, mean_type, var_type, model_output, x, t, noise, clip_denoised=True, out_is_bf16=False):
+    """:455-506 without cond_fn."""
+    f = np.float32
+    out = p_mean_variance(tb, mean_type, var_type, model_output, x, t, clip_denoised, out_is_bf16)
+    lv = out["log_variance"]
+    if var_type == "LEARNED" and out_is_bf16:
+        e = _bf16_round(np.exp(_bf16_round((f(0.5) * lv).astype(f))).astype(f))
+    else:
+        e = np.exp((f(0.5) * lv).astype(f)).astype(f)
+    sample = out["mean"] + ((_nonzero_mask(t) * e).astype(f) * np.asarray(noise, dtype=f)).astype(f)
+    return dict(sample=sample.astype(f), pred_xstart=out["pred_xstart"])
+
+
+def _eps_from_xstart(tb, x, t, xs):
+    f = np.float32
+    return (((extract(tb["sqrt_recip_alphas_cumprod"], t) * x).astype(f) - xs).astype(f)
+            / extract(tb["sqrt_recipm1_alphas_cumprod"], t)).astype(f)
+
+
+def ddim_sample(tb, mean_type, var_type, model_output, x, t, noise, eta=0.0, clip_denoised=True, out_is_bf16=False):
+    """:603-651 without cond_fn."""
+    f = np.float32
+    x = np.asarray(x, dtype=f)
+    out = p_mean_variance(tb, mean_type, var_type, model_output, x, t, clip_denoised, out_is_bf16)
+    xs = out["pred_xstart"]
+    eps = _eps_from_xstart(tb, x, t, xs)
+    ab, abp = extract(tb["alphas_cumprod"], t), extract(tb["alphas_cumprod_prev"], t)
+    one = f(1)
+    sigma = ((f(eta) * np.sqrt(((one - abp).astype(f) / (one - ab).astype(f)).astype(f))).astype(f)
+             * np.sqrt((one - (ab / abp).astype(f)).astype(f))).astype(f)
+    mean_pred = ((xs * np.sqrt(abp)).astype(f)
+                 + (np.sqrt(((one - abp).astype(f) - (sigma * sigma).astype(f)).astype(f)) * eps).astype(f)).astype(f)
+    sample = mean_pred + ((_nonzero_mask(t) * sigma).astype(f) * np.asarray(noise, dtype=f)).astype(f)
+    return dict(sample=sample.astype(f), pred_xstart=xs)
+
+
+def ddim_reverse_sample(tb, mean_type, var_type, model_output, x, t, clip_denoised=True, out_is_bf16=False):
+    """:653-689."""
+    f = np.float32
+    x = np.asarray(x, dtype=f)
+    out = p_mean_variance(tb, mean_type, var_type, model_output, x, t, clip_denoised, out_is_bf16)
+    xs = out["pred_xstart"]
+    eps = _eps_from_xstart(tb, x, t, xs)
+    abn = extract(tb["alphas_cumprod_next"], t)
+    mean_pred = (xs * np.sqrt(abn)).astype(f) + (np.sqrt((f(1) - abn).astype(f)) * eps).astype(f)
+    return dict(sample=mean_pred.astype(f), pred_xstart=xs)
+
+
+def cfg_combine(cond, uncond, scale, is_bf16=False):
+    """tools/sampler.py:46-48: uncond + scale * (cond - uncond), each op rounded in the tensor dtype."""
+    f = np.float32
+    rb = _bf16_round if is_bf16 else (lambda a: a)
+    cond, uncond = np.asarray(cond, dtype=f), np.asarray(uncond, dtype=f)
+    d = rb((cond - uncond).astype(f))
+    m = rb((f(scale) * d).astype(f))
+    return rb((uncond + m).astype(f))

@@ -11,6 +11,8 @@ installed; see oracle/ref_stubs/README.md).  Everything written here is an input
     sampler_golden.npz     LossSecondMomentResampler.weights / sample / update_with_all_losses, UniformSampler.sample
     unet_golden.npz        two tiny UNets (both attention orders / conditioning styles): weights, forward, losses, grads
     unet_shapes.json       state-dict names and shapes of every UNet factory (built on the meta device)
+    reverse_golden.npz     p_mean_variance / p_sample / ddim_sample / ddim_reverse_sample over every mean / variance type
+                           (fp32 and bf16 model outputs, pinned noise), IntervalCFG combine
     dit_golden.npz         a tiny DiT (with REPA projector): weights, forward outputs, full training_losses + grads
 """
 import os
@@ -247,7 +249,80 @@ def unet_golden():
     print("unet_golden.npz", len(out), "arrays; unet_shapes.json", {k: len(v) for k, v in shapes.items()})
 
 
+REVERSE_CASES = [  # (mean type, variance type, model-output dtype, clip_denoised)
+    ("EPSILON", "FIXED_LARGE", "f32", True), ("EPSILON", "FIXED_SMALL", "f32", False),
+    ("EPSILON", "FIXED_LARGE", "bf16", True), ("START_X", "FIXED_LARGE", "f32", True),
+    ("PREVIOUS_X", "FIXED_SMALL", "f32", True), ("EPSILON", "LEARNED_RANGE", "f32", True),
+    ("EPSILON", "LEARNED_RANGE", "bf16", True), ("EPSILON", "LEARNED", "f32", True),
+    ("START_X", "LEARNED", "bf16", False),
+]
+
+
+def reverse_golden():
+    import tools.sampler as rsm   # noqa: E402  (reference)
+    out = {}
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(6, 3, 8, 8, generator=g) * 1.5
+    mo2 = torch.randn(6, 6, 8, 8, generator=g)
+    noise = torch.randn(6, 3, 8, 8, generator=g)
+    t = torch.tensor([0, 1, 500, 998, 999, 37])
+    out.update(x=x.numpy(), model_out2=mo2.numpy(), noise=noise.numpy(), t=t.numpy())
+    orig = torch.randn_like
+    torch.randn_like = lambda a, **k: noise[:a.shape[0]].clone()
+    try:
+        for mean, var, dt, clip in REVERSE_CASES:
+            d = rgd.GaussianDiffusion(args=ref_args(), betas=rgd.get_named_beta_schedule("linear", 1000),
+                                      model_mean_type=rgd.ModelMeanType[mean], model_var_type=rgd.ModelVarType[var],
+                                      loss_type=rgd.LossType.MSE, rescale_timesteps=True, device="cpu")
+            mo = mo2 if var.startswith("LEARNED") else mo2[:, :3].contiguous()
+            if dt == "bf16":
+                mo = mo.bfloat16()
+            model = lambda xx, ts, **k: mo
+            key = f"{mean}_{var}_{dt}_{int(clip)}"
+            pmv = d.p_mean_variance(model, x, t, clip_denoised=clip)
+            for k in ("mean", "variance", "log_variance", "pred_xstart"):
+                out[f"pmv_{k}::{key}"] = pmv[k].float().numpy()
+            out[f"p_sample::{key}"] = d.p_sample(model, x, t, clip_denoised=clip)["sample"].float().numpy()
+            out[f"ddim0::{key}"] = d.ddim_sample(model, x, t, clip_denoised=clip, eta=0.0)["sample"].float().numpy()
+            out[f"ddim7::{key}"] = d.ddim_sample(model, x, t, clip_denoised=clip, eta=0.7)["sample"].float().numpy()
+            out[f"ddimrev::{key}"] = d.ddim_reverse_sample(model, x, t, clip_denoised=clip)["sample"].float().numpy()
+        # VELOCITY: the reference's _predict_xstart_from_v broadcasts its coefficient over the last axis, so it only
+        # means "per sample" for a batch of one
+        d = make_diffusion("cosine", "VELOCITY")
+        for i in (1, 2, 4):
+            model = lambda xx, ts, **k: mo2[i:i + 1, :3]
+            out[f"vel_ddim0::{i}"] = d.ddim_sample(model, x[i:i + 1], t[i:i + 1], eta=0.0)["sample"].numpy()
+            out[f"vel_xs::{i}"] = d.p_mean_variance(model, x[i:i + 1], t[i:i + 1])["pred_xstart"].numpy()
+    finally:
+        torch.randn_like = orig
+    # IntervalCFG (tools/sampler.py:10-48): doubled batch through a recorded "model", guidance inside / outside the interval
+    y = torch.tensor([1, 2, 3])
+    both = torch.randn(6, 3, 8, 8, generator=g)
+    calls = []
+
+    class Rec(torch.nn.Module):
+        def __init__(self, dt):
+            super().__init__()
+            self.dt = dt
+
+        def forward(self, xx, tt, **kw):
+            calls.append((tuple(xx.shape), kw["y"].tolist()))
+            return (both if xx.shape[0] == 6 else both[:3]).to(self.dt)
+
+    for dt, name in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+        cfg = rsm.IntervalCFG(Rec(dt), num_classes=10, guidance_scale=2.5, interval=(100.0, 600.0))
+        out[f"cfg_in::{name}"] = cfg(x[:3], torch.tensor([300.0] * 3), y=y).float().numpy()
+        out[f"cfg_out::{name}"] = cfg(x[:3], torch.tensor([800.0] * 3), y=y).float().numpy()
+    out["cfg_both"] = both.numpy()
+    out["cfg_labels_seen"] = np.array(calls[0][1])
+    np.savez_compressed(os.path.join(HERE, "reverse_golden.npz"), **out)
+    print("reverse_golden.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "reverse":
+        reverse_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "diffusion":
         diffusion_golden()
         sys.exit(0)
@@ -258,4 +333,5 @@ if __name__ == "__main__":
     uvit_golden()
     diffusion_golden()
     sampler_golden()
+    reverse_golden()
     dit_golden()

@@ -9,6 +9,8 @@
 //   x_t    = fl( fl(a*x0) + fl(s*eps) )      two multiplies and one add, never contracted into an FMA
 //   v-tgt  = fl( fl(a*eps) - fl(s*x0) )
 // a = float(sqrt_alphas_cumprod[t]), s = float(sqrt_one_minus_alphas_cumprod[t]) (f64 table rounded once to f32).
+#include <type_traits>
+
 #include "vaw_common.cuh"
 
 namespace {
@@ -219,6 +221,177 @@ sample_from_latent_kernel(const float* __restrict__ latent, const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K8: one fused reverse-process step.  Replaces the elementwise tail of p_mean_variance
+// (gaussian_diffusion.py:278-384) + p_sample (:455-506) / ddim_sample (:603-651) / ddim_reverse_sample (:653-689):
+// the ~25 elementwise launches and 8 table uploads of the reference become one pass that reads the model
+// output, x_t (and the noise) once and writes the next sample (and, on request, pred_xstart / mean / variance).
+// Every product, sum, quotient and square root is rounded separately in the reference's order, so the fp32
+// results are bit-identical to the eager path; only exp() (device libm vs host libm) may differ by an ulp.
+// For a bf16 model output the variance branch keeps the reference's bf16 intermediates.
+// ------------------------------------------------------------------------------------------------
+enum : int { VT_LEARNED = 1, VT_FIXED_SMALL = 2, VT_FIXED_LARGE = 3, VT_LEARNED_RANGE = 4 };
+enum : int { RS_DDPM = 0, RS_DDIM = 1, RS_DDIM_REVERSE = 2, RS_MOMENTS = 3 };
+enum : int { RT_SQRT_RECIP_AC = 0, RT_SQRT_RECIPM1_AC, RT_SQRT_AC, RT_SQRT_1MAC, RT_INV_COEF1, RT_COEF2_OVER_COEF1,
+             RT_COEF1, RT_COEF2, RT_LOGVAR, RT_MAX_LOG, RT_VARIANCE, RT_AC, RT_AC_PREV, RT_AC_NEXT, RT_ROWS };
+
+struct StepCoef {
+  float p, q;          // pred_xstart = p * (x_t or xprev) - q * (model output or x_t)
+  float c1, c2;        // posterior mean
+  float lv, maxlog, var;
+  float recip, recipm1;
+  float k_xs, k_eps, sig;  // DDIM: sample = k_xs * xs + k_eps * eps + sig * noise
+  float mask;
+};
+
+__device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__device__ __forceinline__ StepCoef load_step_coef(const float* __restrict__ tab, int T, long long tt, int mean_type,
+                                                   int mode, float eta) {
+  StepCoef c;
+  auto row = [&](int r) { return __ldg(tab + (long long)r * T + tt); };
+  c.recip = row(RT_SQRT_RECIP_AC);
+  c.recipm1 = row(RT_SQRT_RECIPM1_AC);
+  if (mean_type == MT_EPSILON) { c.p = c.recip; c.q = c.recipm1; }
+  else if (mean_type == MT_VELOCITY) { c.p = row(RT_SQRT_AC); c.q = row(RT_SQRT_1MAC); }
+  else if (mean_type == MT_PREVIOUS_X) { c.p = row(RT_INV_COEF1); c.q = row(RT_COEF2_OVER_COEF1); }
+  else { c.p = 1.f; c.q = 0.f; }
+  c.c1 = row(RT_COEF1);
+  c.c2 = row(RT_COEF2);
+  c.lv = row(RT_LOGVAR);
+  c.maxlog = row(RT_MAX_LOG);
+  c.var = row(RT_VARIANCE);
+  c.mask = tt != 0 ? 1.f : 0.f;
+  c.k_xs = c.k_eps = c.sig = 0.f;
+  if (mode == RS_DDIM) {
+    const float ab = row(RT_AC), abp = row(RT_AC_PREV);
+    const float om_abp = __fsub_rn(1.f, abp);
+    const float s1 = __fsqrt_rn(__fdiv_rn(om_abp, __fsub_rn(1.f, ab)));
+    const float s2 = __fsqrt_rn(__fsub_rn(1.f, __fdiv_rn(ab, abp)));
+    const float sigma = __fmul_rn(__fmul_rn(eta, s1), s2);
+    c.k_xs = __fsqrt_rn(abp);
+    c.k_eps = __fsqrt_rn(__fsub_rn(om_abp, __fmul_rn(sigma, sigma)));
+    c.sig = __fmul_rn(c.mask, sigma);
+  } else if (mode == RS_DDIM_REVERSE) {
+    const float abn = row(RT_AC_NEXT);
+    c.k_xs = __fsqrt_rn(abn);
+    c.k_eps = __fsqrt_rn(__fsub_rn(1.f, abn));
+  }
+  return c;
+}
+
+struct StepOut { float sample, xs, mean, lv, var; };
+
+// BF: the model output arrived as bf16, so the reference's variance arithmetic on it rounds to bf16 per op
+template <bool BF>
+__device__ __forceinline__ StepOut step_elem(const StepCoef& c, float o, float vv, float x, float z, int mean_type,
+                                             int var_type, int mode, bool clip) {
+  StepOut r;
+  float xs;
+  if (mean_type == MT_START_X) xs = o;
+  else if (mean_type == MT_PREVIOUS_X) xs = __fsub_rn(__fmul_rn(c.p, o), __fmul_rn(c.q, x));
+  else xs = __fsub_rn(__fmul_rn(c.p, x), __fmul_rn(c.q, o));
+  if (clip) xs = xs < -1.f ? -1.f : (xs > 1.f ? 1.f : xs);  // NaN stays NaN, as torch.clamp
+  r.xs = xs;
+  r.mean = mean_type == MT_PREVIOUS_X ? o : __fadd_rn(__fmul_rn(c.c1, xs), __fmul_rn(c.c2, x));
+  float half_lv_exp;  // exp(0.5 * log_variance) in the dtype the reference computes it in
+  if (var_type == VT_LEARNED) {
+    r.lv = vv;
+    r.var = BF ? bf16r(expf(vv)) : expf(vv);
+    const float h = __fmul_rn(0.5f, vv);
+    half_lv_exp = BF ? bf16r(expf(bf16r(h))) : expf(h);
+  } else if (var_type == VT_LEARNED_RANGE) {
+    float frac = __fadd_rn(vv, 1.f);
+    if (BF) frac = bf16r(frac);
+    frac = __fdiv_rn(frac, 2.f);
+    if (BF) frac = bf16r(frac);
+    float om = __fsub_rn(1.f, frac);
+    if (BF) om = bf16r(om);
+    r.lv = __fadd_rn(__fmul_rn(frac, c.maxlog), __fmul_rn(om, c.lv));
+    r.var = expf(r.lv);
+    half_lv_exp = expf(__fmul_rn(0.5f, r.lv));
+  } else {
+    r.lv = c.lv;
+    r.var = c.var;
+    half_lv_exp = expf(__fmul_rn(0.5f, c.lv));
+  }
+  if (mode == RS_DDPM) {
+    r.sample = __fadd_rn(r.mean, __fmul_rn(__fmul_rn(c.mask, half_lv_exp), z));
+  } else if (mode == RS_DDIM || mode == RS_DDIM_REVERSE) {
+    const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(c.recip, x), xs), c.recipm1);
+    const float mp = __fadd_rn(__fmul_rn(xs, c.k_xs), __fmul_rn(c.k_eps, eps));
+    r.sample = mode == RS_DDIM ? __fadd_rn(mp, __fmul_rn(c.sig, z)) : mp;
+  } else {
+    r.sample = r.mean;
+  }
+  return r;
+}
+
+struct StepPtrs { float *sample, *xs, *mean, *lv, *var; };
+
+template <typename OutT, bool VEC>
+__global__ void __launch_bounds__(256)
+reverse_step_kernel(const OutT* __restrict__ out, long long out_stride, const float* __restrict__ x,
+                    const float* __restrict__ noise, const long long* __restrict__ t, const float* __restrict__ tab,
+                    int T, StepPtrs dst, int mean_type, int var_type, int mode, float eta, int clip, long long N,
+                    long long chw) {
+  constexpr bool BF = !std::is_same<OutT, float>::value;
+  const bool learned = var_type == VT_LEARNED || var_type == VT_LEARNED_RANGE;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (VEC) {
+    const long long chw4 = chw >> 2, total4 = N * chw4, os4 = out_stride >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+      const long long n = i / chw4, r = i - n * chw4;
+      const StepCoef c = load_step_coef(tab, T, t[n], mean_type, mode, eta);
+      const float4 o = Vec4<OutT>::load(out, n * os4 + r);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f), z = v;
+      if (learned) v = Vec4<OutT>::load(out, n * os4 + chw4 + r);
+      const float4 xv = ldg_stream_f4(reinterpret_cast<const float4*>(x) + i);
+      if (noise) z = ldg_stream_f4(reinterpret_cast<const float4*>(noise) + i);
+      const StepOut a = step_elem<BF>(c, o.x, v.x, xv.x, z.x, mean_type, var_type, mode, clip != 0);
+      const StepOut b = step_elem<BF>(c, o.y, v.y, xv.y, z.y, mean_type, var_type, mode, clip != 0);
+      const StepOut d = step_elem<BF>(c, o.z, v.z, xv.z, z.z, mean_type, var_type, mode, clip != 0);
+      const StepOut e = step_elem<BF>(c, o.w, v.w, xv.w, z.w, mean_type, var_type, mode, clip != 0);
+      if (dst.sample) stg_stream_f4(reinterpret_cast<float4*>(dst.sample) + i, make_float4(a.sample, b.sample, d.sample, e.sample));
+      if (dst.xs) stg_stream_f4(reinterpret_cast<float4*>(dst.xs) + i, make_float4(a.xs, b.xs, d.xs, e.xs));
+      if (dst.mean) stg_stream_f4(reinterpret_cast<float4*>(dst.mean) + i, make_float4(a.mean, b.mean, d.mean, e.mean));
+      if (dst.lv) stg_stream_f4(reinterpret_cast<float4*>(dst.lv) + i, make_float4(a.lv, b.lv, d.lv, e.lv));
+      if (dst.var) stg_stream_f4(reinterpret_cast<float4*>(dst.var) + i, make_float4(a.var, b.var, d.var, e.var));
+    }
+  } else {
+    const long long total = N * chw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+      const long long n = i / chw, r = i - n * chw;
+      const StepCoef c = load_step_coef(tab, T, t[n], mean_type, mode, eta);
+      const float o = (float)out[n * out_stride + r];
+      const float v = learned ? (float)out[n * out_stride + chw + r] : 0.f;
+      const StepOut a = step_elem<BF>(c, o, v, x[i], noise ? noise[i] : 0.f, mean_type, var_type, mode, clip != 0);
+      if (dst.sample) dst.sample[i] = a.sample;
+      if (dst.xs) dst.xs[i] = a.xs;
+      if (dst.mean) dst.mean[i] = a.mean;
+      if (dst.lv) dst.lv[i] = a.lv;
+      if (dst.var) dst.var[i] = a.var;
+    }
+  }
+}
+
+// IntervalCFG combine (tools/sampler.py:46-48): uncond + scale * (cond - uncond) on the two halves of a doubled
+// batch, each op rounded in the tensor's own dtype as the eager expression does.
+template <typename T>
+__global__ void __launch_bounds__(256)
+cfg_combine_kernel(const T* __restrict__ both, T* __restrict__ y, float scale, long long half) {
+  constexpr bool BF = !std::is_same<T, float>::value;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
+    const float c = (float)both[i], u = (float)both[half + i];
+    float d = __fsub_rn(c, u);
+    if (BF) d = bf16r(d);
+    float m = __fmul_rn(scale, d);
+    if (BF) m = bf16r(m);
+    y[i] = (T)__fadd_rn(u, m);
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -232,6 +405,62 @@ extern "C" int vaw_sample_from_latent(const float* latent, const float* eps, flo
   const long long cap = (long long)vaw_num_sms() * 16;
   if (blocks > cap) blocks = cap;
   sample_from_latent_kernel<<<(unsigned)blocks, 256, 0, stream>>>(latent, eps, out, N, chw, scale);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+extern "C" int vaw_reverse_step(const void* model_out, int out_dtype, long long out_stride, const float* x,
+                                const float* noise, const long long* t, const float* tab, int T, float* sample,
+                                float* pred_xstart, float* mean, float* log_variance, float* variance, int mean_type,
+                                int var_type, int mode, float eta, int clip, long long N, long long chw,
+                                cudaStream_t stream) {
+  VAW_CHECK_ARG(model_out && x && t && tab && T > 0, "vaw_reverse_step: null pointer");
+  VAW_CHECK_ARG(out_dtype == 0 || out_dtype == 1, "vaw_reverse_step: out_dtype must be 0 (f32) or 1 (bf16)");
+  VAW_CHECK_ARG(N >= 0 && chw > 0, "vaw_reverse_step: bad shape N=%lld chw=%lld", N, chw);
+  VAW_CHECK_ARG(mean_type >= MT_PREVIOUS_X && mean_type <= MT_VELOCITY,
+                "vaw_reverse_step: mean_type %d has no reverse step (NotImplementedError in the reference)", mean_type);
+  VAW_CHECK_ARG(var_type >= VT_LEARNED && var_type <= VT_LEARNED_RANGE, "vaw_reverse_step: bad var_type %d", var_type);
+  VAW_CHECK_ARG(mode >= RS_DDPM && mode <= RS_MOMENTS, "vaw_reverse_step: bad mode %d", mode);
+  const bool learned = var_type == VT_LEARNED || var_type == VT_LEARNED_RANGE;
+  VAW_CHECK_ARG(out_stride == (learned ? 2 : 1) * chw,
+                "vaw_reverse_step: model output has %lld values per sample, expected %lld", out_stride,
+                (learned ? 2 : 1) * chw);
+  VAW_CHECK_ARG(noise || (mode != RS_DDPM && !(mode == RS_DDIM && eta != 0.f)), "vaw_reverse_step: this mode needs noise");
+  VAW_CHECK_ARG(mode != RS_DDIM_REVERSE || eta == 0.f, "Reverse ODE only for deterministic path");
+  VAW_CHECK_ARG(sample || pred_xstart || mean || log_variance || variance, "vaw_reverse_step: no output requested");
+  if (N == 0) return VAW_OK;
+  if (mode == RS_DDIM && eta == 0.f) noise = nullptr;  // sigma == 0: the reference adds 0 * noise
+  const uintptr_t al = (uintptr_t)model_out | (uintptr_t)x | (uintptr_t)noise | (uintptr_t)sample |
+                       (uintptr_t)pred_xstart | (uintptr_t)mean | (uintptr_t)log_variance | (uintptr_t)variance;
+  const bool vec = (chw % 4 == 0) && ((al & 15) == 0);
+  const long long work = vec ? N * (chw / 4) : N * chw;
+  long long blocks = (work + 255) / 256;
+  const long long cap = (long long)vaw_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  const StepPtrs dst{sample, pred_xstart, mean, log_variance, variance};
+#define VAW_RS_LAUNCH(TY, V)                                                                                     \
+  reverse_step_kernel<TY, V><<<(unsigned)blocks, 256, 0, stream>>>((const TY*)model_out, out_stride, x, noise, t, \
+                                                                   tab, T, dst, mean_type, var_type, mode, eta,  \
+                                                                   clip, N, chw)
+  if (out_dtype == 0) { if (vec) VAW_RS_LAUNCH(float, true); else VAW_RS_LAUNCH(float, false); }
+  else { if (vec) VAW_RS_LAUNCH(bf16, true); else VAW_RS_LAUNCH(bf16, false); }
+#undef VAW_RS_LAUNCH
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+extern "C" int vaw_cfg_combine(const void* both, void* y, int dtype, float scale, long long half,
+                               cudaStream_t stream) {
+  VAW_CHECK_ARG(both && y && half >= 0, "vaw_cfg_combine: bad arguments");
+  VAW_CHECK_ARG(dtype == 0 || dtype == 1, "vaw_cfg_combine: dtype must be 0 (f32) or 1 (bf16)");
+  if (half == 0) return VAW_OK;
+  long long blocks = (half + 255) / 256;
+  const long long cap = (long long)vaw_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (dtype == 0)
+    cfg_combine_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>((const float*)both, (float*)y, scale, half);
+  else
+    cfg_combine_kernel<bf16><<<(unsigned)blocks, 256, 0, stream>>>((const bf16*)both, (bf16*)y, scale, half);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }

@@ -16,6 +16,9 @@ F32, BF16 = 0, 1
 # ModelMeanType codes (reference enum values)
 MEAN_PREVIOUS_X, MEAN_START_X, MEAN_EPSILON, MEAN_VELOCITY, MEAN_VECTOR, MEAN_SCORE = 1, 2, 3, 4, 5, 6
 
+# reverse-step modes (include/vaw_b200.h VAW_RS_*)
+RS_DDPM, RS_DDIM, RS_DDIM_REVERSE, RS_MOMENTS = range(4)
+
 W_CONSTANT, W_LAMBDA, W_MIN_SNR, W_MAX_SNR, W_DEBIAS, W_MIN_DEBIAS, W_MAX_DEBIAS, W_P2, W_TRUNC_SNR, W_SNR, W_INV_SNR = range(11)
 
 (EPI_BF16, EPI_F32, EPI_GELU_TANH, EPI_GELU_ERF, EPI_GATE_RES, EPI_RES, EPI_DGELU_TANH, EPI_DGELU_ERF, EPI_SILU,
@@ -48,6 +51,8 @@ _SIGS = {
     "vaw_device_check": [],
     "vaw_qsample_target": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _LL, _LL, _P],
     "vaw_wmse_fwd_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _LL, _LL, _P],
+    "vaw_reverse_step": [_P, _I, _LL, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _LL, _LL, _P],
+    "vaw_cfg_combine": [_P, _P, _I, _F, _LL, _P],
     "vaw_scale_rows": [_P, _P, _P, _I, _LL, _LL, _P],
     "vaw_loss_weight_lut": [_P, _P, _I, _I, _I, _D, _D, _D, _P],
     "vaw_sampler_sample": [_I, _P, _P, _P, _I, _I, _D, _P, _LL, _P, _P, _P, _P, _P, _P],

@@ -396,6 +396,146 @@ class GaussianDiffusion:
         return terms
 
 
+    # ---- reverse process: one fused kernel per step instead of ~25 elementwise launches ---------
+    def unpack_model_output(self, raw_output):
+        """Reference :208-215: models may return (pred, aux, ...); sampling needs the prediction only."""
+        return raw_output[0] if isinstance(raw_output, tuple) else raw_output
+
+    def _reverse_table(self, device):
+        """[VAW_RT_ROWS, T] fp32 device table (include/vaw_b200.h), every float64 row rounded once like
+        _extract_into_tensor (:1059-1072)."""
+        key = ("reverse", str(device))
+        tb = self._dev_tables.get(key)
+        if tb is None:
+            zero = np.zeros_like(self.betas)
+            if self.model_var_type == ModelVarType.FIXED_LARGE:      # :326-331
+                var = np.append(self.posterior_variance[1], self.betas[1:])
+                logvar = np.log(var)
+            elif self.model_var_type == ModelVarType.FIXED_SMALL:
+                var, logvar = self.posterior_variance, self.posterior_log_variance_clipped
+            else:                                                     # LEARNED_RANGE: min_log (:319-321)
+                var, logvar = zero, self.posterior_log_variance_clipped
+            with np.errstate(divide="ignore", invalid="ignore"):
+                rows = [self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod, self.sqrt_alphas_cumprod,
+                        self.sqrt_one_minus_alphas_cumprod, 1.0 / self.posterior_mean_coef1,
+                        self.posterior_mean_coef2 / self.posterior_mean_coef1, self.posterior_mean_coef1,
+                        self.posterior_mean_coef2, logvar, np.log(self.betas), var, self.alphas_cumprod,
+                        self.alphas_cumprod_prev, self.alphas_cumprod_next]
+            tb = th.from_numpy(np.stack([np.asarray(r, dtype=np.float64) for r in rows])).to(device).float().contiguous()
+            self._dev_tables[key] = tb
+        return tb
+
+    def _model_output(self, model, x, t, model_kwargs):
+        if model_kwargs is None:
+            model_kwargs = {}
+        B, C = x.shape[:2]
+        assert t.shape == (B,)
+        out = self.unpack_model_output(model(x, self._scale_timesteps(t), **model_kwargs))
+        learned = self.model_var_type in (ModelVarType.LEARNED, ModelVarType.LEARNED_RANGE)
+        assert out.shape == (B, C * 2 if learned else C, *x.shape[2:])
+        if out.dtype not in (th.float32, th.bfloat16):
+            out = out.float()
+        return out.contiguous()
+
+    def _reverse(self, mode, model, x, t, *, clip_denoised, denoised_fn, cond_fn, model_kwargs, eta=0.0, noise=None,
+                 want=("sample", "pred_xstart")):
+        if denoised_fn is not None or cond_fn is not None:
+            raise NotImplementedError("denoised_fn / cond_fn hooks are outside the fused reverse step")
+        if self.model_mean_type not in (ModelMeanType.PREVIOUS_X, ModelMeanType.START_X, ModelMeanType.EPSILON,
+                                        ModelMeanType.VELOCITY):
+            raise NotImplementedError(self.model_mean_type)
+        L.require_cuda(x, t)
+        xf = _f32(x)
+        t64 = t.to(th.int64).contiguous()
+        out = self._model_output(model, xf, t64, model_kwargs)
+        need_noise = mode == L.RS_DDPM or (mode == L.RS_DDIM and eta != 0.0)
+        if mode in (L.RS_DDPM, L.RS_DDIM) and noise is None:
+            noise = th.randn_like(xf)        # drawn even when unused, so the RNG stream matches the reference's
+        nz = _f32(noise) if need_noise else None
+        if nz is not None:
+            L.require_cuda(nz)
+            assert nz.shape == xf.shape
+        res = {k: th.empty_like(xf) for k in want}
+        N = xf.shape[0]
+        if xf.numel():
+            tab = self._reverse_table(xf.device)
+            L.call("vaw_reverse_step", out.data_ptr(), L.BF16 if out.dtype == th.bfloat16 else L.F32,
+                   out[0].numel(), xf.data_ptr(), L.ptr(nz), t64.data_ptr(),
+                   tab.data_ptr(), self.num_timesteps, L.ptr(res.get("sample")), L.ptr(res.get("pred_xstart")),
+                   L.ptr(res.get("mean")), L.ptr(res.get("log_variance")), L.ptr(res.get("variance")),
+                   self.model_mean_type.value, self.model_var_type.value, mode, float(eta), 1 if clip_denoised else 0,
+                   N, xf[0].numel(), L.stream_ptr())
+        return res
+
+    def p_mean_variance(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None):
+        """Reference :278-384 -> {"mean", "variance", "log_variance", "pred_xstart"} (fp32, shape of x)."""
+        return self._reverse(L.RS_MOMENTS, model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                             cond_fn=None, model_kwargs=model_kwargs,
+                             want=("mean", "variance", "log_variance", "pred_xstart"))
+
+    def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None):
+        """Reference :455-506 -> {"sample", "pred_xstart"}."""
+        return self._reverse(L.RS_DDPM, model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                             cond_fn=cond_fn, model_kwargs=model_kwargs)
+
+    def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, eta=0.0):
+        """Reference :603-651 -> {"sample", "pred_xstart"}."""
+        return self._reverse(L.RS_DDIM, model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                             cond_fn=cond_fn, model_kwargs=model_kwargs, eta=eta)
+
+    def ddim_reverse_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None, eta=0.0):
+        """Reference :653-689 (deterministic reverse ODE)."""
+        assert eta == 0.0, "Reverse ODE only for deterministic path"
+        return self._reverse(L.RS_DDIM_REVERSE, model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                             cond_fn=None, model_kwargs=model_kwargs)
+
+    def _loop(self, step, model, shape, noise, device, progress, **kw):
+        if device is None:
+            device = next(model.parameters()).device
+        assert isinstance(shape, (tuple, list))
+        img = noise if noise is not None else th.randn(*shape, device=device)
+        indices = list(range(self.num_timesteps))[::-1]
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(indices)
+        for i in indices:
+            t = th.full((shape[0],), i, dtype=th.int64, device=device)
+            with th.no_grad():
+                out = step(model, img, t, **kw)
+                yield out
+                img = out["sample"]
+
+    def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                                  model_kwargs=None, device=None, progress=False):
+        """Reference :555-601."""
+        yield from self._loop(self.p_sample, model, shape, noise, device, progress, clip_denoised=clip_denoised,
+                              denoised_fn=denoised_fn, cond_fn=cond_fn, model_kwargs=model_kwargs)
+
+    def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                      model_kwargs=None, device=None, progress=False):
+        """Reference :508-553."""
+        final = None
+        for final in self.p_sample_loop_progressive(model, shape, noise, clip_denoised, denoised_fn, cond_fn,
+                                                    model_kwargs, device, progress):
+            pass
+        return final["sample"]
+
+    def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
+                                     cond_fn=None, model_kwargs=None, device=None, progress=False, eta=0.0):
+        """Reference :725-774."""
+        yield from self._loop(self.ddim_sample, model, shape, noise, device, progress, clip_denoised=clip_denoised,
+                              denoised_fn=denoised_fn, cond_fn=cond_fn, model_kwargs=model_kwargs, eta=eta)
+
+    def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                         model_kwargs=None, device=None, progress=False, eta=0.0):
+        """Reference :691-723."""
+        final = None
+        for final in self.ddim_sample_loop_progressive(model, shape, noise, clip_denoised, denoised_fn, cond_fn,
+                                                       model_kwargs, device, progress, eta):
+            pass
+        return final["sample"]
+
+
 class FlowMatching:
     """Flow-matching objective (reference :1151-1340): continuous t in (0,1), analytic interpolant; same K1/K2 with
     per-sample coefficient arrays instead of per-timestep tables."""
