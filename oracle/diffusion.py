@@ -325,3 +325,40 @@ def cfg_combine(cond, uncond, scale, is_bf16=False):
     d = rb((cond - uncond).astype(f))
     m = rb((f(scale) * d).astype(f))
     return rb((uncond + m).astype(f))
+
+
+# ---- respacing (tools/respace.py:9-115) -----------------------------------------------------------------------------
+def space_timesteps(num_timesteps, section_counts):
+    """:9-62 -> sorted list of the kept base timesteps."""
+    if isinstance(section_counts, str):
+        if section_counts.startswith("ddim"):
+            n = int(section_counts[4:])
+            for i in range(1, num_timesteps):
+                if len(range(0, num_timesteps, i)) == n:
+                    return sorted(range(0, num_timesteps, i))
+            raise ValueError("no integer stride gives that many steps")
+        section_counts = [int(x) for x in section_counts.split(",")]
+    per, extra = num_timesteps // len(section_counts), num_timesteps % len(section_counts)
+    start, steps = 0, []
+    for i, c in enumerate(section_counts):
+        size = per + (1 if i < extra else 0)
+        if size < c:
+            raise ValueError("section too small")
+        frac = 1 if c <= 1 else (size - 1) / (c - 1)
+        cur = 0.0
+        for _ in range(c):
+            steps.append(start + round(cur))
+            cur += frac
+        start += size
+    return sorted(set(steps))
+
+
+def spaced_betas(betas, kept):
+    """:72-84: betas of the process restricted to `kept`, so that its alphas_cumprod equals the base one there."""
+    ac = np.cumprod(1.0 - np.asarray(betas, dtype=np.float64))
+    last, out = 1.0, []
+    for i, a in enumerate(ac):
+        if i in set(kept):
+            out.append(1 - a / last)
+            last = a
+    return np.array(out)

@@ -258,6 +258,10 @@ REVERSE_CASES = [  # (mean type, variance type, model-output dtype, clip_denoise
 ]
 
 
+RESPACE_CASES = [(1000, "ddim10"), (1000, "ddim50"), (1000, "ddim250"), (300, "10,15,20"), (1000, [1000]),
+                 (1000, "250"), (100, "3,1,7"), (1000, [1, 1, 1]), (999, "37,2")]
+
+
 def reverse_golden():
     import tools.sampler as rsm   # noqa: E402  (reference)
     out = {}
@@ -314,6 +318,20 @@ def reverse_golden():
         out[f"cfg_in::{name}"] = cfg(x[:3], torch.tensor([300.0] * 3), y=y).float().numpy()
         out[f"cfg_out::{name}"] = cfg(x[:3], torch.tensor([800.0] * 3), y=y).float().numpy()
     out["cfg_both"] = both.numpy()
+    # respacing (tools/respace.py): kept timesteps, rebuilt betas, and what the wrapped model is handed
+    import tools.respace as rrp   # noqa: E402  (reference)
+    for n, spec in RESPACE_CASES:
+        out[f"space::{n}::{spec}"] = np.array(sorted(rrp.space_timesteps(n, spec)))
+    for spec in ("ddim10", "ddim50", "10,15,20"):
+        sd = rrp.SpacedDiffusion(use_timesteps=rrp.space_timesteps(1000, spec), args=ref_args(),
+                                 betas=rgd.get_named_beta_schedule("cosine", 1000),
+                                 model_mean_type=rgd.ModelMeanType.EPSILON, model_var_type=rgd.ModelVarType.FIXED_LARGE,
+                                 loss_type=rgd.LossType.MSE, rescale_timesteps=True, device="cpu")
+        out[f"spaced_betas::{spec}"] = sd.betas
+        out[f"spaced_map::{spec}"] = np.array(sd.timestep_map)
+        seen = []
+        sd.p_mean_variance(lambda xx, ts, **k: (seen.append(ts.clone()), xx)[1], x, torch.tensor([0, 1, 2, 3, 5, 9]))
+        out[f"spaced_model_t::{spec}"] = seen[0].numpy()
     out["cfg_labels_seen"] = np.array(calls[0][1])
     np.savez_compressed(os.path.join(HERE, "reverse_golden.npz"), **out)
     print("reverse_golden.npz", len(out), "arrays")

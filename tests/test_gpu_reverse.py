@@ -190,3 +190,50 @@ def test_interval_cfg_matches_reference_fixture(dt):
                                                      torch.zeros(64, device=dev), y=torch.zeros(64, dtype=torch.long, device=dev))
     h = big.float().cpu().numpy()
     close(g, odiff.cfg_combine(h[:64], h[64:], 1.7, dt == "bf16"))
+
+
+def test_dit_guided_ddim_chain_vs_oracle():
+    """The reverse path end to end, as tools/sampler.py:112-141 drives it: eval-mode DiT -> IntervalCFG (doubled batch)
+    -> SpacedDiffusion("ddim10").ddim_sample_loop.  Every step of the chain is checked (teacher-forced on the chain's
+    own x_t) against the oracle: oracle DiT forward under bf16 autocast, oracle guidance combine, oracle DDIM step.
+    bf16 denoiser -> 2e-2 rel-L2 per step."""
+    from gpu_util import dezero, relerr
+    from oracle.dit import dit_forward
+    from vaw_b200.models.dit import DiT
+    from vaw_b200.tools import gaussian_diffusion as gd
+    from vaw_b200.tools.respace import SpacedDiffusion, space_timesteps
+    from vaw_b200.tools.sampler import IntervalCFG
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(5)
+    m = DiT(image_size=16, patch_size=2, in_channels=4, hidden_size=128, depth=2, num_heads=2,
+            class_dropout_prob=0.1, num_classes=10).to(dev)
+    dezero(m)
+    m.eval()
+    d = SpacedDiffusion(use_timesteps=space_timesteps(1000, "ddim10"), args=gd.default_args(),
+                        betas=gd.get_named_beta_schedule("cosine", 1000), model_mean_type=gd.ModelMeanType.EPSILON,
+                        model_var_type=gd.ModelVarType.FIXED_LARGE, loss_type=gd.LossType.MSE, rescale_timesteps=True)
+    scale = 1.5
+    cfg = IntervalCFG(m, 10, scale).eval()
+    B = 4
+    y = torch.tensor([1, 7, 3, 9], device=dev)
+    x = torch.randn(B, 4, 16, 16, device=dev)
+    tb = odiff.tables(odiff.spaced_betas(odiff.named_beta_schedule("cosine", 1000), d.timestep_map))
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    steps = list(d.ddim_sample_loop_progressive(cfg, (B, 4, 16, 16), noise=x, model_kwargs={"y": y}))
+    assert len(steps) == 10
+    cur = x
+    for i, out in zip(reversed(range(10)), steps):
+        t_model = torch.full((2 * B,), float(d.timestep_map[i]), device=dev)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            both, _ = dit_forward(sd, torch.cat([cur, cur]), t_model, torch.cat([y, torch.full_like(y, 10)]),
+                                  patch_size=2, num_heads=2, depth=2)
+        both = both.bfloat16().float().cpu().numpy()
+        guided = odiff.cfg_combine(both[:B], both[B:], scale, True)
+        want = odiff.ddim_sample(tb, "EPSILON", "FIXED_LARGE", guided, cur.cpu().numpy(), np.full(B, i),
+                                 np.zeros((B, 4, 16, 16), np.float32), 0.0, True, True)
+        assert relerr(out["sample"], torch.from_numpy(want["sample"]).to(dev)) < 2e-2, i
+        # x0 = r x_t - rm1 eps: the denoiser's bf16 error reaches the x0 prediction multiplied by rm1
+        rm1 = float(tb["sqrt_recipm1_alphas_cumprod"][i])
+        assert relerr(out["pred_xstart"], torch.from_numpy(want["pred_xstart"]).to(dev)) < 2e-2 * (1 + rm1), i
+        cur = out["sample"]
+    assert torch.isfinite(cur).all() and cur.abs().max().item() <= 1.0 + 1e-6   # t = 0: the clipped x0 prediction
