@@ -237,3 +237,19 @@ def test_dit_guided_ddim_chain_vs_oracle():
         assert relerr(out["pred_xstart"], torch.from_numpy(want["pred_xstart"]).to(dev)) < 2e-2 * (1 + rm1), i
         cur = out["sample"]
     assert torch.isfinite(cur).all() and cur.abs().max().item() <= 1.0 + 1e-6   # t = 0: the clipped x0 prediction
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_cfg_combine_ragged_sizes(dt):
+    """Odd element counts take the scalar kernel; results must not depend on the path."""
+    from vaw_b200.tools.sampler import IntervalCFG
+    dev = torch.device("cuda", 0)
+    for shape in ((3, 3, 5, 7), (1, 1, 1, 1), (2, 4, 6, 6)):
+        torch.manual_seed(sum(shape))
+        both = torch.randn(2 * shape[0], *shape[1:], device=dev)
+        both = both.bfloat16() if dt == "bf16" else both
+        n = shape[0]
+        g = IntervalCFG(lambda a, b, **k: both, 10, 3.25)(torch.zeros(shape, device=dev), torch.zeros(n, device=dev),
+                                                          y=torch.zeros(n, dtype=torch.long, device=dev))
+        h = both.float().cpu().numpy()
+        close(g, odiff.cfg_combine(h[:n], h[n:], 3.25, dt == "bf16"))

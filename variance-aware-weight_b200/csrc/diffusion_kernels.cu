@@ -241,7 +241,7 @@ struct StepCoef {
   float lv, maxlog, var;
   float recip, recipm1;
   float k_xs, k_eps, sig;  // DDIM: sample = k_xs * xs + k_eps * eps + sig * noise
-  float mask;
+  float mask, fixed_scale;
 };
 
 __device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
@@ -262,6 +262,7 @@ __device__ __forceinline__ StepCoef load_step_coef(const float* __restrict__ tab
   c.maxlog = row(RT_MAX_LOG);
   c.var = row(RT_VARIANCE);
   c.mask = tt != 0 ? 1.f : 0.f;
+  c.fixed_scale = mode == RS_DDPM ? expf(__fmul_rn(0.5f, c.lv)) : 0.f;  // fixed variance types: exp(0.5 logvar[t])
   c.k_xs = c.k_eps = c.sig = 0.f;
   if (mode == RS_DDIM) {
     const float ab = row(RT_AC), abp = row(RT_AC_PREV);
@@ -313,7 +314,7 @@ __device__ __forceinline__ StepOut step_elem(const StepCoef& c, float o, float v
   } else {
     r.lv = c.lv;
     r.var = c.var;
-    half_lv_exp = expf(__fmul_rn(0.5f, c.lv));
+    half_lv_exp = c.fixed_scale;
   }
   if (mode == RS_DDPM) {
     r.sample = __fadd_rn(r.mean, __fmul_rn(__fmul_rn(c.mask, half_lv_exp), z));
@@ -329,66 +330,106 @@ __device__ __forceinline__ StepOut step_elem(const StepCoef& c, float o, float v
 
 struct StepPtrs { float *sample, *xs, *mean, *lv, *var; };
 
-template <typename OutT, bool VEC>
-__global__ void __launch_bounds__(256)
-reverse_step_kernel(const OutT* __restrict__ out, long long out_stride, const float* __restrict__ x,
-                    const float* __restrict__ noise, const long long* __restrict__ t, const float* __restrict__ tab,
-                    int T, StepPtrs dst, int mean_type, int var_type, int mode, float eta, int clip, long long N,
-                    long long chw) {
+// Vector path.  The kernel is instruction-issue-bound if every thread re-derives the per-sample coefficients (14
+// table gathers behind a dependent t[n] load and, for DDIM, five IEEE sqrt/div: ~390 warp instructions per float4,
+// ncu in profiles/r01m_k8_reverse_step.txt), so each CTA owns a CONTIGUOUS run of 256-float4 tiles, derives the
+// coefficients of the few samples that run touches once (one thread per sample, in parallel) into shared memory,
+// and then streams its tiles with nothing but the element math in the loop.
+constexpr int RS_MAX_SAMPLES = 128;  // samples one CTA's run may touch (host sizes the grid accordingly)
+
+template <typename OutT, int MODE>
+__global__ void __launch_bounds__(256, 4)
+reverse_step_tile_kernel(const OutT* __restrict__ out, long long out_stride, const float* __restrict__ x,
+                         const float* __restrict__ noise, const long long* __restrict__ t,
+                         const float* __restrict__ tab, int T, StepPtrs dst, int mean_type, int var_type, float eta,
+                         int clip, long long N, long long chw, long long tiles_per_sample, long long tiles_per_cta) {
   constexpr bool BF = !std::is_same<OutT, float>::value;
+  __shared__ StepCoef sc[RS_MAX_SAMPLES];
   const bool learned = var_type == VT_LEARNED || var_type == VT_LEARNED_RANGE;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  if (VEC) {
-    const long long chw4 = chw >> 2, total4 = N * chw4, os4 = out_stride >> 2;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
-      const long long n = i / chw4, r = i - n * chw4;
-      const StepCoef c = load_step_coef(tab, T, t[n], mean_type, mode, eta);
+  const long long chw4 = chw >> 2, os4 = out_stride >> 2, tiles = N * tiles_per_sample;
+  const long long t0 = (long long)blockIdx.x * tiles_per_cta;
+  const long long t1 = t0 + tiles_per_cta < tiles ? t0 + tiles_per_cta : tiles;
+  if (t0 >= t1) return;
+  const long long n0 = t0 / tiles_per_sample, n1 = (t1 - 1) / tiles_per_sample;
+  for (long long s = threadIdx.x; s <= n1 - n0; s += blockDim.x)
+    sc[s] = load_step_coef(tab, T, t[n0 + s], mean_type, MODE, eta);
+  __syncthreads();
+  long long n = n0, k = t0 - n0 * tiles_per_sample;  // tile = n * tiles_per_sample + k
+#pragma unroll 2
+  for (long long tile = t0; tile < t1; ++tile) {
+    const long long r = k * 256 + threadIdx.x;
+    if (r < chw4) {
+      const long long i = n * chw4 + r;
       const float4 o = Vec4<OutT>::load(out, n * os4 + r);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f), z = v;
       if (learned) v = Vec4<OutT>::load(out, n * os4 + chw4 + r);
       const float4 xv = ldg_stream_f4(reinterpret_cast<const float4*>(x) + i);
       if (noise) z = ldg_stream_f4(reinterpret_cast<const float4*>(noise) + i);
-      const StepOut a = step_elem<BF>(c, o.x, v.x, xv.x, z.x, mean_type, var_type, mode, clip != 0);
-      const StepOut b = step_elem<BF>(c, o.y, v.y, xv.y, z.y, mean_type, var_type, mode, clip != 0);
-      const StepOut d = step_elem<BF>(c, o.z, v.z, xv.z, z.z, mean_type, var_type, mode, clip != 0);
-      const StepOut e = step_elem<BF>(c, o.w, v.w, xv.w, z.w, mean_type, var_type, mode, clip != 0);
+      const StepCoef& c = sc[n - n0];
+      const StepOut a = step_elem<BF>(c, o.x, v.x, xv.x, z.x, mean_type, var_type, MODE, clip != 0);
+      const StepOut b = step_elem<BF>(c, o.y, v.y, xv.y, z.y, mean_type, var_type, MODE, clip != 0);
+      const StepOut d = step_elem<BF>(c, o.z, v.z, xv.z, z.z, mean_type, var_type, MODE, clip != 0);
+      const StepOut e = step_elem<BF>(c, o.w, v.w, xv.w, z.w, mean_type, var_type, MODE, clip != 0);
       if (dst.sample) stg_stream_f4(reinterpret_cast<float4*>(dst.sample) + i, make_float4(a.sample, b.sample, d.sample, e.sample));
       if (dst.xs) stg_stream_f4(reinterpret_cast<float4*>(dst.xs) + i, make_float4(a.xs, b.xs, d.xs, e.xs));
       if (dst.mean) stg_stream_f4(reinterpret_cast<float4*>(dst.mean) + i, make_float4(a.mean, b.mean, d.mean, e.mean));
       if (dst.lv) stg_stream_f4(reinterpret_cast<float4*>(dst.lv) + i, make_float4(a.lv, b.lv, d.lv, e.lv));
       if (dst.var) stg_stream_f4(reinterpret_cast<float4*>(dst.var) + i, make_float4(a.var, b.var, d.var, e.var));
     }
-  } else {
-    const long long total = N * chw;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-      const long long n = i / chw, r = i - n * chw;
-      const StepCoef c = load_step_coef(tab, T, t[n], mean_type, mode, eta);
-      const float o = (float)out[n * out_stride + r];
-      const float v = learned ? (float)out[n * out_stride + chw + r] : 0.f;
-      const StepOut a = step_elem<BF>(c, o, v, x[i], noise ? noise[i] : 0.f, mean_type, var_type, mode, clip != 0);
-      if (dst.sample) dst.sample[i] = a.sample;
-      if (dst.xs) dst.xs[i] = a.xs;
-      if (dst.mean) dst.mean[i] = a.mean;
-      if (dst.lv) dst.lv[i] = a.lv;
-      if (dst.var) dst.var[i] = a.var;
-    }
+    if (++k == tiles_per_sample) { k = 0; ++n; }
+  }
+}
+
+// Scalar path (chw not a multiple of 4, or unaligned views).
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+reverse_step_scalar_kernel(const OutT* __restrict__ out, long long out_stride, const float* __restrict__ x,
+                           const float* __restrict__ noise, const long long* __restrict__ t,
+                           const float* __restrict__ tab, int T, StepPtrs dst, int mean_type, int var_type, int mode,
+                           float eta, int clip, long long N, long long chw) {
+  constexpr bool BF = !std::is_same<OutT, float>::value;
+  const bool learned = var_type == VT_LEARNED || var_type == VT_LEARNED_RANGE;
+  const long long stride = (long long)gridDim.x * blockDim.x, total = N * chw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long n = i / chw, r = i - n * chw;
+    const StepCoef c = load_step_coef(tab, T, t[n], mean_type, mode, eta);
+    const float o = (float)out[n * out_stride + r];
+    const float v = learned ? (float)out[n * out_stride + chw + r] : 0.f;
+    const StepOut a = step_elem<BF>(c, o, v, x[i], noise ? noise[i] : 0.f, mean_type, var_type, mode, clip != 0);
+    if (dst.sample) dst.sample[i] = a.sample;
+    if (dst.xs) dst.xs[i] = a.xs;
+    if (dst.mean) dst.mean[i] = a.mean;
+    if (dst.lv) dst.lv[i] = a.lv;
+    if (dst.var) dst.var[i] = a.var;
   }
 }
 
 // IntervalCFG combine (tools/sampler.py:46-48): uncond + scale * (cond - uncond) on the two halves of a doubled
 // batch, each op rounded in the tensor's own dtype as the eager expression does.
-template <typename T>
+template <bool BF>
+__device__ __forceinline__ float cfg_elem(float c, float u, float scale) {
+  float d = __fsub_rn(c, u);
+  if (BF) d = bf16r(d);
+  float m = __fmul_rn(scale, d);
+  if (BF) m = bf16r(m);
+  return __fadd_rn(u, m);  // the store rounds to the tensor dtype
+}
+
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
 cfg_combine_kernel(const T* __restrict__ both, T* __restrict__ y, float scale, long long half) {
   constexpr bool BF = !std::is_same<T, float>::value;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
-    const float c = (float)both[i], u = (float)both[half + i];
-    float d = __fsub_rn(c, u);
-    if (BF) d = bf16r(d);
-    float m = __fmul_rn(scale, d);
-    if (BF) m = bf16r(m);
-    y[i] = (T)__fadd_rn(u, m);
+  if (VEC) {
+    const long long half4 = half >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < half4; i += stride) {
+      const float4 c = Vec4<T>::load(both, i), u = Vec4<T>::load(both, half4 + i);
+      Vec4<T>::store(y, i, make_float4(cfg_elem<BF>(c.x, u.x, scale), cfg_elem<BF>(c.y, u.y, scale),
+                                       cfg_elem<BF>(c.z, u.z, scale), cfg_elem<BF>(c.w, u.w, scale)));
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride)
+      y[i] = (T)cfg_elem<BF>((float)both[i], (float)both[half + i], scale);
   }
 }
 
@@ -433,18 +474,38 @@ extern "C" int vaw_reverse_step(const void* model_out, int out_dtype, long long 
   const uintptr_t al = (uintptr_t)model_out | (uintptr_t)x | (uintptr_t)noise | (uintptr_t)sample |
                        (uintptr_t)pred_xstart | (uintptr_t)mean | (uintptr_t)log_variance | (uintptr_t)variance;
   const bool vec = (chw % 4 == 0) && ((al & 15) == 0);
-  const long long work = vec ? N * (chw / 4) : N * chw;
-  long long blocks = (work + 255) / 256;
-  const long long cap = (long long)vaw_num_sms() * 16;
-  if (blocks > cap) blocks = cap;
   const StepPtrs dst{sample, pred_xstart, mean, log_variance, variance};
-#define VAW_RS_LAUNCH(TY, V)                                                                                     \
-  reverse_step_kernel<TY, V><<<(unsigned)blocks, 256, 0, stream>>>((const TY*)model_out, out_stride, x, noise, t, \
-                                                                   tab, T, dst, mean_type, var_type, mode, eta,  \
-                                                                   clip, N, chw)
-  if (out_dtype == 0) { if (vec) VAW_RS_LAUNCH(float, true); else VAW_RS_LAUNCH(float, false); }
-  else { if (vec) VAW_RS_LAUNCH(bf16, true); else VAW_RS_LAUNCH(bf16, false); }
+  const long long cap = (long long)vaw_num_sms() * 8;
+  if (vec) {
+    const long long tps = (chw / 4 + 255) / 256, tiles = N * tps;
+    long long blocks = tiles < cap ? tiles : cap;
+    const long long min_blocks = (N + RS_MAX_SAMPLES - 3) / (RS_MAX_SAMPLES - 2);  // a run spans <= per/tps + 2 samples
+    if (blocks < min_blocks) blocks = min_blocks;
+    const long long per = (tiles + blocks - 1) / blocks;
+    blocks = (tiles + per - 1) / per;
+#define VAW_RS_LAUNCH(TY, MD)                                                                                  \
+  reverse_step_tile_kernel<TY, MD><<<(unsigned)blocks, 256, 0, stream>>>(                                      \
+      (const TY*)model_out, out_stride, x, noise, t, tab, T, dst, mean_type, var_type, eta, clip, N, chw, tps, per)
+#define VAW_RS_PICK(TY)                                                \
+  do {                                                                 \
+    if (mode == RS_DDPM) VAW_RS_LAUNCH(TY, RS_DDPM);                   \
+    else if (mode == RS_DDIM) VAW_RS_LAUNCH(TY, RS_DDIM);              \
+    else if (mode == RS_DDIM_REVERSE) VAW_RS_LAUNCH(TY, RS_DDIM_REVERSE); \
+    else VAW_RS_LAUNCH(TY, RS_MOMENTS);                                \
+  } while (0)
+    if (out_dtype == 0) VAW_RS_PICK(float); else VAW_RS_PICK(bf16);
+#undef VAW_RS_PICK
 #undef VAW_RS_LAUNCH
+  } else {
+    long long blocks = (N * chw + 255) / 256;
+    if (blocks > 2 * cap) blocks = 2 * cap;
+#define VAW_RS_LAUNCH(TY)                                                                                           \
+  reverse_step_scalar_kernel<TY><<<(unsigned)blocks, 256, 0, stream>>>((const TY*)model_out, out_stride, x, noise, t, \
+                                                                       tab, T, dst, mean_type, var_type, mode, eta,  \
+                                                                       clip, N, chw)
+    if (out_dtype == 0) VAW_RS_LAUNCH(float); else VAW_RS_LAUNCH(bf16);
+#undef VAW_RS_LAUNCH
+  }
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }
@@ -454,13 +515,18 @@ extern "C" int vaw_cfg_combine(const void* both, void* y, int dtype, float scale
   VAW_CHECK_ARG(both && y && half >= 0, "vaw_cfg_combine: bad arguments");
   VAW_CHECK_ARG(dtype == 0 || dtype == 1, "vaw_cfg_combine: dtype must be 0 (f32) or 1 (bf16)");
   if (half == 0) return VAW_OK;
-  long long blocks = (half + 255) / 256;
+  const bool vec = (half % 4 == 0) && ((((uintptr_t)both | (uintptr_t)y) & 15) == 0) &&
+                   ((half * (dtype == 0 ? 4 : 2)) % 16 == 0);
+  long long blocks = ((vec ? half / 4 : half) + 255) / 256;
   const long long cap = (long long)vaw_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  if (dtype == 0)
-    cfg_combine_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>((const float*)both, (float*)y, scale, half);
-  else
-    cfg_combine_kernel<bf16><<<(unsigned)blocks, 256, 0, stream>>>((const bf16*)both, (bf16*)y, scale, half);
+  if (dtype == 0) {
+    if (vec) cfg_combine_kernel<float, true><<<(unsigned)blocks, 256, 0, stream>>>((const float*)both, (float*)y, scale, half);
+    else cfg_combine_kernel<float, false><<<(unsigned)blocks, 256, 0, stream>>>((const float*)both, (float*)y, scale, half);
+  } else {
+    if (vec) cfg_combine_kernel<bf16, true><<<(unsigned)blocks, 256, 0, stream>>>((const bf16*)both, (bf16*)y, scale, half);
+    else cfg_combine_kernel<bf16, false><<<(unsigned)blocks, 256, 0, stream>>>((const bf16*)both, (bf16*)y, scale, half);
+  }
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }
