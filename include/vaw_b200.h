@@ -225,6 +225,15 @@ int vaw_colsum_f32_small(const float* a, long long lda, int rows, int N, float* 
 
 /* ---- embedders, (un)patchify, casts (models/dit.py:41-110,243-256; timm PatchEmbed; models/uvit.py:21-52) ---------- */
 int vaw_patchify_in(const float* x, void* patches, int B, int C, int H, int W, int P, vaw_stream_t stream);
+/* REPA teacher input: preprocess_raw_image (tools/align_utils.py:19-40, the mocov3 / mae / dinov1 branch:
+ * x / 255 then torchvision Normalize(mean, std)) fused into the patchify; raw pixels fp32 [B, C, H, W] -> bf16 patches
+ * [B*T, C*P*P] in Conv2d-weight order.  vaw_vit_assemble builds the ViT residual stream of
+ * encoders/mocov3_vit.py:99-106 (timm VisionTransformer._pos_embed): row 0 of every sample = cls + pos[0], rows 1..L =
+ * the patch tokens [B*L, D] (bias and pos[1..] already added by the patch-embed GEMM's residual-table epilogue). */
+int vaw_patchify_norm(const float* x, const float* mean, const float* stdv, void* patches, int B, int C, int H, int W,
+                      int P, vaw_stream_t stream);
+int vaw_vit_assemble(const float* tok, const float* cls, const float* pos0, float* x, int B, int L, int D,
+                     vaw_stream_t stream);
 int vaw_unpatchify(void* tokens, void* image, int dtype, int B, int C, int H, int W, int P, int to_image,
                    vaw_stream_t stream);
 int vaw_timestep_embedding(const float* t, void* out_bf16, float* out_f32, int B, int dim, vaw_stream_t stream);

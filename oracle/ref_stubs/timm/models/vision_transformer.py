@@ -1,4 +1,5 @@
-"""Restatement of the three timm 0.9.x modules DiT uses (semantics per SURVEY.md §A.3)."""
+"""Restatement of the timm 0.9.x modules the reference imports (semantics per SURVEY.md §A.3): the three DiT uses and the
+VisionTransformer base class of encoders/mocov3_vit.py."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -64,9 +65,50 @@ class Mlp(nn.Module):
         return self.drop2(self.fc2(self.norm(self.drop1(self.act(self.fc1(x))))))
 
 
+class Block(nn.Module):
+    """timm 0.9.x vision_transformer.Block without LayerScale / DropPath (both identity at their defaults)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4., qkv_bias=False, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias)
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=nn.GELU)
+
+    def forward(self, x):
+        x = x + self.attn(self.norm1(x))
+        return x + self.mlp(self.norm2(x))
+
+
 class VisionTransformer(nn.Module):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("timm stub")
+    """Restatement of timm 0.9.x VisionTransformer at the defaults the reference's encoders use (class token, no
+    pre-norm, no patch dropout, global_pool irrelevant for forward_features)."""
+
+    def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12, num_heads=12,
+                 mlp_ratio=4., qkv_bias=True, norm_layer=None, **unused):
+        super().__init__()
+        norm_layer = norm_layer or (lambda d: nn.LayerNorm(d, eps=1e-6))
+        self.embed_dim = embed_dim
+        self.patch_embed = PatchEmbed(img_size, patch_size, in_chans, embed_dim)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.randn(1, self.patch_embed.num_patches + 1, embed_dim) * .02)
+        self.patch_drop = nn.Identity()
+        self.norm_pre = nn.Identity()
+        self.blocks = nn.Sequential(*[Block(embed_dim, num_heads, mlp_ratio, qkv_bias, norm_layer) for _ in range(depth)])
+        self.norm = norm_layer(embed_dim)
+        self.head = nn.Linear(embed_dim, num_classes) if num_classes > 0 else nn.Identity()
+
+    def _pos_embed(self, x):
+        x = torch.cat((self.cls_token.expand(x.shape[0], -1, -1), x), dim=1)
+        return x + self.pos_embed
+
+    def forward_features(self, x):
+        x = self.patch_embed(x)
+        x = self._pos_embed(x)
+        x = self.patch_drop(x)
+        x = self.norm_pre(x)
+        x = self.blocks(x)
+        return self.norm(x)
 
 
 def _cfg(**kwargs):

@@ -13,6 +13,7 @@ installed; see oracle/ref_stubs/README.md).  Everything written here is an input
     unet_shapes.json       state-dict names and shapes of every UNet factory (built on the meta device)
     reverse_golden.npz     p_mean_variance / p_sample / ddim_sample / ddim_reverse_sample over every mean / variance type
                            (fp32 and bf16 model outputs, pinned noise), IntervalCFG combine
+    vit_golden.npz         the MoCo-v3 ViT teacher (tiny), preprocess_raw_image, ViT-B/16 position embedding and names
     dit_golden.npz         a tiny DiT (with REPA projector): weights, forward outputs, full training_losses + grads
 """
 import os
@@ -337,7 +338,40 @@ def reverse_golden():
     print("reverse_golden.npz", len(out), "arrays")
 
 
+def vit_golden():
+    """The reference's VisionTransformerMoCo (encoders/mocov3_vit.py) + preprocess_raw_image (tools/align_utils.py) on a
+    tiny configuration.  timm's VisionTransformer base is the restatement in oracle/ref_stubs (timm is not installed),
+    so this pins the MoCo-specific parts: position embedding, parameter names, preprocessing, cls-token drop."""
+    from functools import partial
+    import encoders.mocov3_vit as rvit      # noqa: E402  (reference)
+    import tools.align_utils as rau         # noqa: E402  (reference)
+    torch.manual_seed(6)
+    m = rvit.VisionTransformerMoCo(img_size=32, patch_size=8, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4,
+                                   qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=0)
+    pos = m.pos_embed.detach().clone()
+    fill_by_name(m)                      # name-keyed deterministic weights (tests refill their own model) ...
+    with torch.no_grad():
+        m.pos_embed.copy_(pos)           # ... except the fixed sin-cos table, which is the reference's own
+    m.eval()
+    g = torch.Generator().manual_seed(14)
+    raw = torch.randint(0, 256, (3, 3, 32, 32), generator=g).float()
+    out = {"pos_embed": pos.numpy(), "names": np.array(sorted(k for k in m.state_dict() if not k.startswith("head")))}
+    out["raw"] = raw.numpy()
+    out["pre"] = rau.preprocess_raw_image(raw, "mocov3-vit-b").numpy()
+    with torch.no_grad():
+        out["features"] = m.forward_features(torch.from_numpy(out["pre"]))[:, 1:].numpy()
+    big = rvit.vit_base(num_classes=0)
+    out["pos_embed_base_sub"] = big.pos_embed.detach().numpy().astype(np.float32)[:, ::8, ::16]
+    out["base_names"] = np.array(sorted(k for k in big.state_dict() if not k.startswith("head")))
+    out["base_shapes"] = np.array([str(tuple(big.state_dict()[k].shape)) for k in out["base_names"]])
+    np.savez_compressed(os.path.join(HERE, "vit_golden.npz"), **out)
+    print("vit_golden.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "vit":
+        vit_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "reverse":
         reverse_golden()
         sys.exit(0)
@@ -352,4 +386,5 @@ if __name__ == "__main__":
     diffusion_golden()
     sampler_golden()
     reverse_golden()
+    vit_golden()
     dit_golden()

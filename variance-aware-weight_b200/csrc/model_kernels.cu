@@ -20,6 +20,39 @@ patchify_in_kernel(const float* __restrict__ x, bf16* __restrict__ patches, int 
   }
 }
 
+// REPA teacher input: preprocess_raw_image (tools/align_utils.py:19-40, mocov3 / mae / dinov1 branch)
+// fused into the patchify: raw pixels 0..255 fp32 [B, C, H, W] -> ((x / 255) - mean[c]) / std[c] (each op rounded like
+// the eager sequence x / 255., Normalize's sub_ and div_) -> bf16 patches [B*T, C*P*P] in Conv2d weight order.
+__global__ void __launch_bounds__(256)
+patchify_norm_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ stdv,
+                     bf16* __restrict__ patches, int B, int C, int H, int W, int P) {
+  const int Wg = W / P, Hg = H / P, Kp = C * P * P;
+  const long long total = (long long)B * Hg * Wg * Kp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % Kp);
+    const long long tok = i / Kp;
+    const int w = (int)(tok % Wg), h = (int)((tok / Wg) % Hg), n = (int)(tok / ((long long)Wg * Hg));
+    const int q = f % P, p = (f / P) % P, c = f / (P * P);
+    const float v = x[(((long long)n * C + c) * H + h * P + p) * W + w * P + q];
+    patches[i] = __float2bfloat16_rn(__fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.f), __ldg(mean + c)), __ldg(stdv + c)));
+  }
+}
+
+// ViT token assembly (timm VisionTransformer._pos_embed): x[n, 0, :] = cls + pos[0], x[n, 1 + l, :] = tok[n, l, :]
+// (the patch-embed GEMM has already added bias and pos[1 + l] through its residual-table epilogue).
+__global__ void __launch_bounds__(256)
+vit_assemble_kernel(const float* __restrict__ tok, const float* __restrict__ cls, const float* __restrict__ pos0,
+                    float* __restrict__ x, int B, int L, int D) {
+  const long long total = (long long)B * (L + 1) * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const long long row = i / D;
+    const int l = (int)(row % (L + 1));
+    const long long n = row / (L + 1);
+    x[i] = l == 0 ? __fadd_rn(cls[d], pos0[d]) : tok[(n * L + (l - 1)) * D + d];
+  }
+}
+
 // tokens [B*T, P*P*C] (feature order (p, q, c)) <-> image [B, C, H, W]   (dit.py:243-256, uvit.py:47-52)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -285,6 +318,24 @@ inline unsigned grid_for(long long work, int per_block = 256) {
 extern "C" int vaw_patchify_in(const float* x, void* patches, int B, int C, int H, int W, int P, cudaStream_t stream) {
   VAW_CHECK_ARG(x && patches && B > 0 && C > 0 && P > 0 && H % P == 0 && W % P == 0, "vaw_patchify_in: bad arguments");
   patchify_in_kernel<<<grid_for((long long)B * C * H * W), 256, 0, stream>>>(x, (bf16*)patches, B, C, H, W, P);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+extern "C" int vaw_patchify_norm(const float* x, const float* mean, const float* stdv, void* patches, int B, int C,
+                                 int H, int W, int P, cudaStream_t stream) {
+  VAW_CHECK_ARG(x && mean && stdv && patches && B > 0 && C > 0 && P > 0 && H % P == 0 && W % P == 0,
+                "vaw_patchify_norm: bad arguments");
+  patchify_norm_kernel<<<grid_for((long long)B * C * H * W), 256, 0, stream>>>(x, mean, stdv, (bf16*)patches, B, C, H,
+                                                                               W, P);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+extern "C" int vaw_vit_assemble(const float* tok, const float* cls, const float* pos0, float* x, int B, int L, int D,
+                                cudaStream_t stream) {
+  VAW_CHECK_ARG(tok && cls && pos0 && x && B > 0 && L > 0 && D > 0, "vaw_vit_assemble: bad arguments");
+  vit_assemble_kernel<<<grid_for((long long)B * (L + 1) * D), 256, 0, stream>>>(tok, cls, pos0, x, B, L, D);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }
