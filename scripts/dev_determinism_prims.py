@@ -1,0 +1,92 @@
+"""Run-to-run determinism of the primitives at the shapes where the engines showed nondeterminism (DiT-XL B=64 forward,
+DiT-S B=256 backward): every call is repeated into NaN-prefilled outputs and compared bit-wise."""
+import os, sys, ctypes as C
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "variance-aware-weight_b200"), os.path.join(ROOT, "tests")]
+import torch
+from vaw_b200 import _lib as L
+from gpu_util import run_gemm
+L.register("vaw_attn_fwd", [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p])
+L.register("vaw_attn_bwd_ws", [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p])
+dev = "cuda"
+torch.manual_seed(0)
+def rep(name, fn, outs, n=4):
+    ref = None; bad = 0; where = ""
+    for r in range(n):
+        for o in outs: o.view(torch.int16 if o.element_size() == 2 else torch.int32).fill_(-1)
+        fn(); torch.cuda.synchronize()
+        cur = [o.clone() for o in outs]
+        if ref is None: ref = cur
+        else:
+            for a, b in zip(ref, cur):
+                ne = (a.view(torch.int16 if a.element_size() == 2 else torch.int32) != b.view(torch.int16 if b.element_size() == 2 else torch.int32))
+                if ne.any():
+                    bad += 1
+                    rows = ne.reshape(a.shape[0], -1).any(1).nonzero().flatten()
+                    where = f"rows {int(rows[0])}..{int(rows[-1])} ({len(rows)} rows), {int(ne.sum())} elements"
+    print(f"{'NONDETERMINISTIC' if bad else 'ok              '} {name} {where}", flush=True)
+def gemm_case(name, M, N, K, epi, a_mn=0, b_mn=0, rps=256, **kw):
+    A = (torch.randn(K, M, device=dev) if a_mn else torch.randn(M, K, device=dev)).bfloat16()
+    B = ((torch.randn(K, N, device=dev) if b_mn else torch.randn(N, K, device=dev)) * 0.05).bfloat16()
+    bias = torch.randn(N, device=dev)
+    o = torch.empty(M, N, device=dev, dtype=torch.bfloat16); o2b = torch.empty_like(o)
+    of = torch.empty(M, N, device=dev)
+    resid = torch.randn(M, N, device=dev); gate = torch.randn(max(M // rps, 1), N, device=dev)
+    aux = torch.randn(M, N, device=dev).bfloat16()
+    if epi == L.EPI_BF16: rep(name, lambda: run_gemm(A, B, a_mn, b_mn, M, N, K, epi, out=o, bias=bias, **kw), [o])
+    elif epi in (L.EPI_GELU_TANH, L.EPI_GELU_ERF): rep(name, lambda: run_gemm(A, B, a_mn, b_mn, M, N, K, epi, out=o, out2=o2b, bias=bias, **kw), [o, o2b])
+    elif epi == L.EPI_GATE_RES: rep(name, lambda: run_gemm(A, B, a_mn, b_mn, M, N, K, epi, out=o, out2=of, bias=bias, resid=resid, gate=gate, rows_per_sample=rps, **kw), [o, of])
+    elif epi == L.EPI_RES: rep(name, lambda: run_gemm(A, B, a_mn, b_mn, M, N, K, epi, out2=of, bias=bias, resid=resid, **kw), [of])
+    elif epi in (L.EPI_DGELU_TANH, L.EPI_DGELU_ERF): rep(name, lambda: run_gemm(A, B, a_mn, b_mn, M, N, K, epi, out=o, aux=aux, **kw), [o])
+    elif epi == L.EPI_F32:
+        ws = torch.empty(148 * 128 * 256, device=dev)
+        rep(name, lambda: run_gemm(A, B, a_mn, b_mn, M, N, K, epi, out=of, bias=None, k_splits=kw.get("k_splits", 0), split_ws=ws if kw.get("k_splits") else None), [of])
+def attn_case(name, B, H, T, hd, bwd):
+    qkv = torch.randn(B * T, 3 * H * hd, device=dev).bfloat16()
+    o = torch.empty(B * T, H * hd, device=dev, dtype=torch.bfloat16); lse = torch.empty(B * H * T, device=dev)
+    rep(name + " fwd", lambda: L.call("vaw_attn_fwd", qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, H, hd, L.stream_ptr()), [o, lse.view(-1, 1)])
+    if bwd:
+        L.call("vaw_attn_fwd", qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, H, hd, L.stream_ptr())
+        do = torch.randn_like(o); dqkv = torch.empty_like(qkv); delta = torch.empty(B * H * T, device=dev)
+        o2, lse2 = o.clone(), lse.clone()
+        rep(name + " bwd", lambda: L.call("vaw_attn_bwd_ws", qkv.data_ptr(), o2.data_ptr(), do.data_ptr(), lse2.data_ptr(), dqkv.data_ptr(), delta.data_ptr(), B, T, H, hd, L.stream_ptr()), [dqkv])
+which = sys.argv[1] if len(sys.argv) > 1 else "xl"
+if which == "xl":
+    M, D, Hd = 16384, 1152, 4608
+    gemm_case("patch-embed f32   K=16", M, D, 16, L.EPI_F32)
+    gemm_case("patch-embed res   K=16", M, D, 16, L.EPI_RES)
+    gemm_case("adaLN f32 M=64", 64, 28 * 6 * D, D, L.EPI_F32)
+    gemm_case("qkv bf16", M, 3 * D, D, L.EPI_BF16)
+    gemm_case("proj gate_res", M, D, D, L.EPI_GATE_RES)
+    gemm_case("fc1 gelu", M, Hd, D, L.EPI_GELU_TANH)
+    gemm_case("fc2 gate_res", M, D, Hd, L.EPI_GATE_RES)
+    gemm_case("final bf16 N=16", M, 16, D, L.EPI_BF16)
+    attn_case("attn B=64 H=16 hd=72", 64, 16, 256, 72, True)
+    gemm_case("fc2 dgrad dgelu", M, Hd, D, L.EPI_DGELU_TANH, b_mn=1)
+    gemm_case("fc1 dgrad bf16", M, D, Hd, L.EPI_BF16, b_mn=1)
+    gemm_case("wgrad fc1 tail-split", Hd, D, M, L.EPI_F32, a_mn=1, b_mn=1, k_splits=-1)
+else:
+    M, D, Hd = 65536, 384, 1536
+    gemm_case("final dgrad bf16 K=16", M, D, 16, L.EPI_BF16, b_mn=1)
+    gemm_case("fc2 dgrad dgelu", M, Hd, D, L.EPI_DGELU_TANH, b_mn=1)
+    gemm_case("fc1 dgrad bf16", M, D, Hd, L.EPI_BF16, b_mn=1)
+    gemm_case("proj dgrad bf16", M, D, D, L.EPI_BF16, b_mn=1)
+    gemm_case("qkv dgrad bf16", M, D, 3 * D, L.EPI_BF16, b_mn=1)
+    gemm_case("wgrad fc1 tail-split", Hd, D, M, L.EPI_F32, a_mn=1, b_mn=1, k_splits=-1)
+    gemm_case("wgrad qkv tail-split", 3 * D, D, M, L.EPI_F32, a_mn=1, b_mn=1, k_splits=-1)
+    gemm_case("wgrad final tail-split", 16, D, M, L.EPI_F32, a_mn=1, b_mn=1, k_splits=-1)
+    attn_case("attn B=256 H=6 hd=64", 256, 6, 256, 64, True)
+    gemm_case("fwd qkv bf16", M, 3 * D, D, L.EPI_BF16)
+    gemm_case("fwd fc1 gelu", M, Hd, D, L.EPI_GELU_TANH)
+if which == "cfg":
+    M, D = 65536, 384
+    for K in (16, 32, 64, 128):
+        for bmn in (1, 0):
+            for tn in (128, 192, 256):
+                for cg in (1, 2):
+                    gemm_case(f"bf16 M={M} N={D} K={K} b_mn={bmn} tile_n={tn} cta_group={cg}", M, D, K, L.EPI_BF16, b_mn=bmn, tile_n=tn, cta_group=cg)
+    M, D = 16384, 1152
+    for tn in (128, 192, 256):
+        for cg in (1, 2):
+            gemm_case(f"gate_res M={M} N={D} K={D} tile_n={tn} cta_group={cg}", M, D, D, L.EPI_GATE_RES, tile_n=tn, cta_group=cg)
+            gemm_case(f"res      M={M} N={D} K={D} tile_n={tn} cta_group={cg}", M, D, D, L.EPI_RES, tile_n=tn, cta_group=cg)

@@ -517,6 +517,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     float4* stg = reinterpret_cast<float4*>(smem + STAGES * C::kStageBytes + 256) + (warp - 2) * 256;
     int acc = 0;
     uint32_t acc_phase = 0, aux_phase = 0;
+    // staging slot of the alternating single-output TMA-store epilogue.  It lives across work items: `wait_group.read 1`
+    // only proves that the store issued two chunks ago is done with its slot, so a tile with an odd number of chunks
+    // per warp must be followed by a tile that starts on the OTHER slot (with a short K loop the next tile's first
+    // chunk otherwise overwrites a slot the store engine is still reading).
+    int slot = 0;
     // after the transpose this lane owns rows {4i + lane/8} (i = 0..7) and column group lane%8 of every chunk
     const int sub_r = lane >> 3, sub_c = lane & 7;
     for (int work = unit; work < num_work; work += num_units) {
@@ -554,7 +559,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // only 256-byte aligned, so the row's swizzle term comes from its address, not from its index.  Both slots are
         // 2048 B apart, i.e. share the term.
         const int sw = (int)(((smem_u32(stg_b) + (uint32_t)lane * 64u) >> 7) & 3u);   // 16-byte chunk c lives at c ^ sw
-        int slot = 0;
         // aux variant: slot 0 receives the aux tile (TMA load, per-warp mbarrier), slot 1 stages the output
         uint64_t* my_bar = &abar[warp - 2];
         auto aux_load = [&](int c) {   // lane 0
@@ -573,6 +577,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               const uint4 t = *reinterpret_cast<const uint4*>(a0 + ((k ^ sw) * 16));
               ax[4 * k] = t.x; ax[4 * k + 1] = t.y; ax[4 * k + 2] = t.z; ax[4 * k + 3] = t.w;
             }
+            fence_proxy_async_smem();   // order this lane's generic reads before the async-proxy (TMA) refill
             __syncwarp();   // every lane has its row: the next chunk's tile may overwrite the slot
             if (lane == 0 && c + kEpiParts < NCH) aux_load(c + kEpiParts);
           }
@@ -672,6 +677,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             float4 r[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) r[k] = *reinterpret_cast<const float4*>(stg_b + lane * 64 + ((k ^ sw) * 16));
+            fence_proxy_async_smem();   // order this lane's generic reads before the async-proxy (TMA) refill
             __syncwarp();   // slot 0 consumed: fetch the next residual tile (other half, or the next chunk's first half)
             if (lane == 0) {
               const int nc = hf == 0 ? c : c + kEpiParts;
