@@ -1,7 +1,6 @@
 """GPU tier: the frozen MoCo-v3 ViT teacher of the REPA loss (vaw_b200.encoders.mocov3_vit) against the
 reference fixture (tests/golden/vit_golden.npz) and the oracle (oracle/vit.py).  bf16 tensor-core path: 2e-2 rel-L2
 against the oracle under bf16 autocast; the fused preprocess + patchify is checked bit-exactly."""
-import ctypes as C
 import os
 import sys
 
