@@ -10,7 +10,7 @@ L.register("vaw_attn_fwd", [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p])
 L.register("vaw_attn_bwd_ws", [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p])
 dev = "cuda"
 torch.manual_seed(0)
-def rep(name, fn, outs, n=4):
+def rep(name, fn, outs, n=int(os.environ.get('REPS', '4'))):
     ref = None; bad = 0; where = ""
     for r in range(n):
         for o in outs: o.view(torch.int16 if o.element_size() == 2 else torch.int32).fill_(-1)
@@ -51,7 +51,15 @@ def attn_case(name, B, H, T, hd, bwd):
         o2, lse2 = o.clone(), lse.clone()
         rep(name + " bwd", lambda: L.call("vaw_attn_bwd_ws", qkv.data_ptr(), o2.data_ptr(), do.data_ptr(), lse2.data_ptr(), dqkv.data_ptr(), delta.data_ptr(), B, T, H, hd, L.stream_ptr()), [dqkv])
 which = sys.argv[1] if len(sys.argv) > 1 else "xl"
-if which == "xl":
+if which == "soak":   # the two epilogue families that had hazards, many repetitions
+    M, D, Hd = 16384, 1152, 4608
+    gemm_case("proj gate_res", M, D, D, L.EPI_GATE_RES)
+    gemm_case("fc2 gate_res", M, D, Hd, L.EPI_GATE_RES)
+    gemm_case("proj res", M, D, D, L.EPI_RES)
+    gemm_case("fc2 dgrad dgelu", M, Hd, D, L.EPI_DGELU_TANH, b_mn=1)
+    gemm_case("final dgrad bf16 K=16", 65536, 384, 16, L.EPI_BF16, b_mn=1)
+    gemm_case("qkv bf16 tile 192", M, 3 * D, D, L.EPI_BF16, tile_n=192)
+elif which == "xl":
     M, D, Hd = 16384, 1152, 4608
     gemm_case("patch-embed f32   K=16", M, D, 16, L.EPI_F32)
     gemm_case("patch-embed res   K=16", M, D, 16, L.EPI_RES)
