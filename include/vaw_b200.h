@@ -81,7 +81,8 @@ int vaw_qsample_target(const float* x0, const float* noise, const long long* t, 
  * evaluates p_mean_variance.  mean_type / var_type use the reference's enum values (:21-45).  Each fp32 operation
  * is rounded separately in the reference's order: results are bit-identical to the eager path except where exp()
  * is involved (device vs host libm, <= 1 ulp).  VELOCITY uses the per-sample coefficient the reference intends
- * (its :392-397 broadcasts over the wrong axis and only runs for N == 1 or N == W). */
+ * (its :392-397 broadcasts over the wrong axis and only runs for N == 1 or N == W).  t outside [0, T) is clamped
+ * (the reference's gather would device-assert); no other validation of device data is done. */
 enum { VAW_VT_LEARNED = 1, VAW_VT_FIXED_SMALL = 2, VAW_VT_FIXED_LARGE = 3, VAW_VT_LEARNED_RANGE = 4 };
 enum { VAW_RS_DDPM = 0, VAW_RS_DDIM = 1, VAW_RS_DDIM_REVERSE = 2, VAW_RS_MOMENTS = 3 };
 enum { VAW_RT_SQRT_RECIP_AC = 0, VAW_RT_SQRT_RECIPM1_AC, VAW_RT_SQRT_AC, VAW_RT_SQRT_1MAC, VAW_RT_INV_COEF1,

@@ -253,3 +253,15 @@ def test_cfg_combine_ragged_sizes(dt):
                                                           y=torch.zeros(n, dtype=torch.long, device=dev))
         h = both.float().cpu().numpy()
         close(g, odiff.cfg_combine(h[:n], h[n:], 3.25, dt == "bf16"))
+
+
+def test_out_of_range_timesteps_are_memory_safe():
+    """t outside [0, T) must not read outside the table (clamped; the reference's gather would device-assert)."""
+    dev = torch.device("cuda", 0)
+    d = make("EPSILON", "FIXED_LARGE")
+    x = torch.randn(4, 3, 8, 8, device=dev)
+    t = torch.tensor([-5, 1000, 10**9, 999], device=dev)
+    out = d.ddim_sample(lambda a, b, **k: a, x, t)["sample"]
+    ref = d.ddim_sample(lambda a, b, **k: a, x, torch.tensor([0, 999, 999, 999], device=dev))["sample"]
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)

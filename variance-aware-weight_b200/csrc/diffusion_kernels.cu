@@ -249,6 +249,7 @@ __device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__floa
 __device__ __forceinline__ StepCoef load_step_coef(const float* __restrict__ tab, int T, long long tt, int mean_type,
                                                    int mode, float eta) {
   StepCoef c;
+  tt = tt < 0 ? 0 : (tt >= T ? T - 1 : tt);  // memory safety only: the reference device-asserts on such an index
   auto row = [&](int r) { return __ldg(tab + (long long)r * T + tt); };
   c.recip = row(RT_SQRT_RECIP_AC);
   c.recipm1 = row(RT_SQRT_RECIPM1_AC);
