@@ -62,3 +62,37 @@ def test_new_entries_have_no_cpu_fallback():
         get_feature(SimpleNamespace(enc_type="clip-vit-L"), torch.zeros(1, 3, 32, 32), m)
     with pytest.raises(L.VawError):
         GraphedTrainingLosses(d, torch.nn.Linear(2, 2), (2, 3, 4, 4))
+
+
+def test_reverse_table_rows_follow_the_header_enum():
+    """The [VAW_RT_ROWS, T] table the host uploads must be laid out in the order include/vaw_b200.h declares."""
+    import os
+    import re
+    import numpy as np
+    from vaw_b200.tools import gaussian_diffusion as gd
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "vaw_b200.h")).read()
+    body = re.search(r"enum \{ (VAW_RT_SQRT_RECIP_AC = 0.*?VAW_RT_ROWS) \};", text, re.S).group(1)
+    names = [n.split("=")[0].strip() for n in re.sub(r"/\*.*?\*/", "", body, flags=re.S).split(",")]
+    assert names[-1] == "VAW_RT_ROWS" and len(names) == 15
+    d = gd.create_gaussian_diffusion(noise_schedule="linear", var_type="fixed_small")
+    want = {
+        "VAW_RT_SQRT_RECIP_AC": d.sqrt_recip_alphas_cumprod, "VAW_RT_SQRT_RECIPM1_AC": d.sqrt_recipm1_alphas_cumprod,
+        "VAW_RT_SQRT_AC": d.sqrt_alphas_cumprod, "VAW_RT_SQRT_1MAC": d.sqrt_one_minus_alphas_cumprod,
+        "VAW_RT_INV_COEF1": 1.0 / d.posterior_mean_coef1,
+        "VAW_RT_COEF2_OVER_COEF1": d.posterior_mean_coef2 / d.posterior_mean_coef1,
+        "VAW_RT_COEF1": d.posterior_mean_coef1, "VAW_RT_COEF2": d.posterior_mean_coef2,
+        "VAW_RT_LOGVAR": d.posterior_log_variance_clipped, "VAW_RT_MAX_LOG": np.log(d.betas),
+        "VAW_RT_VARIANCE": d.posterior_variance, "VAW_RT_AC": d.alphas_cumprod, "VAW_RT_AC_PREV": d.alphas_cumprod_prev,
+        "VAW_RT_AC_NEXT": d.alphas_cumprod_next,
+    }
+    tab = d._reverse_table("cpu").numpy()
+    assert tab.shape == (14, 1000) and tab.dtype == np.float32
+    for i, n in enumerate(names[:-1]):
+        np.testing.assert_array_equal(tab[i], np.asarray(want[n], dtype=np.float64).astype(np.float32), err_msg=n)
+    # FIXED_LARGE swaps in the beta-based variance rows (reference :326-331)
+    dl = gd.create_gaussian_diffusion(noise_schedule="linear", var_type="fixed_large")
+    var = np.append(dl.posterior_variance[1], dl.betas[1:])
+    tl = dl._reverse_table("cpu").numpy()
+    np.testing.assert_array_equal(tl[names.index("VAW_RT_VARIANCE")], var.astype(np.float32))
+    np.testing.assert_array_equal(tl[names.index("VAW_RT_LOGVAR")], np.log(var).astype(np.float32))
