@@ -15,6 +15,9 @@ installed; see oracle/ref_stubs/README.md).  Everything written here is an input
                            (fp32 and bf16 model outputs, pinned noise), IntervalCFG combine
     vit_golden.npz         the MoCo-v3 ViT teacher (tiny), preprocess_raw_image, ViT-B/16 position embedding and names
     dit_golden.npz         a tiny DiT (with REPA projector): weights, forward outputs, full training_losses + grads
+    flow_golden.npz        FlowMatching (tools/gaussian_diffusion.py:1151-1418): interpolant, q_sample, compute_target,
+                           training_losses (+ gradient) over every path type x prediction type, the vector / score
+                           conversions, and sde_sample (euler / heun) with pinned noise
 """
 import os
 import sys
@@ -368,7 +371,74 @@ def vit_golden():
     print("vit_golden.npz", len(out), "arrays")
 
 
+FLOW_CASES = [("START_X", "lambda"), ("EPSILON", "lambda"), ("EPSILON", "min_snr_5"), ("VELOCITY", "lambda"),
+              ("VELOCITY", "min_snr_5"), ("VECTOR", "lambda"), ("VECTOR", "constant"), ("SCORE", "constant")]
+
+
+SDE_CASES = [("linear", "VECTOR"), ("linear", "VELOCITY"), ("linear", "START_X"), ("linear_logsnr", "VECTOR"),
+             ("linear_logsnr", "VELOCITY"), ("linear_logsnr", "START_X"), ("linear_logsnr", "EPSILON"), ("cosine", "VECTOR")]
+
+
+def flow_golden():
+    out = {}
+    g = torch.Generator().manual_seed(31)
+    x0 = torch.randn(6, 3, 8, 8, generator=g).clamp(-1, 1)
+    eps = torch.randn(6, 3, 8, 8, generator=g)
+    model_out = torch.randn(6, 3, 8, 8, generator=g)
+    t = torch.tensor([0.01, 0.2, 0.5, 0.77, 0.9, 0.99])
+    out.update(x0=x0.numpy(), eps=eps.numpy(), model_out=model_out.numpy(), t=t.numpy())
+    for path in ("linear", "cosine", "linear_logsnr"):
+        for mean, wt in FLOW_CASES:
+            fm = rgd.FlowMatching(args=ref_args(weight_type=wt, path_type=path, sampler_type="sde"),
+                                  model_mean_type=rgd.ModelMeanType[mean], device="cpu")
+            key = f"{path}::{mean}::{wt}"
+            if wt in ("lambda", "constant") and mean in ("START_X", "VECTOR", "SCORE"):
+                a, s_, da, ds = fm.interpolant(t)
+                out[f"interp::{path}"] = torch.stack([a, s_, da, ds]).numpy()
+                out[f"xt::{path}"] = fm.q_sample(x0, eps, t).numpy()
+            out[f"target::{path}::{mean}"] = fm.compute_target(x0, eps, t).numpy()
+            mo = model_out.clone().requires_grad_(True)
+            terms = fm.training_losses(lambda x, ts, **k: mo, x0, None, t=t, noise=eps)
+            terms["loss"].float().mean().backward()
+            out[f"mse::{key}"] = terms["mse"].detach().float().numpy()
+            out[f"grad::{key}"] = mo.grad.numpy()
+        # model-output conversions used by the samplers (:1206-1257), t broadcast like sde_sample does
+        tt = t.view(-1, 1, 1, 1)
+        for mean in ("START_X", "EPSILON", "VELOCITY", "VECTOR", "SCORE"):
+            fm = rgd.FlowMatching(args=ref_args(path_type=path, sampler_type="sde"),
+                                  model_mean_type=rgd.ModelMeanType[mean], device="cpu")
+            if mean != "SCORE":
+                out[f"to_vector::{path}::{mean}"] = fm.convert_model_output_to_vector(model_out, x0, tt).numpy()
+            out[f"to_score::{path}::{mean}"] = fm.convert_model_output_to_score(model_out, x0, tt).numpy()
+    # sde_sample (:1370-1408) with the randn_like draws pinned and a linear toy denoiser; ode_sample (:1355-1363) needs
+    # torchdiffeq and reads self.rtol / self.atol, which the class never sets, so it cannot be executed
+    noises = torch.randn(16, 4, 3, 8, 8, generator=g)
+    start = torch.randn(4, 3, 8, 8, generator=g)
+    out.update(sde_noises=noises.numpy(), sde_start=start.numpy())
+    orig = torch.randn_like
+    # (the cosine path makes the reference return NaN: cos(fp32(pi/2)) < 0 puts a negative number under the sqrt of the
+    # diffusion coefficient at t = 1; EPSILON on the linear path divides by alpha(1) = 0 — one such case is recorded)
+    for path, mean in SDE_CASES:
+        if True:
+            for solver in ("euler", "heun"):
+                it = iter(noises)
+                torch.randn_like = lambda a, **k: next(it).to(a.dtype)
+                try:
+                    a_ = ref_args(path_type=path, sampler_type="sde")
+                    fm = rgd.FlowMatching(args=a_, model_mean_type=rgd.ModelMeanType[mean], device="cpu")
+                    toy = lambda x, tm, **k: (0.25 * x - 0.1 * tm.view(-1, 1, 1, 1).to(x.dtype)).float()
+                    res = fm.sample(toy, start, "cpu", num_steps=6, solver=solver)
+                finally:
+                    torch.randn_like = orig
+                out[f"sde::{path}::{mean}::{solver}"] = res.numpy()
+    np.savez_compressed(os.path.join(HERE, "flow_golden.npz"), **out)
+    print("flow_golden.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "flow":
+        flow_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "vit":
         vit_golden()
         sys.exit(0)
@@ -388,3 +458,4 @@ if __name__ == "__main__":
     reverse_golden()
     vit_golden()
     dit_golden()
+    flow_golden()

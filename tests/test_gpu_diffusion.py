@@ -101,24 +101,73 @@ def test_k2_linearity_at_scale():
     assert torch.equal(mse_p, mse[perm])
 
 
-def test_flow_matching_objective_vs_torch():
-    torch.manual_seed(3)
-    for path in ("linear", "cosine", "linear_logsnr"):
-        for mean in ("vector", "velocity", "epsilon"):
-            fm = gd.FlowMatching(args=gd.default_args(path_type=path, weight_type="lambda"),
-                                 model_mean_type=gd.ModelMeanType[mean.upper()])
-            x0 = torch.randn(8, 3, 16, 16, device=DEV); eps = torch.randn_like(x0)
-            t = torch.rand(8, device=DEV) * 0.98 + 0.01
-            out = torch.randn_like(x0).requires_grad_(True)
-            terms = fm.training_losses(lambda x, ts, **k: out, x0, None, t=t, noise=eps)
-            a, s, da, ds = fm.interpolant(t)
-            e = lambda v: v.view(-1, 1, 1, 1)
-            tgt = {"vector": e(da) * x0 + e(ds) * eps, "velocity": e(a) * eps - e(s) * x0, "epsilon": eps}[mean]
-            w = gd.compute_mse_loss_weight(fm.model_mean_type, "lambda", t, a, s)
-            ref = w * ((tgt - out) ** 2).mean(dim=(1, 2, 3))
-            np.testing.assert_allclose(terms["mse"].detach().cpu().numpy(), ref.detach().cpu().numpy(), rtol=2e-5)
-            xt = fm.q_sample(x0, eps, t)
-            assert torch.equal(xt, e(a) * x0 + e(s) * eps)
+FLOW_CASES = [("START_X", "lambda"), ("EPSILON", "lambda"), ("EPSILON", "min_snr_5"), ("VELOCITY", "lambda"),
+              ("VELOCITY", "min_snr_5"), ("VECTOR", "lambda"), ("VECTOR", "constant"), ("SCORE", "constant")]
+
+
+@pytest.mark.parametrize("path", ("linear", "cosine", "linear_logsnr"))
+def test_flow_matching_vs_reference_golden(path):
+    """FlowMatching.training_losses / q_sample / compute_target (reference :1273-1340) against the fixture produced by
+    executing the reference (tests/golden/make_golden.py::flow_golden).  The linear path has no transcendental in its
+    coefficients -> x_t and targets bit-exact; cos / sin / sigmoid differ between the device's and the host's libm in
+    the last bit, so those paths carry a 2-ulp tolerance.  The reduction (fp32, different summation order) 1e-5."""
+    g = np.load(os.path.join(G, "flow_golden.npz"))
+    x0, eps, t, mo = (torch.from_numpy(g[k]).to(DEV) for k in ("x0", "eps", "t", "model_out"))
+    exact = path == "linear"
+    tol = dict(rtol=0, atol=0) if exact else dict(rtol=1e-6, atol=1e-6)
+    for mean, wt in FLOW_CASES:
+        fm = gd.FlowMatching(args=gd.default_args(path_type=path, weight_type=wt), model_mean_type=gd.ModelMeanType[mean])
+        np.testing.assert_allclose(fm.q_sample(x0, eps, t).cpu().numpy(), g[f"xt::{path}"], **tol)
+        np.testing.assert_allclose(fm.compute_target(x0, eps, t).cpu().numpy(), g[f"target::{path}::{mean}"], **tol)
+        out = mo.clone().requires_grad_(True)
+        seen = {}
+        def model(x, ts, **k):
+            seen["x"], seen["t"] = x, ts
+            return out
+        terms = fm.training_losses(model, x0, None, t=t, noise=eps)
+        terms["loss"].mean().backward()
+        assert torch.equal(seen["t"], t)                      # the model is handed the continuous time itself (:1319)
+        np.testing.assert_allclose(seen["x"].cpu().numpy(), g[f"xt::{path}"], **tol)
+        np.testing.assert_allclose(terms["mse"].detach().cpu().numpy(), g[f"mse::{path}::{mean}::{wt}"], rtol=1e-5)
+        np.testing.assert_allclose(out.grad.cpu().numpy(), g[f"grad::{path}::{mean}::{wt}"], rtol=2e-5, atol=1e-9)
+    with pytest.raises(ValueError):
+        bad = gd.FlowMatching(args=gd.default_args(path_type=path, weight_type="snr"), model_mean_type=gd.ModelMeanType.VECTOR)
+        bad.training_losses(lambda x, ts, **k: mo, x0, None, t=t, noise=eps)
+
+
+def test_seeded_draw_order_noise_then_t():
+    """training_losses(model, x) with t=None, noise=None draws `randn_like(x_start)` FIRST and the timesteps SECOND from
+    the device generator (reference :849-852 diffusion, :1300-1303 flow): the seeded implicit call must equal the
+    explicit call fed with draws made in that order, and must differ from the opposite order."""
+    x0 = torch.randn(8, 4, 16, 16, device=DEV)
+    rec = []
+    def model(x, ts, **k):
+        rec.append((x.clone(), ts.clone()))
+        return torch.zeros_like(x)
+    d = gd.create_gaussian_diffusion(noise_schedule="cosine", mean_type="epsilon", weight_type="lambda")
+    torch.manual_seed(77)
+    a = d.training_losses(model, x0)
+    torch.manual_seed(77)
+    noise = torch.randn_like(x0)
+    t = torch.randint(0, d.num_timesteps, (8,), device=DEV)
+    b = d.training_losses(model, x0, t=t, noise=noise)
+    assert torch.equal(rec[0][0], rec[1][0]) and torch.equal(rec[0][1], rec[1][1]) and torch.equal(a["mse"], b["mse"])
+    assert torch.equal(rec[0][1], d._scale_timesteps(t))
+    torch.manual_seed(77)
+    t_first = torch.randint(0, d.num_timesteps, (8,), device=DEV)   # the opposite order consumes the stream differently
+    assert not torch.equal(t_first, t)
+    # flow matching: noise, then torch.rand (uniform) or torch.randn -> sigmoid (lognorm), reference :1259-1270
+    for dist, draw in ((["uniform"], lambda: torch.rand(8, device=DEV)),
+                       (["lognorm", 0.0, 1.0], lambda: torch.sigmoid(torch.randn(8, device=DEV) * 1.0 + 0.0))):
+        fm = gd.FlowMatching(args=gd.default_args(path_type="linear", time_dist=dist), model_mean_type=gd.ModelMeanType.VECTOR)
+        rec.clear()
+        torch.manual_seed(5)
+        a = fm.training_losses(model, x0)
+        torch.manual_seed(5)
+        noise = torch.randn_like(x0)
+        tt = draw()
+        b = fm.training_losses(model, x0, t=tt, noise=noise)
+        assert torch.equal(rec[0][1], tt) and torch.equal(rec[0][0], rec[1][0]) and torch.equal(a["mse"], b["mse"])
 
 
 def test_align_loss_kernel_vs_torch():

@@ -32,20 +32,23 @@ def _oracle_grads(m, x, t, y, gout, gz, heads, depth, align, enc, autocast):
     return o, z, sd
 
 
-@pytest.mark.parametrize("hidden,heads,depth,img,align,B", [(128, 2, 2, 16, False, 4), (144, 2, 3, 16, True, 4),
-                                                             (384, 6, 4, 32, False, 8), (128, 2, 2, 16, False, 1)])
-def test_forward_backward_vs_oracle(hidden, heads, depth, img, align, B):
+# The last two rows are the widths the benchmark numbers are quoted on (BASELINE.json configs 3 and 5): DiT-XL/2,
+# D = 1152, 16 heads of 72, T = 256, without and with the REPA projector at its real size (2048 -> 2048 -> 768).
+@pytest.mark.parametrize("hidden,heads,depth,img,align,B,zd,pd", [
+    (128, 2, 2, 16, False, 4, 48, 64), (144, 2, 3, 16, True, 4, 48, 64), (384, 6, 4, 32, False, 8, 48, 64),
+    (128, 2, 2, 16, False, 1, 48, 64), (1152, 16, 2, 32, False, 4, 48, 64), (1152, 16, 2, 32, True, 4, 768, 2048)])
+def test_forward_backward_vs_oracle(hidden, heads, depth, img, align, B, zd, pd):
     torch.manual_seed(1)
     enc = max(1, depth // 2)
     m = DiT(image_size=img, patch_size=2, in_channels=4, hidden_size=hidden, depth=depth, num_heads=heads,
-            class_dropout_prob=0.0, num_classes=10, learn_align=align, encoder_depth=enc, z_dims=48,
-            projector_dim=64).to(DEV).train()
+            class_dropout_prob=0.0, num_classes=10, learn_align=align, encoder_depth=enc, z_dims=zd,
+            projector_dim=pd).to(DEV).train()
     dezero(m)
     T = (img // 2) ** 2
     x = torch.randn(B, 4, img, img, device=DEV); t = torch.rand(B, device=DEV) * 999
     y = torch.randint(0, 10, (B,), device=DEV)
     gout = torch.randn(B, 4, img, img, device=DEV)
-    gz = torch.randn(B, T, 48, device=DEV) * 0.1 if align else None
+    gz = torch.randn(B, T, zd, device=DEV) * 0.1 if align else None
     out, zs = m(x, t, y)
     assert out.dtype == torch.bfloat16 and out.shape == x.shape
     ((out.float() * gout).sum() + ((zs.float() * gz).sum() if align else 0.0)).backward()

@@ -16,8 +16,10 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 2e-2
 
 
+# The last row is U-ViT-M's width and sequence (BASELINE.json config 4): D = 768, 12 heads of 64, 64x64x3 pixels at patch 4
+# -> T = 256 + 2 extra tokens = 258, depth 3 (one in-block, the mid block, one out-block with its skip_linear).
 @pytest.mark.parametrize("dim,heads,depth,img,patch,classes,B", [(128, 2, 3, 16, 2, 10, 4), (128, 2, 5, 16, 4, -1, 3),
-                                                                 (384, 6, 5, 32, 4, 100, 8)])
+                                                                 (384, 6, 5, 32, 4, 100, 8), (768, 12, 3, 64, 4, 1000, 4)])
 def test_forward_backward_vs_oracle(dim, heads, depth, img, patch, classes, B):
     torch.manual_seed(1)
     m = UViT(image_size=img, patch_size=patch, in_channels=3 if patch == 4 else 4, embed_dim=dim, depth=depth,
