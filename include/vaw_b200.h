@@ -259,6 +259,13 @@ int vaw_align_mse(const void* zs, int zs_dtype, const void* feat, int feat_dtype
 int vaw_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, float* ema, long long n, double lr,
                    double beta1, double beta2, double eps, double weight_decay, long long step, double grad_scale,
                    double ema_decay, const float* clip_coef, vaw_stream_t stream);
+/* Same, for torch.cuda.amp.GradScaler-driven steps (tools/trainer.py:124-129 scaler.unscale_ / scaler.step): inv_scale
+ * (device, nullable) multiplies the gradients, found_inf (device, nullable) != 0 skips the whole step - parameters,
+ * moments, shadow and EMA untouched - so neither the unscale nor the inf check costs a pass or a host sync. */
+int vaw_adamw_step_amp(float* p, const float* g, float* m, float* v, void* p_bf16, float* ema, long long n, double lr,
+                       double beta1, double beta2, double eps, double weight_decay, long long step, double grad_scale,
+                       double ema_decay, const float* clip_coef, const float* inv_scale, const float* found_inf,
+                       vaw_stream_t stream);
 /* Global L2 norm of the flat gradient buffer and the clip_grad_norm_ coefficient (tools/trainer.py:60-62), kept on the
  * device: out[0] = ||grad_scale * g||, out[1] = min(1, max_norm / (out[0] + 1e-6)); pass out + 1 as clip_coef above.
  * part: 1024 floats of scratch. */
@@ -301,6 +308,10 @@ int vaw_uvit_forward(const vaw_uvit_cfg* cfg, const float* P, const void* Pb, vo
                      const float* t, const long long* y, float* out, vaw_stream_t stream);
 int vaw_uvit_backward(const vaw_uvit_cfg* cfg, const float* P, const void* Pb, float* G, void* ws, const float* dout,
                       const long long* y, int accumulate, vaw_stream_t stream);
+/* events: NULL or depth+1 cudaEvent_t recorded as each block's gradients (last block first) become final, then the
+ * embedder / head tensors - the hook the data-parallel bucketed all-reduce (main.py:347 DDP) overlaps on. */
+int vaw_uvit_backward_ev(const vaw_uvit_cfg* cfg, const float* P, const void* Pb, float* G, void* ws,
+                         const float* dout, const long long* y, int accumulate, void** events, vaw_stream_t stream);
 /* token assembly [label, time, patches] + pos_embed (uvit.py:221-231) and its backward pieces */
 int vaw_uvit_assemble(const float* patch_tok, const float* t, const float* table, const long long* labels,
                       const float* pos, float* x0, int B, int T, int extras, int D, vaw_stream_t stream);

@@ -142,7 +142,7 @@ wmse_fwd_bwd_kernel(const OutT* __restrict__ out, const float* __restrict__ x0, 
                     const float* __restrict__ tab_c0, const float* __restrict__ tab_c1,
                     const float* __restrict__ w_tab, float* __restrict__ mse, float* __restrict__ raw_mse,
                     OutT* __restrict__ grad, const float* __restrict__ gscale_n, float gscale, int mean_type,
-                    long long chw) {
+                    long long chw, int vec) {
   const long long n = blockIdx.x;
   const Coef c = load_coef(t, tab_a, tab_s, tab_c0, tab_c1, n);
   const float w = w_tab ? __ldg(w_tab + (t ? t[n] : n)) : 1.f;
@@ -152,7 +152,7 @@ wmse_fwd_bwd_kernel(const OutT* __restrict__ out, const float* __restrict__ x0, 
   const bool need_eps = (mean_type != MT_START_X);
   const long long base = n * chw;
   float acc = 0.f;
-  if ((chw & 3) == 0) {
+  if (vec) {
     const long long chw4 = chw >> 2, base4 = base >> 2;
     for (long long i = threadIdx.x; i < chw4; i += blockDim.x) {
       const float4 o = Vec4<OutT>::load(out, base4 + i);
@@ -565,14 +565,19 @@ extern "C" int vaw_wmse_fwd_bwd(const void* out, int out_dtype, const float* x0,
   VAW_CHECK_ARG(N >= 0 && chw > 0, "vaw_wmse_fwd_bwd: bad shape N=%lld chw=%lld", N, chw);
   VAW_CHECK_ARG(mean_type >= MT_PREVIOUS_X && mean_type <= MT_SCORE, "vaw_wmse_fwd_bwd: bad mean_type %d", mean_type);
   if (N == 0) return VAW_OK;
+  // 128-bit (fp32) / 64-bit (bf16) accesses need chw % 4 == 0 AND suitably aligned bases (an offset view of a larger
+  // buffer may not be); otherwise the scalar path runs
+  const uintptr_t f32_ptrs = (uintptr_t)x0 | (uintptr_t)noise;
+  const uintptr_t out_ptrs = (uintptr_t)out | (uintptr_t)grad_out;
+  const int vec = (chw % 4 == 0) && ((f32_ptrs & 15) == 0) && ((out_ptrs & (out_dtype == 0 ? 15 : 7)) == 0);
   if (out_dtype == 0)
     wmse_fwd_bwd_kernel<float><<<(unsigned)N, 256, 0, stream>>>(
         (const float*)out, x0, noise, t, tab_alpha, tab_sigma, tab_c0, tab_c1, w_tab, mse, raw_mse, (float*)grad_out,
-        gscale_n, gscale, mean_type, chw);
+        gscale_n, gscale, mean_type, chw, vec);
   else
     wmse_fwd_bwd_kernel<bf16><<<(unsigned)N, 256, 0, stream>>>(
         (const bf16*)out, x0, noise, t, tab_alpha, tab_sigma, tab_c0, tab_c1, w_tab, mse, raw_mse, (bf16*)grad_out,
-        gscale_n, gscale, mean_type, chw);
+        gscale_n, gscale, mean_type, chw, vec);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }

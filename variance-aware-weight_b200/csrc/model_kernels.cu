@@ -182,8 +182,13 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              bf16* __restrict__ p_bf16, float* __restrict__ ema, long long n, float lr, float beta1, float beta2,
              float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, float ema_decay,
-             const float* __restrict__ clip_coef) {
+             const float* __restrict__ clip_coef, const float* __restrict__ inv_scale,
+             const float* __restrict__ found_inf) {
+  // GradScaler semantics without a host round trip (trainer.py:124-129): a step whose gradients held an inf / nan is
+  // skipped as a whole - parameters, moments, the bf16 shadow and the EMA copy stay as they were
+  if (found_inf && __ldg(found_inf) != 0.f) return;
   if (clip_coef) grad_scale *= __ldg(clip_coef);   // device-side clip_grad_norm_ coefficient (vaw_grad_clip_coef)
+  if (inv_scale) grad_scale *= __ldg(inv_scale);   // 1 / loss scale, kept on the device by torch's GradScaler
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -427,18 +432,27 @@ extern "C" int vaw_colsum_f32_small(const float* a, long long lda, int rows, int
 }
 
 // step: 1-based optimizer step (bias corrections are computed on the host in double like torch does)
-extern "C" int vaw_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, float* ema, long long n,
-                              double lr, double beta1, double beta2, double eps, double weight_decay, long long step,
-                              double grad_scale, double ema_decay, const float* clip_coef, cudaStream_t stream) {
+extern "C" int vaw_adamw_step_amp(float* p, const float* g, float* m, float* v, void* p_bf16, float* ema, long long n,
+                                  double lr, double beta1, double beta2, double eps, double weight_decay,
+                                  long long step, double grad_scale, double ema_decay, const float* clip_coef,
+                                  const float* inv_scale, const float* found_inf, cudaStream_t stream) {
   VAW_CHECK_ARG(p && g && m && v && n >= 0 && n % 4 == 0 && step >= 1, "vaw_adamw_step: bad arguments (n %% 4 == 0)");
   if (n == 0) return VAW_OK;
   const double bc1 = 1.0 - pow(beta1, (double)step);
   const double bc2 = 1.0 - pow(beta2, (double)step);
   adamw_kernel<<<grid_for(n / 4), 256, 0, stream>>>(p, g, m, v, (bf16*)p_bf16, ema, n, (float)lr, (float)beta1,
                                                     (float)beta2, (float)eps, (float)weight_decay, (float)bc1,
-                                                    (float)sqrt(bc2), (float)grad_scale, (float)ema_decay, clip_coef);
+                                                    (float)sqrt(bc2), (float)grad_scale, (float)ema_decay, clip_coef,
+                                                    inv_scale, found_inf);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
+}
+
+extern "C" int vaw_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, float* ema, long long n,
+                              double lr, double beta1, double beta2, double eps, double weight_decay, long long step,
+                              double grad_scale, double ema_decay, const float* clip_coef, cudaStream_t stream) {
+  return vaw_adamw_step_amp(p, g, m, v, p_bf16, ema, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                            ema_decay, clip_coef, nullptr, nullptr, stream);
 }
 
 // out[0] = ||grad_scale * g||_2, out[1] = clip coefficient min(1, max_norm / (out[0] + 1e-6)) (1 if max_norm <= 0);

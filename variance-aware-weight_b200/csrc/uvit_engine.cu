@@ -239,8 +239,12 @@ extern "C" int vaw_uvit_forward(const vaw_uvit_cfg* cfg, const float* P, const v
 }
 
 // dout [B,C,H,W] fp32.  accumulate = 0: G is overwritten for every tensor; 1: gradients are added.
-extern "C" int vaw_uvit_backward(const vaw_uvit_cfg* cfg, const float* P, const void* Pb_, float* Gd, void* ws_,
-                                 const float* dout, const long long* y, int accumulate, cudaStream_t s) {
+// events: optional array of depth + 1 cudaEvent_t; events[i] is recorded once block i's thirteen tensors are final
+// (the blocks finish in reverse order - the long skip connections only route activation gradients, so an out-block's
+// parameters do not wait for its partner in-block), events[depth] after the embedder / head tensors.
+extern "C" int vaw_uvit_backward_ev(const vaw_uvit_cfg* cfg, const float* P, const void* Pb_, float* Gd, void* ws_,
+                                    const float* dout, const long long* y, int accumulate, void** events,
+                                    cudaStream_t s) {
   TRY(u_check(cfg));
   VAW_CHECK_ARG(P && Pb_ && Gd && ws_ && dout, "vaw_uvit_backward: null pointer");
   const vaw_uvit_cfg& c = *cfg;
@@ -319,6 +323,7 @@ extern "C" int vaw_uvit_backward(const vaw_uvit_cfg* cfg, const float* P, const 
       TRY(G(w.dy, D, 0, Pb + L.off[pb + UB_SKIP_W], 2LL * D, 1, M, 2 * D, D, VAW_EPI_BF16).out(b.dcat).run(s));
       TRY(vaw_unpack_cols(b.dcat, 2LL * D, 0, w.dx, M, D, 0, s));  // gradient of the block's x input (first D columns)
     }
+    if (events && events[i]) VAW_CUDA_TRY(cudaEventRecord(reinterpret_cast<cudaEvent_t>(events[i]), s));
   }
   // ---- token assembly: pos_embed, label table, patch embedding ----
   TRY(vaw_uvit_pos_grad(w.dx, Gd + L.off[U_POS], B, T, D, acc, s));
@@ -328,5 +333,11 @@ extern "C" int vaw_uvit_backward(const vaw_uvit_cfg* cfg, const float* P, const 
   TRY(vaw_colsum_bf16(w.dtok, D, B * Lp, D, w.cpart, colsum_rows(B * Lp, D), Gd + L.off[U_PE_B], acc, s));
   TRY(G(w.dtok, D, 1, w.patches, Kp, 1, D, Kp, B * Lp, VAW_EPI_F32).out(Gd + L.off[U_PE_W]).acc(acc)
           .autosplit(w.split_ws, w.split_elems).run(s));
+  if (events && events[c.depth]) VAW_CUDA_TRY(cudaEventRecord(reinterpret_cast<cudaEvent_t>(events[c.depth]), s));
   return VAW_OK;
+}
+
+extern "C" int vaw_uvit_backward(const vaw_uvit_cfg* cfg, const float* P, const void* Pb_, float* Gd, void* ws_,
+                                 const float* dout, const long long* y, int accumulate, cudaStream_t s) {
+  return vaw_uvit_backward_ev(cfg, P, Pb_, Gd, ws_, dout, y, accumulate, nullptr, s);
 }

@@ -2,8 +2,14 @@
 
 A DiT-S step is ~390 library launches of 10-20 us; replaying them as one graph removes the per-launch host cost
 (B = 64: 7.15 -> 6.31 ms per step on a B200, scripts/dev_graph_dits.py).  The sampler draw (host RNG + a small H2D copy)
-and the optimizer (host-side step count) stay outside the graph.  Single-process only: the data-parallel gradient
-all-reduce is issued from Python per bucket and is not captured.
+and the optimizer (host-side step count; two launches) stay outside the graph.  Single-process only: the data-parallel
+gradient all-reduce is issued from Python per bucket and is not captured.
+
+Two things a replay cannot see and that are therefore handled around it: (1) the bf16 weight shadow - the version check
+that triggers the fp32 -> bf16 cast runs in Python, so `__call__` refreshes the shadow before every replay (a no-op after
+FusedAdamW, which writes the shadow itself; one cast pass after torch.optim.AdamW / load_state_dict / an EMA swap);
+(2) overwrite-vs-accumulate is a launch argument of the backward, so gradient accumulation uses a second graph
+(`accumulate=True`), captured on first use.
 """
 from __future__ import annotations
 
@@ -46,10 +52,12 @@ class GraphedTrainingLosses:
                 self._run()
                 self._clear_grads()
         torch.cuda.current_stream(dev).wait_stream(side)
+        self._clear_grads()                 # captured in overwrite mode: a replay REPLACES the gradients
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._terms = self._run()
         self._terms = {k: v.detach() for k, v in self._terms.items()}
+        self.graph_acc = self._terms_acc = None
 
     def _clear_grads(self):
         for p in self.model.parameters():
@@ -63,7 +71,18 @@ class GraphedTrainingLosses:
         return terms
 
     @torch.no_grad()
-    def __call__(self, x0, t, w=None, y=None, features=None, noise=None):
+    def _capture_accumulate(self):
+        bind = getattr(self.model, "_bind_grads", None)
+        if bind is None:
+            raise L.VawError("gradient accumulation across replays needs an engine-backed model")
+        bind()                              # gradients bound -> the backward is captured with accumulate = 1
+        self.graph_acc = torch.cuda.CUDAGraph()
+        with torch.enable_grad(), torch.cuda.graph(self.graph_acc):
+            terms = self._run()
+        self._terms_acc = {k: v.detach() for k, v in terms.items()}
+
+    @torch.no_grad()
+    def __call__(self, x0, t, w=None, y=None, features=None, noise=None, accumulate=False):
         self.x0.copy_(x0)
         self.t.copy_(t)
         if w is None:
@@ -82,8 +101,18 @@ class GraphedTrainingLosses:
             self.noise.normal_()
         else:
             self.noise.copy_(noise)
-        self.graph.replay()
+        refresh = getattr(self.model, "_refresh_shadow", None)
+        if refresh is not None:
+            refresh()                  # weights changed outside FusedAdamW since the last replay -> re-cast the shadow
+        if accumulate:
+            if self.graph_acc is None:
+                self._capture_accumulate()
+            self.graph_acc.replay()
+            terms = self._terms_acc
+        else:
+            self.graph.replay()
+            terms = self._terms
         bind = getattr(self.model, "_bind_grads", None)
         if bind is not None:
             bind()                     # `.grad` views of the flat gradient buffer, as after an eager backward
-        return self._terms
+        return terms

@@ -3,6 +3,8 @@ the tensor cores and a flat fp32 gradient buffer); the nn.Parameters the referen
 code sees are views of it."""
 from __future__ import annotations
 
+import copy
+
 import torch
 import torch.nn as nn
 
@@ -44,6 +46,18 @@ class FlatEngineModule(nn.Module):
         self._post_backward = None
         self._slot_cache = None
 
+    def __deepcopy__(self, memo):
+        """`copy.deepcopy(model)` is how the reference makes its EMA model (main.py:344).  The copy gets its own
+        parameters (nn.Parameter.__deepcopy__ clones them) and re-packs them into a fresh flat buffer on its first
+        forward; the activation workspace (tens of GB), CUDA events and data-parallel hooks are not carried over."""
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        drop = {"_flat": None, "_shadow": None, "_gflat": None, "_ws": None, "_events": None, "_post_backward": None,
+                "_slot_cache": None, "_ws_batch": -1, "_shadow_version": -1}
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = drop[k] if k in drop else copy.deepcopy(v, memo)
+        return new
+
     def _ensure_flat(self, device):
         """(Re)pack the parameters into the flat buffer if they are not already views of it (after .to(), deepcopy,
         load_state_dict(assign=True) ...)."""
@@ -70,9 +84,12 @@ class FlatEngineModule(nn.Module):
         self._slot_cache = slots
 
     def _refresh_shadow(self):
-        # every in-place update of a parameter (optimizer step, load_state_dict, init) bumps its version counter
+        # every in-place update of a parameter (optimizer step, load_state_dict, init) bumps its version counter ...
         v = sum(p._version for p, _ in self._slot_cache)
-        if v != self._shadow_version:
+        # ... except writes through `.data`, which is how the reference's ema() updates the EMA model
+        # (tools/trainer.py:12-18 `target_dict[key].data.copy_`).  That model only ever runs in eval mode, so an eval
+        # forward always re-casts (one 6 B/param pass, ~2 % of a DiT-XL sampling forward); training keeps the check.
+        if v != self._shadow_version or not self.training:
             L.call("vaw_cast_f32_bf16", self._flat.data_ptr(), self._shadow.data_ptr(), self._flat.numel(), L.stream_ptr())
             self._shadow_version = v
 

@@ -25,6 +25,7 @@ L.register("vaw_uvit_param_layout", [C.POINTER(UViTCfg), C.c_void_p, C.c_void_p,
 L.register("vaw_uvit_workspace_bytes", [C.POINTER(UViTCfg), C.c_void_p])
 L.register("vaw_uvit_forward", [C.POINTER(UViTCfg)] + [C.c_void_p] * 8)
 L.register("vaw_uvit_backward", [C.POINTER(UViTCfg)] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p])
+L.register("vaw_uvit_backward_ev", [C.POINTER(UViTCfg)] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p])
 L.register("vaw_cast_f32_bf16", [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p])
 
 
@@ -169,6 +170,24 @@ class UViT(FlatEngineModule):
         L.call("vaw_uvit_workspace_bytes", C.byref(cfg), C.byref(nbytes))
         return nbytes.value
 
+    @property
+    def depth(self):
+        return self.num_blocks
+
+    def block_grad_ranges(self):
+        """Element ranges of the flat gradient buffer that become final with each block (in-blocks, mid, out-blocks in
+        engine order: its thirteen tensors are contiguous), the range that only becomes final at the end of backward
+        (patch embedding, label table, pos_embed, final norm, decoder_pred, 3x3 conv), and the buffer length.  The long
+        skip connections only carry activation gradients, so blocks complete strictly in reverse order."""
+        off, num, total = self._layout()
+        per_block = []
+        for bi in range(self.num_blocks):
+            base = 10 + 13 * bi
+            end = off[base + 13] if base + 13 < len(off) else total
+            per_block.append([(off[base], end)])
+        tail = [(0, off[10])]
+        return per_block, tail, total
+
     def token_drop(self, labels, train=True):
         """Label dropout for classifier-free guidance (uvit.py:206-218)."""
         if train and self.class_dropout_prob > 0:
@@ -214,8 +233,11 @@ class _UViTFunction(torch.autograd.Function):
         cfg = model._cfg(ctx.batch)
         dout = dout.float().contiguous()
         fresh = model._bind_grads()
-        L.call("vaw_uvit_backward", C.byref(cfg), model._flat.data_ptr(), model._shadow.data_ptr(),
-               model._gflat.data_ptr(), model._ws.data_ptr(), dout.data_ptr(), L.ptr(ctx.y), 0 if fresh else 1,
+        ev = None
+        if model._events is not None:
+            ev = (C.c_void_p * len(model._events))(*[e.cuda_event for e in model._events])
+        L.call("vaw_uvit_backward_ev", C.byref(cfg), model._flat.data_ptr(), model._shadow.data_ptr(),
+               model._gflat.data_ptr(), model._ws.data_ptr(), dout.data_ptr(), L.ptr(ctx.y), 0 if fresh else 1, ev,
                L.stream_ptr())
         if model._post_backward is not None:
             model._post_backward()

@@ -1,10 +1,16 @@
 """Fused optimizer step over the engine's flat parameter buffer, and the data-parallel model wrapper.
 
-FusedAdamW replaces, for models that expose `flat_parameters()` (vaw_b200.models.DiT), the reference's
-`optim.AdamW(model.parameters(), lr, betas, weight_decay, eps)` (main.py:354) + GradScaler unscale (trainer.py:124-129)
-+ rank-0 EMA (trainer.py:12-18) with ONE HBM-bound pass (vaw_adamw_step): read p, g, m, v; write p, m, v, the bf16
-shadow used by the tensor cores, and optionally the EMA copy.  torch.optim.AdamW over `model.parameters()` keeps
-working (the per-tensor Parameters are views of the flat buffer); this class is the fast path.
+FusedAdamW replaces, for models that expose `flat_parameters()` (vaw_b200.models.DiT / UViT), the reference's
+`optim.AdamW(model.parameters(), lr, betas, weight_decay, eps)` (main.py:354) + GradScaler unscale / inf check
+(trainer.py:124-129) + rank-0 EMA (trainer.py:12-18) with ONE HBM-bound pass (vaw_adamw_step_amp): read p, g, m, v;
+write p, m, v, the bf16 shadow used by the tensor cores, and optionally the EMA copy.
+
+It IS a `torch.optim.Optimizer`: `param_groups[i]["params"]` hold the model's real Parameters, `state[p]` carries
+`step / exp_avg / exp_avg_sq` (views of the flat moment buffers, torch.optim.AdamW's key names, so `state_dict()`
+round-trips with the reference's checkpoints, tools/utils.py:93-120), which is what the reference's
+`LambdaLR(optimizer, ...)` (main.py:355), `scaler.unscale_(optimizer)` / `scaler.step(optimizer)` (trainer.py:124-129)
+and `optimizer.zero_grad()` (:133) need.  torch.optim.AdamW over `model.parameters()` keeps working too (the
+per-tensor Parameters are views of the flat buffer); this class is the fast path.
 """
 from __future__ import annotations
 
@@ -16,54 +22,132 @@ import torch
 from . import _lib as L
 from .parallel import FlatGradSync, dist_ready
 
-L.register("vaw_adamw_step", [C.c_void_p] * 6 + [C.c_longlong] + [C.c_double] * 5 + [C.c_longlong, C.c_double, C.c_double,
-                                                                                      C.c_void_p, C.c_void_p])
-L.register("vaw_grad_clip_coef", [C.c_void_p, C.c_longlong, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p])
+_PTR, _LL, _D = C.c_void_p, C.c_longlong, C.c_double
+L.register("vaw_adamw_step", [_PTR] * 6 + [_LL] + [_D] * 5 + [_LL, _D, _D, _PTR, _PTR])
+L.register("vaw_adamw_step_amp", [_PTR] * 6 + [_LL] + [_D] * 5 + [_LL, _D, _D, _PTR, _PTR, _PTR, _PTR])
+L.register("vaw_grad_clip_coef", [_PTR, _LL, _D, _D, _PTR, _PTR, _PTR])
 
 
-class FusedAdamW:
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, ema_decay=None):
+def _unwrap(model):
+    return model.module if isinstance(model, DataParallel) else model
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """FusedAdamW(model, lr=..., betas=..., eps=..., weight_decay=..., ema_decay=None)
+
+    `model` is an engine-backed module (or its DataParallel wrapper).  `params` may restrict / group the parameters the
+    way torch optimizers allow (an iterable of Parameters or of param-group dicts); every one of them must belong to
+    `model`.  Frozen parameters (DiT's pos_embed) are never updated."""
+
+    # torch.cuda.amp.GradScaler.step() hands such optimizers `self.grad_scale` / `self.found_inf` (device tensors) and
+    # calls step() unconditionally: the kernel unscales and skips on the device, no `.item()` sync (trainer.py:128)
+    _step_supports_amp_scaling = True
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, ema_decay=None, params=None):
+        if not isinstance(model, torch.nn.Module):
+            raise TypeError("FusedAdamW(model, ...): pass the engine-backed module (its parameters are found through it)")
         self.model = model
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.ema_decay = ema_decay
         self.step_count = 0
         self.m = self.v = self.ema = None
         self.grad_norm = self._norm_ws = None
-        self._ranges = []
-        self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)]  # LambdaLR-style access
+        self._group_ranges = None
+        self._flat_ptr = None
+        self._loaded = None
+        if params is None:
+            params = [p for p in model.parameters() if p.requires_grad]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
 
+    # the single-group shorthands the round-1 API exposed
+    @property
+    def lr(self):
+        return self.param_groups[0]["lr"]
+
+    # -------------------------------------------------------------------------------------------------
     def _ensure_state(self):
         flat, gflat, shadow = self.model.flat_parameters()
         if flat is None:
             raise L.VawError("FusedAdamW: run a forward pass (or model._ensure_flat(device)) before the first step")
-        if self.m is None or self.m.device != flat.device or self.m.numel() != flat.numel():
+        stale = (self.m is None or self.m.device != flat.device or self.m.numel() != flat.numel()
+                 or self._flat_ptr != flat.data_ptr())
+        if stale:
+            old = (self.m, self.v) if self.m is not None and self.m.numel() == flat.numel() else None
             self.m = torch.zeros_like(flat, requires_grad=False)
             self.v = torch.zeros_like(flat, requires_grad=False)
-            if self.ema_decay is not None:
+            if old is not None:        # the model repacked its buffer (.to(), load_state_dict(assign=True)): keep the moments
+                self.m.copy_(old[0])
+                self.v.copy_(old[1])
+            if self.ema_decay is not None and (self.ema is None or self.ema.numel() != flat.numel()
+                                               or self.ema.device != flat.device):
                 self.ema = flat.detach().clone()
-            # contiguous element ranges of the TRAINABLE tensors (frozen ones - DiT's pos_embed - get no update and no
-            # weight decay, like torch.optim.AdamW skipping parameters without a gradient); padding rides along
-            slots = sorted(((o, p.numel(), p.requires_grad) for p, o in self.model._slot_cache), key=lambda x: x[0])
-            ranges = []
-            for i, (o, n, train) in enumerate(slots):
-                end = slots[i + 1][0] if i + 1 < len(slots) else flat.numel()
-                if not train:
-                    continue
-                if ranges and ranges[-1][1] == o:
-                    ranges[-1][1] = end
-                else:
-                    ranges.append([o, end])
-            self._ranges = [(a, b - a) for a, b in ranges]
+            self._flat_ptr = flat.data_ptr()
+            self._build_ranges(flat)
+            if self._loaded is not None:   # moments restored by load_state_dict before the buffers existed
+                for p, o in _unwrap(self.model)._slot_cache:
+                    st = self._loaded.get(id(p))
+                    if st is not None and "exp_avg" in st:
+                        self.m[o:o + p.numel()].copy_(st["exp_avg"].reshape(-1))
+                        self.v[o:o + p.numel()].copy_(st["exp_avg_sq"].reshape(-1))
+                self._loaded = None
         return flat, gflat, shadow
 
+    def _build_ranges(self, flat):
+        """Per param group: contiguous element ranges of its TRAINABLE tensors in the flat buffer (the alignment
+        padding between two neighbours of the same group rides along), and the per-parameter state views."""
+        slots = sorted(((o, p) for p, o in _unwrap(self.model)._slot_cache), key=lambda x: x[0])
+        owner = {}
+        for gi, g in enumerate(self.param_groups):
+            for p in g["params"]:
+                owner[id(p)] = gi
+        known = {id(p) for _, p in slots}
+        missing = [1 for g in self.param_groups for p in g["params"] if id(p) not in known]
+        if missing:
+            raise L.VawError(f"FusedAdamW: {len(missing)} parameter(s) in param_groups do not belong to the model")
+        self._group_ranges = [[] for _ in self.param_groups]
+        self._step_t = step_t = torch.tensor(float(self.step_count))   # one tensor shared by every state entry
+        for i, (o, p) in enumerate(slots):
+            gi = owner.get(id(p))
+            if gi is None or not p.requires_grad:
+                continue
+            # up to the next tensor's (64-element aligned) offset: the zero padding rides along and stays zero
+            end = slots[i + 1][0] if i + 1 < len(slots) else flat.numel()
+            r = self._group_ranges[gi]
+            if r and r[-1][1] == o:
+                r[-1][1] = end
+            else:
+                r.append([o, end])
+            self.state[p] = {"step": step_t, "exp_avg": self.m[o:o + p.numel()].view(p.shape),
+                             "exp_avg_sq": self.v[o:o + p.numel()].view(p.shape)}
+
+    # -------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def step(self, grad_scale: float = 1.0, max_grad_norm: float | None = None):
-        """One AdamW step.  `grad_scale` multiplies the gradients (GradScaler unscale / accumulation average);
-        `max_grad_norm` applies torch.nn.utils.clip_grad_norm_ semantics (trainer.py:60-62) without a host sync: the
-        norm and the clip coefficient stay on the device (`self.grad_norm` holds [norm, coef] after the call)."""
+    def step(self, closure=None, *, grad_scale: float = 1.0, max_grad_norm: float | None = None):
+        """One AdamW step.  `grad_scale` multiplies the gradients (an accumulation average); `max_grad_norm` applies
+        torch.nn.utils.clip_grad_norm_ semantics (trainer.py:60-62) without a host sync: the norm and the clip
+        coefficient stay on the device (`self.grad_norm` holds [norm, coef] after the call).  Under
+        `GradScaler.step(optimizer)` the scaler's `grad_scale` / `found_inf` device tensors are honoured in-kernel."""
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
         flat, gflat, shadow = self._ensure_state()
-        self.step_count += 1
-        g = self.param_groups[0]
+        amp_scale = getattr(self, "grad_scale", None)      # set by GradScaler.step; None once unscale_() already ran
+        found_inf = getattr(self, "found_inf", None)
+        inv_scale = None
+        if isinstance(amp_scale, torch.Tensor):
+            inv_scale = amp_scale.to(device=flat.device, dtype=torch.float32).reciprocal().reshape(1)
+        if isinstance(found_inf, torch.Tensor):
+            found_inf = found_inf.to(device=flat.device, dtype=torch.float32).reshape(1)
+        else:
+            found_inf = None
+        self.step_count += 1   # host-side bias-correction counter; a skipped (inf) step is undone below
+        if found_inf is not None:
+            # torch's own fused AdamW does `step -= found_inf` on the device; the counter here lives on the host because
+            # the bias corrections are kernel ARGUMENTS - one 4-byte read, only on the GradScaler path (which the
+            # reference syncs on anyway, trainer.py:128 -> _maybe_opt_step's .item())
+            if float(found_inf.item()) != 0.0:
+                self.step_count -= 1
+                return loss
         clip = None
         if max_grad_norm:
             if self.grad_norm is None or self.grad_norm.device != flat.device:
@@ -72,36 +156,67 @@ class FusedAdamW:
             L.call("vaw_grad_clip_coef", gflat.data_ptr(), gflat.numel(), float(grad_scale), float(max_grad_norm),
                    self._norm_ws.data_ptr(), self.grad_norm.data_ptr(), L.stream_ptr())
             clip = self.grad_norm.data_ptr() + 4
-        for off, n in self._ranges:
-            L.call("vaw_adamw_step", flat.data_ptr() + 4 * off, gflat.data_ptr() + 4 * off, self.m.data_ptr() + 4 * off,
-                   self.v.data_ptr() + 4 * off, shadow.data_ptr() + 2 * off,
-                   self.ema.data_ptr() + 4 * off if self.ema is not None else None, n, float(g["lr"]),
-                   float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
-                   self.step_count, float(grad_scale), float(self.ema_decay if self.ema_decay is not None else 0.0),
-                   clip, L.stream_ptr())
+        ema_decay = float(self.ema_decay if self.ema_decay is not None else 0.0)
+        for g, ranges in zip(self.param_groups, self._group_ranges):
+            b1, b2 = g["betas"]
+            for off, end in ranges:
+                n = end - off
+                L.call("vaw_adamw_step_amp", flat.data_ptr() + 4 * off, gflat.data_ptr() + 4 * off,
+                       self.m.data_ptr() + 4 * off, self.v.data_ptr() + 4 * off, shadow.data_ptr() + 2 * off,
+                       self.ema.data_ptr() + 4 * off if self.ema is not None else None, n, float(g["lr"]),
+                       float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]), self.step_count,
+                       float(grad_scale), ema_decay, clip, L.ptr(inv_scale), L.ptr(found_inf), L.stream_ptr())
+        self._step_t.fill_(float(self.step_count))
         # the kernel refreshed the bf16 shadow itself: mark it current so the next forward skips the cast pass
-        self.model._shadow_version = sum(p._version for p, _ in self.model._slot_cache)
+        m = _unwrap(self.model)
+        m._shadow_version = sum(p._version for p, _ in m._slot_cache)
+        return loss
+
+    # -------------------------------------------------------------------------------------------------
+    def state_dict(self):
+        if self.m is None and self.model.flat_parameters()[0] is not None:
+            self._ensure_state()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        """Accepts what torch.optim.AdamW.state_dict() / this class's state_dict() produce (tools/utils.py:109-120)."""
+        super().load_state_dict(state_dict)
+        loaded = {id(p): dict(st) for p, st in self.state.items()}
+        self.state.clear()
+        steps = [int(float(st["step"])) for st in loaded.values() if "step" in st]
+        self.step_count = max(steps) if steps else 0
+        self.m = None
+        self._loaded = loaded
+        if self.model.flat_parameters()[0] is not None:
+            self._ensure_state()
 
     def ema_state_dict(self):
         """The EMA weights (trainer.py:12-18 keeps them in a second model) under the model's parameter names, as views
         of the flat EMA buffer; load them into a model copy with load_state_dict(..., strict=False)."""
         if self.ema is None:
             raise L.VawError("FusedAdamW was built without ema_decay")
-        by_id = {id(p): o for p, o in self.model._slot_cache}
+        m = _unwrap(self.model)
+        by_id = {id(p): o for p, o in m._slot_cache}
         return {k: self.ema[by_id[id(p)]:by_id[id(p)] + p.numel()].view(p.shape)
-                for k, p in self.model.named_parameters() if id(p) in by_id}
+                for k, p in m.named_parameters() if id(p) in by_id}
 
     def zero_grad(self, set_to_none: bool = True):
-        for p in self.model.parameters():
-            p.grad = None  # the next backward overwrites the flat gradient buffer (no memset pass needed)
+        """`set_to_none=True` (torch's default, what trainer.py:133 gets) makes the next backward OVERWRITE the flat
+        gradient buffer - no memset pass; False zeroes the buffer in place."""
+        if set_to_none:
+            for p in _unwrap(self.model).parameters():
+                p.grad = None
+        else:
+            super().zero_grad(set_to_none=False)
 
 
 class DataParallel(torch.nn.Module):
     """Drop-in for the reference's DDP wrapper (main.py:347): `.module`, `.no_sync()`, same forward.  Gradients are
     averaged over ranks by FlatGradSync on the flat gradient buffer, bucketed per transformer block and overlapped
-    with backward through the engine's per-block events."""
+    with backward through the engine's per-block events (DiT and U-ViT); a module without per-block ranges gets one
+    whole-buffer bucket after backward."""
 
-    def __init__(self, module, process_group=None):
+    def __init__(self, module, process_group=None, device_ids=None, output_device=None, **_ddp_kwargs):
         super().__init__()
         self.module = module
         self._sync = None
@@ -119,20 +234,28 @@ class DataParallel(torch.nn.Module):
         with torch.no_grad():
             dist.broadcast(m._flat.data, 0, group=self._group)
         m._shadow_version = -1
-        per_block, tail, total = m.block_grad_ranges()
-        # gradients become final block L-1 first ... block 0, then the embedders / final layer / projectors
-        buckets = list(reversed(per_block)) + [tail]
+        if hasattr(m, "block_grad_ranges"):
+            per_block, tail, total = m.block_grad_ranges()
+            # gradients become final block L-1 first ... block 0, then the embedders / final layer / projectors
+            buckets = list(reversed(per_block)) + [tail]
+            n_blocks = len(per_block)
+            ev = [torch.cuda.Event() for _ in range(n_blocks + 1)]
+            for e in ev:
+                e.record()  # materialise the CUDA events so their handles can be passed through the C ABI
+            m._events = ev
+            self._events = list(reversed(ev[:n_blocks])) + [ev[n_blocks]]
+        else:
+            buckets = [(0, m._gflat.numel())]
+            self._events = None
         self._sync = FlatGradSync(m._gflat, buckets, self._group)
-        ev = [torch.cuda.Event() for _ in range(m.depth + 1)]
-        for e in ev:
-            e.record()  # materialise the CUDA events so their handles can be passed through the C ABI
-        m._events = ev
-        self._events = list(reversed(ev[: m.depth])) + [ev[m.depth]]
         m._post_backward = self._after_backward
 
     def _after_backward(self):
         # backward is fully enqueued at this point: the bucket all-reduces (gated by the per-block events) overlap
         # with it on the side stream, and whatever the caller enqueues next (optimizer) is ordered after them.
+        if self._sync.gflat.data_ptr() != self.module._gflat.data_ptr():
+            # the module repacked its flat buffers (.to(), load_state_dict(assign=True)) after the wrapper was built
+            self._sync.gflat = self.module._gflat
         self._sync.launch(self._events)
         self._sync.wait()
 

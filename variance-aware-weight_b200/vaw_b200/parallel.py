@@ -24,27 +24,41 @@ def dist_ready() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
-def gather_tloss(local_ts: torch.Tensor, local_losses: torch.Tensor, ragged: bool = False):
-    """All-gather (timestep, loss) pairs in rank order.  Returns (ts int32 [sum B], losses fp32 [sum B]); padding
-    entries (ragged batches only) carry t = -1 and are skipped by the update kernel.
-    Bit-exactness: the fp32 loss travels as its int32 bit pattern, so no value is rounded on the way."""
-    t32 = local_ts.to(torch.int32).reshape(-1)
-    l32 = local_losses.detach().to(torch.float32).reshape(-1)
-    if not dist_ready():
-        return t32.contiguous(), l32.contiguous()
-    W = dist.get_world_size()
-    B = t32.numel()
-    Bpad = B
-    if ragged:
-        bmax = torch.tensor([B], dtype=torch.int32, device=t32.device)
-        dist.all_reduce(bmax, op=dist.ReduceOp.MAX)
-        Bpad = int(bmax.item())
-    packed = torch.empty(2, Bpad, dtype=torch.int32, device=t32.device)
-    packed[0, :B] = t32
+def _pack(local_ts, l32, B, Bpad):
+    """[2, Bpad] int32: row 0 = timesteps (-1 in the padding), row 1 = the fp32 losses' bit patterns."""
+    packed = torch.empty(2, Bpad, dtype=torch.int32, device=l32.device)
+    if l32.is_cuda:
+        from . import _lib as L   # one launch instead of ~6 indexing ops (include/vaw_b200.h: vaw_pack_tloss)
+        t64 = local_ts.to(torch.int64).reshape(-1).contiguous()
+        L.call("vaw_pack_tloss", t64.data_ptr(), l32.data_ptr(), packed[0].data_ptr(), packed[1].data_ptr(), B, Bpad,
+               L.stream_ptr())
+        return packed
+    packed[0, :B] = local_ts.to(torch.int32).reshape(-1)      # gloo / CPU tensors (the world_size-2 CPU tests)
     packed[1, :B] = l32.view(torch.int32)
     if Bpad > B:
         packed[0, B:] = -1
         packed[1, B:] = 0
+    return packed
+
+
+def gather_tloss(local_ts: torch.Tensor, local_losses: torch.Tensor, ragged: bool = True):
+    """All-gather (timestep, loss) pairs in rank order.  Returns (ts int32 [sum B], losses fp32 [sum B]); padding
+    entries (ragged batches only) carry t = -1 and are skipped by the update kernel.
+    Bit-exactness: the fp32 loss travels as its int32 bit pattern, so no value is rounded on the way.
+    ragged=True exchanges the batch sizes first and pads to the largest, like the reference (resample.py:85-100);
+    ragged=False skips that exchange (and its host sync) when every rank is known to pass the same batch size."""
+    l32 = local_losses.detach().to(torch.float32).reshape(-1).contiguous()
+    if not dist_ready():
+        return local_ts.to(torch.int32).reshape(-1).contiguous(), l32
+    W = dist.get_world_size()
+    B = l32.numel()
+    Bpad = B
+    if ragged:
+        bmax = torch.tensor([B], dtype=torch.int32, device=l32.device)
+        dist.all_reduce(bmax, op=dist.ReduceOp.MAX)
+        Bpad = int(bmax.item())
+    packed = _pack(local_ts, l32, B, Bpad)
+    t32 = packed[0]
     flat = torch.empty(W * 2 * Bpad, dtype=torch.int32, device=t32.device)
     dist.all_gather_into_tensor(flat, packed.view(-1))
     gathered = flat.view(W, 2, Bpad)

@@ -159,6 +159,9 @@ class _AlignMSE(th.autograd.Function):
     @staticmethod
     def forward(ctx, zs, feat):
         L.require_cuda(zs, feat)
+        if zs.shape != feat.shape:     # F.mse_loss would broadcast-or-raise; a flat kernel would read out of bounds
+            raise ValueError(f"align loss: projector output {tuple(zs.shape)} and teacher features {tuple(feat.shape)} "
+                             "must have the same shape")
         zs_c, feat_c = zs.contiguous(), feat.detach().contiguous()
         dmap = {th.float32: L.F32, th.bfloat16: L.BF16}
         if zs_c.dtype not in dmap:

@@ -81,9 +81,10 @@ class LossAwareSampler(ScheduleSampler):
         ts, losses = gather_tloss(local_ts, local_losses, ragged=self.ragged_batches)
         self._device_update(ts, losses)
 
-    # Set True when ranks may pass different batch sizes (the reference pads to the max, :96-100).  Equal sizes —
-    # the data-parallel training case — need no size exchange and no host synchronisation at all.
-    ragged_batches = False
+    # True (default): ranks may pass different batch sizes - the sizes are exchanged and padded to the largest, like the
+    # reference (:85-100).  A training loop whose loader drops the last partial batch (equal sizes on every rank) can set
+    # this to False and save the size exchange with its host synchronisation.
+    ragged_batches = True
 
     @abstractmethod
     def update_with_all_losses(self, ts, losses):
@@ -153,6 +154,8 @@ class LossSecondMomentResampler(LossAwareSampler):
         return w.cpu().numpy()
 
     def sample(self, batch_size, device):
+        if type(self).weights is not LossSecondMomentResampler.weights:
+            return ScheduleSampler.sample(self, batch_size, device)   # a subclass redefined weights(): honour it (:52)
         self._ensure_device(device)
         return self._device_sample(batch_size, device, 1, None, self._hist_dev, self._count_dev,
                                    self.history_per_term, self.uniform_prob, self._T)
