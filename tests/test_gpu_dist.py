@@ -15,6 +15,58 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
+def _uvit_worker(rank, world, port, q):
+    """U-ViT under the data-parallel wrapper (BASELINE config 4 is defined on 2/4/8 GPUs): per-block buckets gated by the
+    events vaw_uvit_backward_ev records, gradients == single-process gradients of the concatenated batch, and after a
+    FusedAdamW step every rank holds bit-identical parameters."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "variance-aware-weight_b200"), os.path.join(ROOT, "tests")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from gpu_util import relerr
+        from vaw_b200.models.uvit import UViT
+        from vaw_b200.optim import DataParallel, FusedAdamW
+        from vaw_b200.tools import gaussian_diffusion as gd
+        torch.manual_seed(200 + rank)
+        m = UViT(image_size=32, patch_size=4, in_channels=3, embed_dim=128, depth=5, num_heads=2, num_classes=10).to(dev).train()
+        net = DataParallel(m, device_ids=[rank], output_device=rank)
+        assert net._events is not None and len(net._events) == m.num_blocks + 1
+        B = 4
+        g = torch.Generator().manual_seed(9)
+        X = torch.randn(world * B, 3, 32, 32, generator=g); Y = torch.randint(0, 10, (world * B,), generator=g)
+        E = torch.randn(world * B, 3, 32, 32, generator=g); T = torch.randint(0, 1000, (world * B,), generator=g)
+        d = gd.create_gaussian_diffusion(noise_schedule="linear")
+        sl = slice(rank * B, (rank + 1) * B)
+        terms = d.training_losses(net, X[sl].to(dev), None, t=T[sl].to(dev), model_kwargs={"y": Y[sl].to(dev)}, noise=E[sl].to(dev))
+        terms["loss"].mean().backward()
+        torch.cuda.synchronize()
+        dp_grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+        with net.no_sync():
+            for p in m.parameters():
+                p.grad = None
+            allt = d.training_losses(net, X.to(dev), None, t=T.to(dev), model_kwargs={"y": Y.to(dev)}, noise=E.to(dev))
+            allt["loss"].mean().backward()
+        worst = max(relerr(dp_grads[k], p.grad) for k, p in m.named_parameters())
+        assert worst < 2e-3, f"U-ViT DP gradient mismatch {worst}"
+        # one optimizer step on the all-reduced gradients: bit-identical parameters everywhere
+        for k, p in m.named_parameters():
+            p.grad.copy_(dp_grads[k])
+        opt = FusedAdamW(net, lr=1e-3, betas=(0.9, 0.95))
+        opt.step()
+        chk = m._flat.detach().view(torch.int32).to(torch.int64).sum().reshape(1)
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        assert all(torch.equal(allc[0], c) for c in allc), "parameters diverged across ranks after the step"
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
 def _worker(rank, world, port, q):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "variance-aware-weight_b200"), os.path.join(ROOT, "tests")]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -72,16 +124,25 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_data_parallel_parity():
+def _run(target, port_base):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 300
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    port = port_base + os.getpid() % 300
+    procs = [ctx.Process(target=target, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_data_parallel_parity():
+    _run(_worker, 29600)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_uvit_data_parallel_parity():
+    _run(_uvit_worker, 30000)
