@@ -247,6 +247,7 @@ int vaw_cast_f32_bf16(const float* src, void* dst, long long n, vaw_stream_t str
 int vaw_cast_f32_bf16_2d(const float* src, long long lds, void* dst, long long ldd, int rows, int cols,
                          vaw_stream_t stream);
 int vaw_add_bf16_into_f32(const void* src, float* dst, long long n, vaw_stream_t stream);
+int vaw_add_f32(const float* src, float* dst, long long n, vaw_stream_t stream); /* dst += src (n % 4 == 0) */
 
 /* ---- K5: REPA alignment loss, type 'mse' (tools/gaussian_diffusion.py:1011-1013) ------------------------------------
  * loss = mean((zs - feat)^2) (scalar, deterministic two-stage reduction); dzs = gscale * 2 (zs - feat) / n (nullable).

@@ -536,39 +536,69 @@ dit_block_finish_kernel(const float* __restrict__ pA, const float* __restrict__ 
   const int gate_slot = which == 0 ? 5 : 2;
   float t0 = 0.f, t1 = 0.f;
   if (col < D) {
-    for (int n = ny; n < B; n += 16) {
-      // loads of four chunks are issued before they are folded (the kernel is latency-bound: 21 MB in 72-element strides);
-      // the sums still run in chunk order
-      float q0 = 0.f, q1 = 0.f;
-      const float* pn = part + ((long long)n * ch * 2) * D + col;
+    // The kernel is latency-bound (21 MB in 72-element strides, few warps): every thread owns up to four samples per
+    // pass and issues the loads of four chunks of ALL of them (32 independent loads) before folding any, which cuts the
+    // dependent memory round trips per thread from 12 to 3 at B = 64, ch = 9.  Each sample's sum still runs in chunk
+    // order, each thread's sample order is unchanged: results are bit-identical to the one-sample-at-a-time loop.
+    constexpr int S = 4;
+    for (int n0 = ny; n0 < B; n0 += 16 * S) {
+      float q0[S], q1[S];
+      const float* pn[S];
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        q0[j] = 0.f;
+        q1[j] = 0.f;
+        const int n = n0 + 16 * j;
+        pn[j] = part + ((long long)(n < B ? n : n0) * ch * 2) * D + col;
+      }
       int c = 0;
       for (; c + 4 <= ch; c += 4) {
-        float a[4], b[4];
+        float a[S][4], b[S][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          a[u] = __ldg(pn + (long long)(c + u) * 2 * D);
-          b[u] = __ldg(pn + (long long)(c + u) * 2 * D + D);
+        for (int j = 0; j < S; ++j) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            a[j][u] = __ldg(pn[j] + (long long)(c + u) * 2 * D);
+            b[j][u] = __ldg(pn[j] + (long long)(c + u) * 2 * D + D);
+          }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          q0 += a[u];
-          q1 += b[u];
+        for (int j = 0; j < S; ++j) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            q0[j] += a[j][u];
+            q1[j] += b[j][u];
+          }
         }
       }
       for (; c < ch; ++c) {
-        q0 += __ldg(pn + (long long)c * 2 * D);
-        q1 += __ldg(pn + (long long)c * 2 * D + D);
+        float a[S], b[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          a[j] = __ldg(pn[j] + (long long)c * 2 * D);
+          b[j] = __ldg(pn[j] + (long long)c * 2 * D + D);
+        }
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          q0[j] += a[j];
+          q1[j] += b[j];
+        }
       }
-      const long long mo = (long long)n * ldm + col;
-      dmod[mo + (long long)slot1 * D] = q1;
-      dmod_b[mo + (long long)slot1 * D] = __float2bfloat16(q1);
-      t1 += q1;
-      if (slot0 >= 0) {
-        dmod[mo + (long long)slot0 * D] = q0;
-        dmod_b[mo + (long long)slot0 * D] = __float2bfloat16(q0);
-        t0 += q0;
-      } else {
-        t0 += mod[mo + (long long)gate_slot * D] * q0;
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        const int n = n0 + 16 * j;
+        if (n >= B) break;
+        const long long mo = (long long)n * ldm + col;
+        dmod[mo + (long long)slot1 * D] = q1[j];
+        dmod_b[mo + (long long)slot1 * D] = __float2bfloat16(q1[j]);
+        t1 += q1[j];
+        if (slot0 >= 0) {
+          dmod[mo + (long long)slot0 * D] = q0[j];
+          dmod_b[mo + (long long)slot0 * D] = __float2bfloat16(q0[j]);
+          t0 += q0[j];
+        } else {
+          t0 += mod[mo + (long long)gate_slot * D] * q0[j];
+        }
       }
     }
   }

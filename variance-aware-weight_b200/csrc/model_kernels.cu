@@ -415,6 +415,26 @@ extern "C" int vaw_cast_f32_bf16_2d(const float* src, long long lds, void* dst, 
   return VAW_OK;
 }
 
+// dst += src over a flat fp32 buffer (gradient accumulation around a CUDA-graph replay, vaw_b200/graph.py)
+__global__ void __launch_bounds__(256) add_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = ldg_stream_f4(reinterpret_cast<const float4*>(src) + i);
+    float4 d = reinterpret_cast<float4*>(dst)[i];
+    d.x += a.x; d.y += a.y; d.z += a.z; d.w += a.w;
+    reinterpret_cast<float4*>(dst)[i] = d;
+  }
+}
+
+extern "C" int vaw_add_f32(const float* src, float* dst, long long n, cudaStream_t stream) {
+  VAW_CHECK_ARG(src && dst && n >= 0 && n % 4 == 0, "vaw_add_f32: n must be a multiple of 4");
+  if (n == 0) return VAW_OK;
+  add_f32_kernel<<<grid_for(n / 4), 256, 0, stream>>>(src, dst, n);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
 extern "C" int vaw_add_bf16_into_f32(const void* src, float* dst, long long n, cudaStream_t stream) {
   VAW_CHECK_ARG(src && dst && n >= 0 && n % 4 == 0, "vaw_add_bf16_into_f32: n must be a multiple of 4");
   if (n == 0) return VAW_OK;

@@ -58,6 +58,7 @@ _SIGS = {
     "vaw_sampler_sample": [_I, _P, _P, _P, _I, _I, _D, _P, _LL, _P, _P, _P, _P, _P, _P],
     "vaw_sampler_update": [_P, _P, _P, _P, _LL, _I, _I, _P],
     "vaw_pack_tloss": [_P, _P, _P, _P, _LL, _LL, _P],
+    "vaw_add_f32": [_P, _P, _LL, _P],
     "vaw_gemm_bf16": [C.POINTER(GemmArgs), _P],
 }
 

@@ -8,8 +8,10 @@ gradient all-reduce is issued from Python per bucket and is not captured.
 Two things a replay cannot see and that are therefore handled around it: (1) the bf16 weight shadow - the version check
 that triggers the fp32 -> bf16 cast runs in Python, so `__call__` refreshes the shadow before every replay (a no-op after
 FusedAdamW, which writes the shadow itself; one cast pass after torch.optim.AdamW / load_state_dict / an EMA swap);
-(2) overwrite-vs-accumulate is a launch argument of the backward, so gradient accumulation uses a second graph
-(`accumulate=True`), captured on first use.
+(2) overwrite-vs-accumulate is a launch argument of the backward and the graph is captured in overwrite mode, so
+`accumulate=True` (gradient accumulation over micro-batches) saves the flat gradient buffer before the replay and adds
+it back afterwards (vaw_add_f32: one extra pass over the gradients, small next to the step for the models that need a
+graph at all).
 """
 from __future__ import annotations
 
@@ -57,7 +59,7 @@ class GraphedTrainingLosses:
         with torch.cuda.graph(self.graph):
             self._terms = self._run()
         self._terms = {k: v.detach() for k, v in self._terms.items()}
-        self.graph_acc = self._terms_acc = None
+        self._saved_grads = None
 
     def _clear_grads(self):
         for p in self.model.parameters():
@@ -69,17 +71,6 @@ class GraphedTrainingLosses:
                                                noise=self.noise)
         (terms["loss"] * self.w).mean().backward()
         return terms
-
-    @torch.no_grad()
-    def _capture_accumulate(self):
-        bind = getattr(self.model, "_bind_grads", None)
-        if bind is None:
-            raise L.VawError("gradient accumulation across replays needs an engine-backed model")
-        bind()                              # gradients bound -> the backward is captured with accumulate = 1
-        self.graph_acc = torch.cuda.CUDAGraph()
-        with torch.enable_grad(), torch.cuda.graph(self.graph_acc):
-            terms = self._run()
-        self._terms_acc = {k: v.detach() for k, v in terms.items()}
 
     @torch.no_grad()
     def __call__(self, x0, t, w=None, y=None, features=None, noise=None, accumulate=False):
@@ -104,14 +95,19 @@ class GraphedTrainingLosses:
         refresh = getattr(self.model, "_refresh_shadow", None)
         if refresh is not None:
             refresh()                  # weights changed outside FusedAdamW since the last replay -> re-cast the shadow
+        gflat = None
         if accumulate:
-            if self.graph_acc is None:
-                self._capture_accumulate()
-            self.graph_acc.replay()
-            terms = self._terms_acc
-        else:
-            self.graph.replay()
-            terms = self._terms
+            flat_parameters = getattr(self.model, "flat_parameters", None)
+            if flat_parameters is None:
+                raise L.VawError("gradient accumulation across replays needs an engine-backed model")
+            gflat = flat_parameters()[1]
+            if self._saved_grads is None or self._saved_grads.shape != gflat.shape:
+                self._saved_grads = torch.empty_like(gflat)
+            self._saved_grads.copy_(gflat)
+        self.graph.replay()
+        terms = self._terms
+        if gflat is not None:
+            L.call("vaw_add_f32", self._saved_grads.data_ptr(), gflat.data_ptr(), gflat.numel(), L.stream_ptr())
         bind = getattr(self.model, "_bind_grads", None)
         if bind is not None:
             bind()                     # `.grad` views of the flat gradient buffer, as after an eager backward

@@ -56,7 +56,11 @@ class FusedAdamW(torch.optim.Optimizer):
         self._loaded = None
         if params is None:
             params = [p for p in model.parameters() if p.requires_grad]
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        # the param-group keys of torch.optim.AdamW, so that a state_dict saved here loads into torch's AdamW with the
+        # same meaning (without `decoupled_weight_decay` torch's Adam.__setstate__ falls back to L2 decay) and back
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False,
+                                      maximize=False, foreach=None, capturable=False, differentiable=False,
+                                      fused=None, decoupled_weight_decay=True))
 
     # the single-group shorthands the round-1 API exposed
     @property
@@ -158,6 +162,9 @@ class FusedAdamW(torch.optim.Optimizer):
             clip = self.grad_norm.data_ptr() + 4
         ema_decay = float(self.ema_decay if self.ema_decay is not None else 0.0)
         for g, ranges in zip(self.param_groups, self._group_ranges):
+            if g.get("amsgrad") or g.get("maximize") or not g.get("decoupled_weight_decay", True):
+                raise L.VawError("FusedAdamW implements torch.optim.AdamW's default update only "
+                                 "(amsgrad=False, maximize=False, decoupled weight decay)")
             b1, b2 = g["betas"]
             for off, end in ranges:
                 n = end - off
@@ -176,7 +183,12 @@ class FusedAdamW(torch.optim.Optimizer):
     def state_dict(self):
         if self.m is None and self.model.flat_parameters()[0] is not None:
             self._ensure_state()
-        return super().state_dict()
+        sd = super().state_dict()
+        # inside this class every entry shares ONE step tensor; a consumer such as torch.optim.AdamW increments the step
+        # of every parameter separately (`_foreach_add_` over the list), so each entry leaves with its own copy
+        sd["state"] = {k: {kk: (vv.clone() if kk == "step" else vv) for kk, vv in st.items()}
+                       for k, st in sd["state"].items()}
+        return sd
 
     def load_state_dict(self, state_dict):
         """Accepts what torch.optim.AdamW.state_dict() / this class's state_dict() produce (tools/utils.py:109-120)."""
