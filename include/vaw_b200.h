@@ -87,7 +87,8 @@ enum { VAW_VT_LEARNED = 1, VAW_VT_FIXED_SMALL = 2, VAW_VT_FIXED_LARGE = 3, VAW_V
 enum { VAW_RS_DDPM = 0, VAW_RS_DDIM = 1, VAW_RS_DDIM_REVERSE = 2, VAW_RS_MOMENTS = 3 };
 enum { VAW_RT_SQRT_RECIP_AC = 0, VAW_RT_SQRT_RECIPM1_AC, VAW_RT_SQRT_AC, VAW_RT_SQRT_1MAC, VAW_RT_INV_COEF1,
        VAW_RT_COEF2_OVER_COEF1, VAW_RT_COEF1, VAW_RT_COEF2, VAW_RT_LOGVAR /* LEARNED_RANGE: min_log */,
-       VAW_RT_MAX_LOG, VAW_RT_VARIANCE, VAW_RT_AC, VAW_RT_AC_PREV, VAW_RT_AC_NEXT, VAW_RT_ROWS };
+       VAW_RT_MAX_LOG, VAW_RT_VARIANCE, VAW_RT_AC, VAW_RT_AC_PREV, VAW_RT_AC_NEXT,
+       VAW_RT_TRUE_LOGVAR /* posterior_log_variance_clipped whatever the variance type (vaw_vb_terms) */, VAW_RT_ROWS };
 int vaw_reverse_step(const void* model_out, int out_dtype, long long out_stride, const float* x, const float* noise,
                      const long long* t, const float* tab, int T, float* sample, float* pred_xstart, float* mean,
                      float* log_variance, float* variance, int mean_type, int var_type, int mode, float eta, int clip,
@@ -106,6 +107,28 @@ int vaw_wmse_fwd_bwd(const void* out, int out_dtype, const float* x0, const floa
                      const float* tab_alpha, const float* tab_sigma, const float* tab_c0, const float* tab_c1,
                      const float* w_tab, float* mse, float* raw_mse, void* grad_out, const float* gscale_n,
                      float gscale, int mean_type, long long N, long long chw, vaw_stream_t stream);
+
+/* Same with the model output / gradient rows `out_stride` / `grad_stride` values apart (>= chw): the mean channels of a
+ * [N, 2C, H, W] learned-variance output (tools/gaussian_diffusion.py:891 th.split) are read in place. */
+int vaw_wmse_fwd_bwd_strided(const void* out, int out_dtype, long long out_stride, const float* x0, const float* noise,
+                             const long long* t, const float* tab_alpha, const float* tab_sigma, const float* tab_c0,
+                             const float* tab_c1, const float* w_tab, float* mse, float* raw_mse, void* grad_out,
+                             long long grad_stride, const float* gscale_n, float gscale, int mean_type, long long N,
+                             long long chw, vaw_stream_t stream);
+
+/* ---- variational-bound term (learned variance / KL objectives) ----------------------------------------------
+ * Replaces GaussianDiffusion._vb_terms_bpd (tools/gaussian_diffusion.py:775-808: q_posterior_mean_variance :254-276,
+ * p_mean_variance :278-384 with clip_denoised=False, normal_kl and discretized_gaussian_log_likelihood of
+ * tools/losses.py:12-77, mean_flat / ln 2, th.where(t == 0, nll, kl)) as used by training_losses (:862-875 LossType.KL /
+ * RESCALED_KL; :886-906 the term added to the MSE objective with the mean prediction detached) and its autograd
+ * backward.  out: model output, rows out_stride apart, mean channels [chw] followed (LEARNED / LEARNED_RANGE) by the
+ * variance channels [chw].  tab: the [VAW_RT_ROWS][T] table of vaw_reverse_step.  vb[n] = out_scale * bound in bits.
+ * grad (nullable, layout of out, rows grad_stride apart): gscale * gscale_n[n] * d vb[n] / d out; with detach_mean the
+ * mean channels are left untouched (the caller's MSE gradient lives there).  mean_type PREVIOUS_X..VELOCITY. */
+int vaw_vb_terms(const void* out, int out_dtype, long long out_stride, const float* x0, const float* x_t,
+                 const long long* t, const float* tab, int T, float* vb, void* grad, long long grad_stride,
+                 const float* gscale_n, float gscale, int mean_type, int var_type, int detach_mean, float out_scale,
+                 long long N, long long chw, vaw_stream_t stream);
 
 /* y[n,:] = x[n,:] * s[n] — applies a late per-sample upstream gradient to K2's grad_out */
 int vaw_scale_rows(const void* x, const float* s, void* y, int dtype, long long N, long long chw,

@@ -15,6 +15,8 @@ installed; see oracle/ref_stubs/README.md).  Everything written here is an input
                            (fp32 and bf16 model outputs, pinned noise), IntervalCFG combine
     vit_golden.npz         the MoCo-v3 ViT teacher (tiny), preprocess_raw_image, ViT-B/16 position embedding and names
     dit_golden.npz         a tiny DiT (with REPA projector): weights, forward outputs, full training_losses + grads
+    vb_golden.npz          training_losses with a learned variance (LEARNED / LEARNED_RANGE x MSE / RESCALED_MSE / KL /
+                           RESCALED_KL): terms + the gradient w.r.t. the 2C-channel model output
     flow_golden.npz        FlowMatching (tools/gaussian_diffusion.py:1151-1418): interpolant, q_sample, compute_target,
                            training_losses (+ gradient) over every path type x prediction type, the vector / score
                            conversions, and sde_sample (euler / heun) with pinned noise
@@ -371,6 +373,40 @@ def vit_golden():
     print("vit_golden.npz", len(out), "arrays")
 
 
+VB_CASES = [("EPSILON", "LEARNED_RANGE", "MSE", "lambda"), ("EPSILON", "LEARNED", "RESCALED_MSE", "min_snr_5"),
+            ("START_X", "LEARNED_RANGE", "KL", "constant"), ("EPSILON", "LEARNED_RANGE", "RESCALED_KL", "constant"),
+            ("PREVIOUS_X", "LEARNED", "KL", "constant"), ("START_X", "LEARNED_RANGE", "RESCALED_MSE", "lambda")]
+
+
+def vb_golden():
+    out = {}
+    g = torch.Generator().manual_seed(41)
+    x0 = torch.randn(6, 3, 8, 8, generator=g).clamp(-1, 1)
+    x0[:, :, 0, :4] = -1.0          # pixels at the ends of the range take the one-sided branches of the decoder NLL
+    x0[:, :, 1, :4] = 1.0
+    eps = torch.randn(6, 3, 8, 8, generator=g)
+    t = torch.tensor([0, 0, 1, 500, 998, 999])
+    mo = torch.randn(6, 6, 8, 8, generator=g)
+    mo[:, 3:] *= 0.5
+    out.update(x0=x0.numpy(), eps=eps.numpy(), t=t.numpy(), model_out=mo.numpy())
+    for sched in ("linear", "cosine"):
+        for mean, var, loss, wt in VB_CASES:
+            d = rgd.GaussianDiffusion(args=ref_args(weight_type=wt, learn_sigma=True),
+                                      betas=rgd.get_named_beta_schedule(sched, 1000),
+                                      model_mean_type=rgd.ModelMeanType[mean], model_var_type=rgd.ModelVarType[var],
+                                      loss_type=rgd.LossType[loss], rescale_timesteps=True, device="cpu")
+            m = mo.clone().requires_grad_(True)
+            terms = d.training_losses(lambda x, ts, **k: m, x0, None, t=t, noise=eps)
+            terms["loss"].mean().backward()
+            key = f"{sched}::{mean}::{var}::{loss}::{wt}"
+            for k in ("mse", "vb", "loss"):
+                if k in terms:
+                    out[f"{k}::{key}"] = terms[k].detach().float().numpy()
+            out[f"grad::{key}"] = m.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "vb_golden.npz"), **out)
+    print("vb_golden.npz", len(out), "arrays")
+
+
 FLOW_CASES = [("START_X", "lambda"), ("EPSILON", "lambda"), ("EPSILON", "min_snr_5"), ("VELOCITY", "lambda"),
               ("VELOCITY", "min_snr_5"), ("VECTOR", "lambda"), ("VECTOR", "constant"), ("SCORE", "constant")]
 
@@ -436,6 +472,9 @@ def flow_golden():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "vb":
+        vb_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "flow":
         flow_golden()
         sys.exit(0)
@@ -459,3 +498,4 @@ if __name__ == "__main__":
     vit_golden()
     dit_golden()
     flow_golden()
+    vb_golden()

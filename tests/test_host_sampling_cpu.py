@@ -74,7 +74,7 @@ def test_reverse_table_rows_follow_the_header_enum():
     text = open(os.path.join(root, "include", "vaw_b200.h")).read()
     body = re.search(r"enum \{ (VAW_RT_SQRT_RECIP_AC = 0.*?VAW_RT_ROWS) \};", text, re.S).group(1)
     names = [n.split("=")[0].strip() for n in re.sub(r"/\*.*?\*/", "", body, flags=re.S).split(",")]
-    assert names[-1] == "VAW_RT_ROWS" and len(names) == 15
+    assert names[-1] == "VAW_RT_ROWS" and len(names) == 16
     d = gd.create_gaussian_diffusion(noise_schedule="linear", var_type="fixed_small")
     want = {
         "VAW_RT_SQRT_RECIP_AC": d.sqrt_recip_alphas_cumprod, "VAW_RT_SQRT_RECIPM1_AC": d.sqrt_recipm1_alphas_cumprod,
@@ -84,10 +84,10 @@ def test_reverse_table_rows_follow_the_header_enum():
         "VAW_RT_COEF1": d.posterior_mean_coef1, "VAW_RT_COEF2": d.posterior_mean_coef2,
         "VAW_RT_LOGVAR": d.posterior_log_variance_clipped, "VAW_RT_MAX_LOG": np.log(d.betas),
         "VAW_RT_VARIANCE": d.posterior_variance, "VAW_RT_AC": d.alphas_cumprod, "VAW_RT_AC_PREV": d.alphas_cumprod_prev,
-        "VAW_RT_AC_NEXT": d.alphas_cumprod_next,
+        "VAW_RT_AC_NEXT": d.alphas_cumprod_next, "VAW_RT_TRUE_LOGVAR": d.posterior_log_variance_clipped,
     }
     tab = d._reverse_table("cpu").numpy()
-    assert tab.shape == (14, 1000) and tab.dtype == np.float32
+    assert tab.shape == (15, 1000) and tab.dtype == np.float32
     for i, n in enumerate(names[:-1]):
         np.testing.assert_array_equal(tab[i], np.asarray(want[n], dtype=np.float64).astype(np.float32), err_msg=n)
     # FIXED_LARGE swaps in the beta-based variance rows (reference :326-331)
@@ -96,3 +96,4 @@ def test_reverse_table_rows_follow_the_header_enum():
     tl = dl._reverse_table("cpu").numpy()
     np.testing.assert_array_equal(tl[names.index("VAW_RT_VARIANCE")], var.astype(np.float32))
     np.testing.assert_array_equal(tl[names.index("VAW_RT_LOGVAR")], np.log(var).astype(np.float32))
+    np.testing.assert_array_equal(tl[names.index("VAW_RT_TRUE_LOGVAR")], dl.posterior_log_variance_clipped.astype(np.float32))

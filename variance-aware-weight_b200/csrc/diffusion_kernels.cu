@@ -142,8 +142,10 @@ wmse_fwd_bwd_kernel(const OutT* __restrict__ out, const float* __restrict__ x0, 
                     const float* __restrict__ tab_c0, const float* __restrict__ tab_c1,
                     const float* __restrict__ w_tab, float* __restrict__ mse, float* __restrict__ raw_mse,
                     OutT* __restrict__ grad, const float* __restrict__ gscale_n, float gscale, int mean_type,
-                    long long chw, int vec) {
+                    long long chw, int vec, long long out_stride, long long grad_stride) {
   const long long n = blockIdx.x;
+  out += n * (out_stride - chw);     // rows of the model output / gradient may be further apart than chw (the mean
+  if (grad) grad += n * (grad_stride - chw);   // channels of a [N, 2C, H, W] learned-variance output)
   const Coef c = load_coef(t, tab_a, tab_s, tab_c0, tab_c1, n);
   const float w = w_tab ? __ldg(w_tab + (t ? t[n] : n)) : 1.f;
   const float inv = 1.0f / (float)chw;
@@ -555,12 +557,14 @@ extern "C" int vaw_qsample_target(const float* x0, const float* noise, const lon
   return VAW_OK;
 }
 
-extern "C" int vaw_wmse_fwd_bwd(const void* out, int out_dtype, const float* x0, const float* noise,
-                                const long long* t, const float* tab_alpha, const float* tab_sigma,
-                                const float* tab_c0, const float* tab_c1, const float* w_tab, float* mse,
-                                float* raw_mse, void* grad_out, const float* gscale_n, float gscale, int mean_type,
-                                long long N, long long chw, cudaStream_t stream) {
+extern "C" int vaw_wmse_fwd_bwd_strided(const void* out, int out_dtype, long long out_stride, const float* x0,
+                                        const float* noise, const long long* t, const float* tab_alpha,
+                                        const float* tab_sigma, const float* tab_c0, const float* tab_c1,
+                                        const float* w_tab, float* mse, float* raw_mse, void* grad_out,
+                                        long long grad_stride, const float* gscale_n, float gscale, int mean_type,
+                                        long long N, long long chw, cudaStream_t stream) {
   VAW_CHECK_ARG(out && x0 && noise && tab_alpha && tab_sigma && mse, "vaw_wmse_fwd_bwd: null pointer");
+  VAW_CHECK_ARG(out_stride >= chw && (!grad_out || grad_stride >= chw), "vaw_wmse_fwd_bwd: row strides below chw");
   VAW_CHECK_ARG(out_dtype == 0 || out_dtype == 1, "vaw_wmse_fwd_bwd: out_dtype must be 0 (f32) or 1 (bf16)");
   VAW_CHECK_ARG(N >= 0 && chw > 0, "vaw_wmse_fwd_bwd: bad shape N=%lld chw=%lld", N, chw);
   VAW_CHECK_ARG(mean_type >= MT_PREVIOUS_X && mean_type <= MT_SCORE, "vaw_wmse_fwd_bwd: bad mean_type %d", mean_type);
@@ -569,17 +573,27 @@ extern "C" int vaw_wmse_fwd_bwd(const void* out, int out_dtype, const float* x0,
   // buffer may not be); otherwise the scalar path runs
   const uintptr_t f32_ptrs = (uintptr_t)x0 | (uintptr_t)noise;
   const uintptr_t out_ptrs = (uintptr_t)out | (uintptr_t)grad_out;
-  const int vec = (chw % 4 == 0) && ((f32_ptrs & 15) == 0) && ((out_ptrs & (out_dtype == 0 ? 15 : 7)) == 0);
+  const int vec = (chw % 4 == 0) && ((f32_ptrs & 15) == 0) && ((out_ptrs & (out_dtype == 0 ? 15 : 7)) == 0) &&
+                  (out_stride % 4 == 0) && (grad_stride % 4 == 0);
   if (out_dtype == 0)
     wmse_fwd_bwd_kernel<float><<<(unsigned)N, 256, 0, stream>>>(
         (const float*)out, x0, noise, t, tab_alpha, tab_sigma, tab_c0, tab_c1, w_tab, mse, raw_mse, (float*)grad_out,
-        gscale_n, gscale, mean_type, chw, vec);
+        gscale_n, gscale, mean_type, chw, vec, out_stride, grad_out ? grad_stride : chw);
   else
     wmse_fwd_bwd_kernel<bf16><<<(unsigned)N, 256, 0, stream>>>(
         (const bf16*)out, x0, noise, t, tab_alpha, tab_sigma, tab_c0, tab_c1, w_tab, mse, raw_mse, (bf16*)grad_out,
-        gscale_n, gscale, mean_type, chw, vec);
+        gscale_n, gscale, mean_type, chw, vec, out_stride, grad_out ? grad_stride : chw);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
+}
+
+extern "C" int vaw_wmse_fwd_bwd(const void* out, int out_dtype, const float* x0, const float* noise,
+                                const long long* t, const float* tab_alpha, const float* tab_sigma,
+                                const float* tab_c0, const float* tab_c1, const float* w_tab, float* mse,
+                                float* raw_mse, void* grad_out, const float* gscale_n, float gscale, int mean_type,
+                                long long N, long long chw, cudaStream_t stream) {
+  return vaw_wmse_fwd_bwd_strided(out, out_dtype, chw, x0, noise, t, tab_alpha, tab_sigma, tab_c0, tab_c1, w_tab, mse,
+                                  raw_mse, grad_out, chw, gscale_n, gscale, mean_type, N, chw, stream);
 }
 
 extern "C" int vaw_scale_rows(const void* x, const float* s, void* y, int dtype, long long N, long long chw,

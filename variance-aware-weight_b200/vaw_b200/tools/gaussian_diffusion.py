@@ -10,7 +10,8 @@ Host-side mirror of /root/reference/tools/gaussian_diffusion.py for the TRAINING
     create_gaussian_diffusion(**kw)                    alias asked for by the north-star text
 
 training_losses launches K1 (fused q_sample + target), the denoiser, and K2 (fused weighted-MSE forward+backward)
-through the C ABI (include/vaw_b200.h).  Sampling / VLB code of the reference is out of scope.
+through the C ABI (include/vaw_b200.h); with a learned variance or a KL loss type the variational-bound term
+(:775-808, :862-906) is one more fused pass (vaw_vb_terms).
 """
 from __future__ import annotations
 
@@ -221,20 +222,25 @@ class _WeightedMSE(th.autograd.Function):
     @staticmethod
     def forward(ctx, out, x0, noise, t, coef, mean_code):
         # coef = (tab_alpha, tab_sigma, tab_c0, tab_c1, w_tab); tables are [T] when t is given, per-sample [N] otherwise
+        # `out` may carry the variance channels behind the mean channels ([N, 2C, H, W], reference :889-891): the mean
+        # half is read in place through the row stride and the gradient of the variance half is zero
         L.require_cuda(out, x0, noise)
         N = out.shape[0]
-        chw = out[0].numel()
+        chw = x0[0].numel() if N else 1
         o = out.contiguous()
         if o.dtype not in (th.float32, th.bfloat16):
             o = o.float()
+        stride = o[0].numel() if N else chw
         code = L.F32 if o.dtype == th.float32 else L.BF16
         mse = th.empty(N, dtype=th.float32, device=out.device)
         need_grad = out.requires_grad
-        g = th.empty_like(o) if need_grad else None
+        g = None
+        if need_grad:
+            g = th.empty_like(o) if stride == chw else th.zeros_like(o)
         ta, ts, c0, c1, wt = coef
-        L.call("vaw_wmse_fwd_bwd", o.data_ptr(), code, x0.data_ptr(), noise.data_ptr(), L.ptr(t), ta.data_ptr(),
-               ts.data_ptr(), L.ptr(c0), L.ptr(c1), L.ptr(wt), mse.data_ptr(), None, L.ptr(g), None, 1.0,
-               mean_code, N, chw, L.stream_ptr())
+        L.call("vaw_wmse_fwd_bwd_strided", o.data_ptr(), code, stride, x0.data_ptr(), noise.data_ptr(), L.ptr(t),
+               ta.data_ptr(), ts.data_ptr(), L.ptr(c0), L.ptr(c1), L.ptr(wt), mse.data_ptr(), None, L.ptr(g), stride,
+               None, 1.0, mean_code, N, chw, L.stream_ptr())
         ctx.g, ctx.in_dtype, ctx.code = g, out.dtype, code
         return mse
 
@@ -248,6 +254,51 @@ class _WeightedMSE(th.autograd.Function):
         L.call("vaw_scale_rows", g.data_ptr(), s.data_ptr(), out.data_ptr(), ctx.code, g.shape[0], g[0].numel(),
                L.stream_ptr())
         return out.to(ctx.in_dtype), None, None, None, None, None
+
+
+L.register("vaw_wmse_fwd_bwd_strided", [L.C.c_void_p, L.C.c_int, L.C.c_longlong] + [L.C.c_void_p] * 11 +
+           [L.C.c_longlong, L.C.c_void_p, L.C.c_float, L.C.c_int, L.C.c_longlong, L.C.c_longlong, L.C.c_void_p])
+L.register("vaw_vb_terms", [L.C.c_void_p, L.C.c_int, L.C.c_longlong] + [L.C.c_void_p] * 4 + [L.C.c_int] +
+           [L.C.c_void_p] * 2 + [L.C.c_longlong, L.C.c_void_p, L.C.c_float, L.C.c_int, L.C.c_int, L.C.c_int, L.C.c_float,
+                                 L.C.c_longlong, L.C.c_longlong, L.C.c_void_p])
+
+
+class _VbTerm(th.autograd.Function):
+    """terms['vb'] = _vb_terms_bpd(...)["output"] (reference :775-808) with d vb_n / d out from the same pass.
+    detach_mean=True is the learned-variance term of the MSE objective (:896-906: the bound must not move the mean
+    prediction); False is the KL objective (:865-872)."""
+
+    @staticmethod
+    def forward(ctx, out, x0, x_t, t, tab, T, mean_code, var_code, detach_mean, out_scale):
+        L.require_cuda(out, x0, x_t, t)
+        N = out.shape[0]
+        chw = x0[0].numel() if N else 1
+        o = out.contiguous()
+        if o.dtype not in (th.float32, th.bfloat16):
+            o = o.float()
+        stride = o[0].numel() if N else chw
+        code = L.F32 if o.dtype == th.float32 else L.BF16
+        vb = th.empty(N, dtype=th.float32, device=out.device)
+        g = None
+        if out.requires_grad:
+            g = th.zeros_like(o) if detach_mean else th.empty_like(o)
+        if N:
+            L.call("vaw_vb_terms", o.data_ptr(), code, stride, x0.data_ptr(), x_t.data_ptr(), t.data_ptr(),
+                   tab.data_ptr(), T, vb.data_ptr(), L.ptr(g), stride, None, 1.0, mean_code, var_code,
+                   1 if detach_mean else 0, float(out_scale), N, chw, L.stream_ptr())
+        ctx.g, ctx.in_dtype, ctx.code = g, out.dtype, code
+        return vb
+
+    @staticmethod
+    def backward(ctx, gv):
+        g = ctx.g
+        if g is None:
+            return (None,) * 10
+        res = th.empty_like(g)
+        s = gv.float().contiguous()
+        L.call("vaw_scale_rows", g.data_ptr(), s.data_ptr(), res.data_ptr(), ctx.code, g.shape[0], g[0].numel(),
+               L.stream_ptr())
+        return (res.to(ctx.in_dtype),) + (None,) * 9
 
 
 def _f32(x0):
@@ -369,10 +420,6 @@ class GaussianDiffusion:
             noise = th.randn_like(x_start)      # RNG order as in the reference: noise first ...
         if t is None:
             t = self.sample_t(x_start)          # ... then the timesteps (:849-852)
-        if self.loss_type not in (LossType.MSE, LossType.RESCALED_MSE):
-            raise NotImplementedError(f"{self.loss_type}: the variational-bound objectives are outside the B200 hot path")
-        if self.model_var_type in (ModelVarType.LEARNED, ModelVarType.LEARNED_RANGE):
-            raise NotImplementedError("learn_sigma (vb term) is outside the B200 hot path; use a FIXED_* variance type")
         assert noise.shape == x_start.shape
         x0, eps = _f32(x_start), _f32(noise)
         t64 = t.to(th.int64).contiguous()
@@ -385,14 +432,37 @@ class GaussianDiffusion:
             sec_out = raw_output[1] if len(raw_output) > 1 else None
         else:
             model_output = raw_output
-        assert model_output.shape == x_start.shape
+        learned = self.model_var_type in (ModelVarType.LEARNED, ModelVarType.LEARNED_RANGE)
+        B, C = x_t.shape[:2]
+        if learned:
+            assert model_output.shape == (B, C * 2, *x_t.shape[2:])
+        else:
+            assert model_output.shape == x_start.shape
 
         terms = {}
+        if self.loss_type.is_vb():
+            # LossType.KL / RESCALED_KL (:862-875): the bound itself is the loss, gradient through mean AND variance
+            if self.model_mean_type.value > ModelMeanType.VELOCITY.value:
+                raise NotImplementedError(self.model_mean_type)
+            scale = float(self.num_timesteps) if self.loss_type == LossType.RESCALED_KL else 1.0
+            terms["loss"] = _VbTerm.apply(model_output, x0, x_t, t64, self._reverse_table(x0.device), self.num_timesteps,
+                                          self.model_mean_type.value, self.model_var_type.value, False, scale)
+            return terms
+        if self.loss_type not in (LossType.MSE, LossType.RESCALED_MSE):
+            raise NotImplementedError(self.loss_type)
+        if learned:
+            # learn the variance with the variational bound without letting it move the mean prediction (:886-906)
+            scale = self.num_timesteps / 1000.0 if self.loss_type == LossType.RESCALED_MSE else 1.0
+            terms["vb"] = _VbTerm.apply(model_output, x0, x_t, t64, self._reverse_table(x0.device), self.num_timesteps,
+                                        self.model_mean_type.value, self.model_var_type.value, True, scale)
         terms["mse"] = _WeightedMSE.apply(model_output, x0, eps, t64, self._tables(x0.device),
                                           self.model_mean_type.value)
         if self.args.learn_align:
             assert self.gamma > 0, "Gamma must be greater than 0 for align loss"
             terms["align"] = compute_align_loss(features, sec_out, self.args.align_type)
+        if "vb" in terms:                       # :921-926, same precedence as the reference
+            terms["loss"] = terms["mse"] + terms["vb"]
+        elif self.args.learn_align:
             terms["loss"] = terms["mse"] + self.gamma * terms["align"]
         else:
             terms["loss"] = terms["mse"]
@@ -423,7 +493,7 @@ class GaussianDiffusion:
                         self.sqrt_one_minus_alphas_cumprod, 1.0 / self.posterior_mean_coef1,
                         self.posterior_mean_coef2 / self.posterior_mean_coef1, self.posterior_mean_coef1,
                         self.posterior_mean_coef2, logvar, np.log(self.betas), var, self.alphas_cumprod,
-                        self.alphas_cumprod_prev, self.alphas_cumprod_next]
+                        self.alphas_cumprod_prev, self.alphas_cumprod_next, self.posterior_log_variance_clipped]
             tb = th.from_numpy(np.stack([np.asarray(r, dtype=np.float64) for r in rows])).to(device).float().contiguous()
             self._dev_tables[key] = tb
         return tb
