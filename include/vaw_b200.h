@@ -278,6 +278,18 @@ int vaw_add_f32(const float* src, float* dst, long long n, vaw_stream_t stream);
 int vaw_align_mse(const void* zs, int zs_dtype, const void* feat, int feat_dtype, void* dzs, float gscale, long long n,
                   float* part, float* loss, vaw_stream_t stream);
 
+/* Fold the [ceil(M/32) * ceil(N/32)] partials of VAW_EPI_ALIGN_MSE in fixed order: loss = sum / n. */
+int vaw_align_mse_finish(const float* part, long long nparts, long long n, float* loss, vaw_stream_t stream);
+/* dzs = (*g) * 2 (zs - feat) / n with the upstream gradient g a DEVICE scalar (backward of the fused loss). */
+int vaw_align_mse_bwd(const void* zs, int zs_dtype, const void* feat, int feat_dtype, const float* g, void* dzs,
+                      long long n, vaw_stream_t stream);
+/* Row-wise alignment losses over [rows, D] (tools/gaussian_diffusion.py:1008-1019; F.cosine_similarity eps 1e-8,
+ * F.normalize eps 1e-12): kind 0 'cosine': loss = -mean_r cos(feat_r, zs_r); kind 1 'mse_l2': loss = mean over all
+ * elements of (zs_r/|zs_r| - feat_r/|feat_r|)^2.  dzs (nullable, dtype of zs) = gscale * d loss / d zs.  part: scratch
+ * of >= rows floats.  One warp per row, fixed-order two-stage reduction. */
+int vaw_align_rowwise(const void* zs, int zs_dtype, const void* feat, int feat_dtype, int kind, void* dzs, float gscale,
+                      long long rows, int D, float* part, float* loss, vaw_stream_t stream);
+
 /* ---- fused AdamW over the flat parameter buffer (main.py:354 optim.AdamW; trainer.py:12-18 EMA; §8f-1) ----------------
  * One pass: p, m, v updated in place from g * grad_scale; p_bf16 (nullable) refreshed; ema (nullable) updated.        */
 int vaw_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, float* ema, long long n, double lr,
@@ -312,6 +324,11 @@ int vaw_dit_workspace_bytes(const vaw_dit_cfg* cfg, long long* bytes);
  * _scale_timesteps, tools/gaussian_diffusion.py:417-420), y int64 [B]; out bf16 [B,C_out,H,W]; zs bf16 [B*T,z_dim]. */
 int vaw_dit_forward(const vaw_dit_cfg* cfg, const float* P, const void* Pb, void* ws, const float* x_t, const float* t,
                     const long long* y, void* out, void* zs, vaw_stream_t stream);
+/* Same, with the alignment loss fused into the last projector GEMM (VAW_EPI_ALIGN_MSE): feat bf16 [B*T, z_dim] are the
+ * teacher features, align_loss (device scalar) receives mean((zs - feat)^2).  learn_align configs only. */
+int vaw_dit_forward_align(const vaw_dit_cfg* cfg, const float* P, const void* Pb, void* ws, const float* x_t,
+                          const float* t, const long long* y, void* out, void* zs, const void* feat, float* align_loss,
+                          vaw_stream_t stream);
 /* G fp32 gradients (same layout as P); dout bf16 [B,C_out,H,W]; dzs bf16 or NULL; accumulate 0 = overwrite G.
  * events: NULL or depth+1 cudaEvent_t recorded as each block's gradients (last block first) become final.          */
 int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const void* Pb, float* G, void* ws, const void* dout,

@@ -185,6 +185,31 @@ def test_align_loss_kernel_vs_torch():
         gd.compute_align_loss(feat, zs, "nope")
 
 
+@pytest.mark.parametrize("kind", ("cosine", "mse_l2"))
+@pytest.mark.parametrize("dtype,tol_v,tol_g", [(torch.float32, 1e-5, 2e-5), (torch.bfloat16, 1e-5, 6e-3)])
+def test_rowwise_align_losses_vs_torch(kind, dtype, tol_v, tol_g):
+    """compute_align_loss 'cosine' / 'mse_l2' (reference :1008-1017): vaw_align_rowwise against the reference's own
+    expressions (F.cosine_similarity / F.normalize + F.mse_loss) evaluated in fp32 on the same values, value + gradient;
+    REPA shapes [N, 256, 768] and a ragged width."""
+    import torch.nn.functional as F
+    torch.manual_seed(5)
+    for shape in ((4, 256, 768), (3, 17, 50)):
+        zs = torch.randn(*shape, device=DEV).to(dtype).requires_grad_(True)
+        feat = (torch.randn(*shape, device=DEV) * 3).to(dtype)
+        loss = gd.compute_align_loss(feat, zs, kind)
+        (loss * 0.7).backward()
+        z2 = zs.detach().float().requires_grad_(True)
+        f2 = feat.float()
+        ref = (-F.cosine_similarity(f2, z2, dim=-1).mean() if kind == "cosine"
+               else F.mse_loss(F.normalize(z2, dim=-1), F.normalize(f2, dim=-1)))
+        (ref * 0.7).backward()
+        assert abs(loss.item() - ref.item()) <= tol_v * abs(ref.item()) + 1e-7
+        assert zs.grad.dtype == dtype
+        assert ((zs.grad.float() - z2.grad).norm() / z2.grad.norm()).item() < tol_g
+    with pytest.raises(ValueError):
+        gd.compute_align_loss(feat[:, :5], zs, kind)
+
+
 def test_sample_from_latent_bit_exact_and_seeded():
     """tools/trainer.py:21-25: the kernel against the reference golden (bit-exact, explicit noise through the C ABI) and
     the Python mirror against the same formula in torch with the same generator state."""

@@ -130,3 +130,36 @@ def test_workspace_guard_and_label_dropout():
     drop, _ = m(x, t, y, force_drop_ids=torch.ones(2, device=DEV))
     null, _ = m(x, t, torch.full((2,), 10, device=DEV))
     assert torch.equal(drop, null)    # dropped labels use the extra embedding row (dit.py:94-103)
+
+
+def test_alignment_loss_fused_into_the_projector_gemm():
+    """REPA, align_type 'mse' with bf16 teacher features: training_losses hands the features to the engine, the last
+    projector GEMM's epilogue accumulates Sigma (zs - feat)^2 (VAW_EPI_ALIGN_MSE) and the backward is one pass.  Must
+    agree with the unfused path (separate vaw_align_mse kernel; taken when the features are fp32) on the same values."""
+    torch.manual_seed(3)
+    B, img, zd = 4, 16, 48
+    m = DiT(image_size=img, patch_size=2, in_channels=4, hidden_size=128, depth=2, num_heads=2, class_dropout_prob=0.0,
+            num_classes=10, learn_align=True, encoder_depth=1, z_dims=zd, projector_dim=64).to(DEV).train()
+    dezero(m)
+    T = (img // 2) ** 2
+    d = gd.create_gaussian_diffusion(noise_schedule="cosine", mean_type="epsilon", weight_type="lambda", learn_align=True,
+                                     gamma=0.5)
+    x0 = torch.randn(B, 4, img, img, device=DEV); eps = torch.randn_like(x0)
+    t = torch.randint(0, 1000, (B,), device=DEV); y = torch.randint(0, 10, (B,), device=DEV)
+    feats = torch.randn(B, T, zd, device=DEV).bfloat16()
+    terms = d.training_losses(m, x0, feats, t=t, model_kwargs={"y": y}, noise=eps)          # fused (bf16 features)
+    terms["loss"].mean().backward()
+    g_fused = m._gflat.clone()
+    for p in m.parameters():
+        p.grad = None
+    ref = d.training_losses(m, x0, feats.float(), t=t, model_kwargs={"y": y}, noise=eps)    # unfused (fp32 features)
+    ref["loss"].mean().backward()
+    assert abs(terms["align"].item() - ref["align"].item()) <= 1e-5 * abs(ref["align"].item())
+    assert torch.equal(terms["mse"], ref["mse"])
+    assert relerr(g_fused, m._gflat) < 5e-3                       # bf16 roundings of d zs differ between the two paths
+    # an oracle check of the fused value itself
+    zs = m(d.q_sample(x0, t, eps), d._scale_timesteps(t), y)[1]
+    want = torch.nn.functional.mse_loss(zs.float(), feats.float())
+    assert abs(terms["align"].item() - want.item()) <= 1e-5 * want.item()
+    with pytest.raises(ValueError):
+        m(x0, t.float(), y, align_target=feats[:, :5])

@@ -168,6 +168,22 @@ def test_tma_store_epilogues_every_tile_config(tile_n, cta_group, M, N, K):
         o.fill_(float("nan"))
         _rg(A, B, 0, 0, M, N, K, epi, out=o, aux=aux, tile_n=tile_n, cta_group=cta_group)
         assert relerr(o, (acc - bias) * h.grad) < 4e-3, epi
+    # REPA alignment loss accumulated in the epilogue: zs out, one partial per 32 x 32 block of (zs - feat)^2
+    if N % 4 == 0:
+        feat = torch.randn(M, N, device=DEV).bfloat16()
+        nrb, ncb = (M + 31) // 32, (N + 31) // 32
+        part = torch.full((nrb * ncb,), float("nan"), device=DEV)
+        o.fill_(float("nan"))
+        _rg(A, B, 0, 0, M, N, K, L.EPI_ALIGN_MSE, out=o, out2=part, bias=bias, aux=feat, tile_n=tile_n, cta_group=cta_group)
+        assert relerr(o, acc) < 3e-3
+        d2 = (o.float() - feat.float()) ** 2                      # the loss sees the bf16 zs that was written
+        pad = torch.zeros(nrb * 32, ncb * 32, device=DEV)
+        pad[:M, :N] = d2
+        want = pad.view(nrb, 32, ncb, 32).sum(dim=(1, 3)).reshape(-1)
+        torch.testing.assert_close(part, want, rtol=1e-5, atol=1e-6)
+        part2 = torch.empty_like(part)
+        _rg(A, B, 0, 0, M, N, K, L.EPI_ALIGN_MSE, out=o, out2=part2, bias=bias, aux=feat, tile_n=tile_n, cta_group=cta_group)
+        assert torch.equal(part, part2)                           # fixed reduction tree: bit-reproducible
 
 
 @pytest.mark.parametrize("epi", ["bf16", "gelu", "dgelu", "gate_res", "f32"])

@@ -81,6 +81,8 @@ struct Ws {
   bf16 *dy, *dh, *dqkv, *d_o, *dxn, *dtok, *dz, *dxa;
   float* attn_delta;   // [B*H*T] rowsum(dO*O) scratch of the attention backward
   float *part, *part_a2, *part_b, *part_c, *part_d, *cpart, *dmod_all, *dmod_final, *dcs, *dc;
+  float* align_part;   // [ceil(M/32) * ceil(z_dim/32)] partial sums of the fused alignment loss (VAW_EPI_ALIGN_MSE)
+  long long align_parts;
   bf16 *dmod_all_b, *dmod_final_b, *dc_b, *dth;
   float* split_ws;
   long long split_elems;
@@ -165,6 +167,8 @@ void carve(const vaw_dit_cfg& c, void* base, Ws& w) {
   w.dth = k.take<bf16>(B * D);
   w.split_elems = (long long)vaw_num_sms() * 128 * 256;  // one 128x256 fp32 slab per SM
   w.split_ws = k.take<float>(w.split_elems);
+  w.align_parts = c.learn_align ? ((M + 31) / 32) * ((c.z_dim + 31) / 32) : 0;
+  w.align_part = k.take<float>(w.align_parts);
   w.bytes = k.cur;
 }
 
@@ -213,8 +217,9 @@ extern "C" int vaw_dit_workspace_bytes(const vaw_dit_cfg* cfg, long long* bytes)
 
 // x_t [B,C_in,H,W] fp32, t [B] fp32 (already scaled, gaussian_diffusion.py:417-420), y [B] int64 (may be null when
 // table_rows == 0) -> out [B,C_out,H,W] bf16 and, with learn_align, zs [B*T, z_dim] bf16.
-extern "C" int vaw_dit_forward(const vaw_dit_cfg* cfg, const float* P, const void* Pb_, void* ws_, const float* x_t,
-                               const float* t, const long long* y, void* out, void* zs, cudaStream_t s) {
+static int dit_forward_impl(const vaw_dit_cfg* cfg, const float* P, const void* Pb_, void* ws_, const float* x_t,
+                            const float* t, const long long* y, void* out, void* zs, const void* feat, float* align_loss,
+                            cudaStream_t s) {
   TRY(check_cfg(cfg));
   VAW_CHECK_ARG(P && Pb_ && ws_ && x_t && t && out, "vaw_dit_forward: null pointer");
   const vaw_dit_cfg& c = *cfg;
@@ -270,7 +275,15 @@ extern "C" int vaw_dit_forward(const vaw_dit_cfg* cfg, const float* P, const voi
               .out(w.z1_pre, w.z1).bias(P + L.off[P_PR0_B]).run(s));
       TRY(G(w.z1, pd, 0, Pb + L.off[P_PR2_W], pd, 0, M, pd, pd, VAW_EPI_SILU)
               .out(w.z2_pre, w.z2).bias(P + L.off[P_PR2_B]).run(s));
-      TRY(G(w.z2, pd, 0, Pb + L.off[P_PR4_W], pd, 0, M, zd, pd, VAW_EPI_BF16).out(zs).bias(P + L.off[P_PR4_B]).run(s));
+      if (feat) {
+        // REPA: Sigma (zs - feat)^2 is accumulated in the epilogue that produces zs (north-star piece 5); the partials
+        // are folded in fixed order by one small launch
+        TRY(G(w.z2, pd, 0, Pb + L.off[P_PR4_W], pd, 0, M, zd, pd, VAW_EPI_ALIGN_MSE)
+                .out(zs, w.align_part).bias(P + L.off[P_PR4_B]).aux(feat).run(s));
+        TRY(vaw_align_mse_finish(w.align_part, w.align_parts, (long long)M * zd, align_loss, s));
+      } else {
+        TRY(G(w.z2, pd, 0, Pb + L.off[P_PR4_W], pd, 0, M, zd, pd, VAW_EPI_BF16).out(zs).bias(P + L.off[P_PR4_B]).run(s));
+      }
     }
   }
   // final layer: LN -> modulate -> linear -> unpatchify
@@ -280,6 +293,21 @@ extern "C" int vaw_dit_forward(const vaw_dit_cfg* cfg, const float* P, const voi
   TRY(G(w.xnf, D, 0, Pb + L.off[P_FLIN_W], D, 0, M, PPC, D, VAW_EPI_BF16).out(w.out_tok).bias(P + L.off[P_FLIN_B]).run(s));
   TRY(vaw_unpatchify(w.out_tok, out, 1, B, c.C_out, c.img_h, c.img_w, c.P, 1, s));
   return VAW_OK;
+}
+
+extern "C" int vaw_dit_forward(const vaw_dit_cfg* cfg, const float* P, const void* Pb_, void* ws_, const float* x_t,
+                               const float* t, const long long* y, void* out, void* zs, cudaStream_t s) {
+  return dit_forward_impl(cfg, P, Pb_, ws_, x_t, t, y, out, zs, nullptr, nullptr, s);
+}
+
+extern "C" int vaw_dit_forward_align(const vaw_dit_cfg* cfg, const float* P, const void* Pb_, void* ws_,
+                                     const float* x_t, const float* t, const long long* y, void* out, void* zs,
+                                     const void* feat, float* align_loss, cudaStream_t s) {
+  VAW_CHECK_ARG(cfg && cfg->learn_align && feat && align_loss,
+                "vaw_dit_forward_align: needs a learn_align config, teacher features and a loss output");
+  VAW_CHECK_ARG((reinterpret_cast<uintptr_t>(feat) & 15) == 0 && cfg->z_dim % 8 == 0,
+                "vaw_dit_forward_align: features must be 16-byte aligned bf16 [B*T, z_dim]");
+  return dit_forward_impl(cfg, P, Pb_, ws_, x_t, t, y, out, zs, feat, align_loss, s);
 }
 
 // dout [B,C_out,H,W] bf16 (gradient of the model output), dzs [B*T, z_dim] bf16 or null.

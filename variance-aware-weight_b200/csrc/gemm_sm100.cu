@@ -49,7 +49,9 @@ enum : int {
   EPI_DGELU_ERF = 7,   // out_bf16 = acc * gelu_erf'(aux)
   EPI_SILU = 8,        // out_bf16 = pre ; out2_bf16 = silu(pre)           (REPA projector)
   EPI_DSILU = 9,       // out_bf16 = acc * silu'(aux)
-  EPI_COUNT = 10
+  EPI_ALIGN_MSE = 10,  // out_bf16 = zs = acc + bias ; out2_f32[(row / 32) * ceil(N / 32) + col / 32] = sum over the
+                       // 32 x 32 block of (zs - aux)^2: the REPA alignment loss accumulated where zs is produced
+  EPI_COUNT = 11
 };
 
 struct EpiParams {
@@ -350,7 +352,8 @@ template <int EPI>
 struct TmaEpi {
   // aux: the d-activation epilogues also READ a bf16 tile (the saved pre-activation); it arrives by TMA in the same box
   // geometry, one chunk ahead of the math (om.c2 is then the map of that input)
-  static constexpr bool aux = (EPI == EPI_DGELU_TANH || EPI == EPI_DGELU_ERF || EPI == EPI_DSILU);
+  static constexpr bool aux = (EPI == EPI_DGELU_TANH || EPI == EPI_DGELU_ERF || EPI == EPI_DSILU ||
+                               EPI == EPI_ALIGN_MSE);
   static constexpr bool value =
       (EPI == EPI_BF16 || EPI == EPI_GELU_TANH || EPI == EPI_GELU_ERF || EPI == EPI_SILU) || aux;
   static constexpr bool two = (EPI == EPI_GELU_TANH || EPI == EPI_GELU_ERF || EPI == EPI_SILU);
@@ -593,6 +596,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           tmem_ld_wait();
           const int col0 = wk.n0 + c * 32;
           uint32_t pk[16], ak[16];
+          [[maybe_unused]] float align_sq = 0.f;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -601,7 +605,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                    make_float2(b.x, b.y));
             float2 hi = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])),
                                    make_float2(b.z, b.w));
-            if constexpr (TmaEpi<EPI>::aux) {   // dX = dY * act'(saved pre-activation)
+            if constexpr (EPI == EPI_ALIGN_MSE) {
+              // zs leaves as bf16; the loss sees the rounded value, like F.mse_loss on the bf16 projector output
+              const float2 f0 = unpack_bf16(ax[2 * j]), f1 = unpack_bf16(ax[2 * j + 1]);
+              const float2 z0 = unpack_bf16(pack_bf16(lo.x, lo.y)), z1 = unpack_bf16(pack_bf16(hi.x, hi.y));
+              if (col0 + 4 * j < p.N) {   // N % 4 == 0; columns past N hold bias-free zero padding on both sides anyway
+                const float d0 = z0.x - f0.x, d1 = z0.y - f0.y, d2 = z1.x - f1.x, d3 = z1.y - f1.y;
+                align_sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+              }
+            } else if constexpr (TmaEpi<EPI>::aux) {   // dX = dY * act'(saved pre-activation)
               const float2 h0 = unpack_bf16(ax[2 * j]), h1 = unpack_bf16(ax[2 * j + 1]);
               if constexpr (EPI == EPI_DGELU_TANH) {
                 lo = __fmul2_rn(lo, gelu_tanh_grad_f2(h0));
@@ -631,6 +643,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 ak[2 * j + 1] = pack_bf16(silu_f(h1.x), silu_f(h1.y));
               }
             }
+          }
+          if constexpr (EPI == EPI_ALIGN_MSE) {
+            // one partial per (32-row group, 32-column chunk), written by exactly one warp: the fold order of the loss
+            // does not depend on the tile configuration (deterministic)
+            if (grow + lane >= p.M) align_sq = 0.f;
+            align_sq = warp_sum(align_sq);
+            if (lane == 0 && grow < p.M)
+              reinterpret_cast<float*>(p.out2)[(long long)(grow >> 5) * ((p.N + 31) >> 5) + (col0 >> 5)] = align_sq;
           }
           if constexpr (TmaEpi<EPI>::aux) slot = 1;
           uint8_t* s0 = stg_b + (TmaEpi<EPI>::two ? 0 : slot * 2048) + lane * 64;
@@ -984,6 +1004,7 @@ int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     case EPI_DGELU_ERF: return launch_gemm<BN, EPI_DGELU_ERF, PAIR>(tmA, tmB, om, p, s);
     case EPI_SILU: return launch_gemm<BN, EPI_SILU, PAIR>(tmA, tmB, om, p, s);
     case EPI_DSILU: return launch_gemm<BN, EPI_DSILU, PAIR>(tmA, tmB, om, p, s);
+    case EPI_ALIGN_MSE: return launch_gemm<BN, EPI_ALIGN_MSE, PAIR>(tmA, tmB, om, p, s);
   }
   vaw_set_error("vaw_gemm_bf16: unknown epilogue %d", epi);
   return VAW_ERR_INVALID;
@@ -1024,7 +1045,7 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
   VAW_CHECK_ARG(!needs_out2 || a->out2, "vaw_gemm_bf16: missing out2");
   VAW_CHECK_ARG(!(epi == EPI_GATE_RES || epi == EPI_RES) || a->resid, "vaw_gemm_bf16: missing resid");
   VAW_CHECK_ARG(epi != EPI_GATE_RES || (a->gate && a->rows_per_sample > 0), "vaw_gemm_bf16: missing gate");
-  VAW_CHECK_ARG(!(epi == EPI_DGELU_TANH || epi == EPI_DGELU_ERF || epi == EPI_DSILU) || a->aux,
+  VAW_CHECK_ARG(!(epi == EPI_DGELU_TANH || epi == EPI_DGELU_ERF || epi == EPI_DSILU || epi == EPI_ALIGN_MSE) || a->aux,
                 "vaw_gemm_bf16: missing aux");
   VAW_CHECK_ARG(a->cta_group >= 0 && a->cta_group <= 2, "vaw_gemm_bf16: cta_group must be 0 (auto), 1 or 2");
 
@@ -1151,7 +1172,8 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
     if (rc) return rc;
     p.tma_res = 1;
   }
-  const bool aux_epi = (epi == EPI_DGELU_TANH || epi == EPI_DGELU_ERF || epi == EPI_DSILU);
+  const bool aux_epi = (epi == EPI_DGELU_TANH || epi == EPI_DGELU_ERF || epi == EPI_DSILU || epi == EPI_ALIGN_MSE);
+  VAW_CHECK_ARG(epi != EPI_ALIGN_MSE || (a->out2 && a->N % 4 == 0), "vaw_gemm_bf16: EPI_ALIGN_MSE needs out2 (partials)");
   if (aux_epi) {
     VAW_CHECK_ARG(a->aux && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0 && a->out &&
                       (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,

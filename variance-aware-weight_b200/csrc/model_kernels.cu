@@ -2,6 +2,8 @@
 // dtype casts of the flat parameter buffer, the fused AdamW(+bf16 shadow) update, and the REPA alignment loss.
 // Reference: models/dit.py:41-110 (embedders), :243-256 (unpatchify), timm PatchEmbed,
 // models/uvit.py:21-52, tools/gaussian_diffusion.py:1007-1013 (compute_align_loss, 'mse'), main.py:354 (AdamW).
+#include <type_traits>
+
 #include "vaw_common.cuh"
 
 namespace {
@@ -310,6 +312,67 @@ __global__ void align_mse_stage2(const float* __restrict__ part, int nparts, flo
   if (threadIdx.x == 0) *loss = red[0] * inv_n;
 }
 
+// backward of the fused alignment loss: dzs = g * 2 (zs - feat) / n, g a device scalar
+template <typename ZT, typename FT>
+__global__ void __launch_bounds__(256)
+align_mse_bwd_kernel(const ZT* __restrict__ zs, const FT* __restrict__ feat, const float* __restrict__ g,
+                     ZT* __restrict__ dzs, float two_over_n, long long n) {
+  const float coef = __ldg(g) * two_over_n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dzs[i] = (ZT)(coef * ((float)zs[i] - (float)feat[i]));
+}
+
+// Row-wise alignment losses (gaussian_diffusion.py:1008-1019), one warp per row of D values:
+//   kind 0 'cosine': c = <t, o> / (max(|t|, 1e-8) max(|o|, 1e-8)); row value -c;          d/do = -(t / (|t||o|) - c o / |o|^2)
+//   kind 1 'mse_l2': row value |o/|o| - t/|t||^2 (the mean runs over rows * D elements);  d/do = (2 / |o|)(oh <oh, th> - th)
+template <typename ZT, typename FT>
+__global__ void __launch_bounds__(256)
+align_rowwise_kernel(const ZT* __restrict__ zs, const FT* __restrict__ feat, int kind, ZT* __restrict__ dzs,
+                     float gcoef, long long rows, int D, float* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const ZT* o = zs + r * D;
+  const FT* t = feat + r * D;
+  float dot = 0.f, oo = 0.f, tt = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    const float a = (float)o[i], b = (float)t[i];
+    dot += a * b;
+    oo += a * a;
+    tt += b * b;
+  }
+  dot = warp_sum(dot);
+  oo = warp_sum(oo);
+  tt = warp_sum(tt);
+  const float eps = kind == 0 ? 1e-8f : 1e-12f;
+  const float no = fmaxf(sqrtf(oo), eps), nt = fmaxf(sqrtf(tt), eps);
+  const float c = dot / (no * nt);
+  float val, ko, kt;   // gradient row = ko * o + kt * t
+  if (kind == 0) {
+    val = -c;
+    ko = c / (no * no);
+    kt = -1.f / (no * nt);
+  } else {
+    // sum_i (o_i / |o| - t_i / |t|)^2, accumulated element by element like the reference (the closed form 2 - 2c
+    // cancels catastrophically once the projector has learned to align)
+    const float io = 1.f / no, it = 1.f / nt;
+    float acc = 0.f;
+    for (int i = lane; i < D; i += 32) {
+      const float d = (float)o[i] * io - (float)t[i] * it;
+      acc += d * d;
+    }
+    val = warp_sum(acc);
+    ko = 2.f * c / (no * no);
+    kt = -2.f / (no * nt);
+  }
+  if (lane == 0) part[r] = val;
+  if (dzs) {
+    ZT* d = dzs + r * D;
+    for (int i = lane; i < D; i += 32) d[i] = (ZT)(gcoef * (ko * (float)o[i] + kt * (float)t[i]));
+  }
+}
+
 inline unsigned grid_for(long long work, int per_block = 256) {
   long long b = (work + per_block - 1) / per_block;
   const long long cap = (long long)vaw_num_sms() * 16;
@@ -484,6 +547,62 @@ extern "C" int vaw_grad_clip_coef(const float* g, long long n, double grad_scale
   grad_sqnorm_stage1<<<kNormBlocks, 256, 0, stream>>>(g, n, (float)grad_scale, part);
   VAW_LAUNCH_CHECK();
   grad_sqnorm_stage2<<<1, 256, 0, stream>>>(part, (float)max_norm, out);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+extern "C" int vaw_align_mse_finish(const float* part, long long nparts, long long n, float* loss, cudaStream_t stream) {
+  VAW_CHECK_ARG(part && loss && nparts > 0 && nparts < (1LL << 31) && n > 0, "vaw_align_mse_finish: bad arguments");
+  align_mse_stage2<<<1, 256, 0, stream>>>(part, (int)nparts, 1.0f / (float)n, loss);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+#define TRY_RC(expr) do { int _rc = (expr); if (_rc != VAW_OK) return _rc; } while (0)
+
+namespace {
+// dtype dispatch of the (zs, feat) pairs: F is called with two typed null pointers that only carry the element types
+template <typename F>
+int dispatch_zf(int zs_dtype, int feat_dtype, F&& f) {
+  if (zs_dtype == 1 && feat_dtype == 1) f((bf16*)nullptr, (bf16*)nullptr);
+  else if (zs_dtype == 1 && feat_dtype == 0) f((bf16*)nullptr, (float*)nullptr);
+  else if (zs_dtype == 0 && feat_dtype == 0) f((float*)nullptr, (float*)nullptr);
+  else if (zs_dtype == 0 && feat_dtype == 1) f((float*)nullptr, (bf16*)nullptr);
+  else { vaw_set_error("bad dtypes %d %d", zs_dtype, feat_dtype); return VAW_ERR_INVALID; }
+  return VAW_OK;
+}
+}  // namespace
+
+extern "C" int vaw_align_mse_bwd(const void* zs, int zs_dtype, const void* feat, int feat_dtype, const float* g,
+                                 void* dzs, long long n, cudaStream_t stream) {
+  VAW_CHECK_ARG(zs && feat && g && dzs && n > 0, "vaw_align_mse_bwd: bad arguments");
+  const unsigned blocks = grid_for(n);
+  const float k = 2.f / (float)n;
+  TRY_RC(dispatch_zf(zs_dtype, feat_dtype, [&](auto* z, auto* f) {
+    using ZT = std::remove_pointer_t<decltype(z)>;
+    using FT = std::remove_pointer_t<decltype(f)>;
+    align_mse_bwd_kernel<ZT, FT><<<blocks, 256, 0, stream>>>((const ZT*)zs, (const FT*)feat, g, (ZT*)dzs, k, n);
+  }));
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+extern "C" int vaw_align_rowwise(const void* zs, int zs_dtype, const void* feat, int feat_dtype, int kind, void* dzs,
+                                 float gscale, long long rows, int D, float* part, float* loss, cudaStream_t stream) {
+  VAW_CHECK_ARG(zs && feat && part && loss && rows > 0 && rows < (1LL << 31) && D > 0 && (kind == 0 || kind == 1),
+                "vaw_align_rowwise: bad arguments");
+  const unsigned blocks = (unsigned)((rows + 7) / 8);
+  // 'cosine' averages over rows, 'mse_l2' over rows * D elements
+  const float inv = kind == 0 ? 1.0f / (float)rows : 1.0f / ((float)rows * (float)D);
+  const float gcoef = gscale * inv;
+  TRY_RC(dispatch_zf(zs_dtype, feat_dtype, [&](auto* z, auto* f) {
+    using ZT = std::remove_pointer_t<decltype(z)>;
+    using FT = std::remove_pointer_t<decltype(f)>;
+    align_rowwise_kernel<ZT, FT><<<blocks, 256, 0, stream>>>((const ZT*)zs, (const FT*)feat, kind, (ZT*)dzs, gcoef, rows,
+                                                             D, part);
+  }));
+  VAW_LAUNCH_CHECK();
+  align_mse_stage2<<<1, 256, 0, stream>>>(part, (int)rows, inv, loss);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }

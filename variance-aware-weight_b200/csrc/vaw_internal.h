@@ -29,7 +29,8 @@ struct vaw_gemm_args {
 
 enum : int {
   VAW_EPI_BF16 = 0, VAW_EPI_F32 = 1, VAW_EPI_GELU_TANH = 2, VAW_EPI_GELU_ERF = 3, VAW_EPI_GATE_RES = 4,
-  VAW_EPI_RES = 5, VAW_EPI_DGELU_TANH = 6, VAW_EPI_DGELU_ERF = 7, VAW_EPI_SILU = 8, VAW_EPI_DSILU = 9
+  VAW_EPI_RES = 5, VAW_EPI_DGELU_TANH = 6, VAW_EPI_DGELU_ERF = 7, VAW_EPI_SILU = 8, VAW_EPI_DSILU = 9,
+  VAW_EPI_ALIGN_MSE = 10
 };
 
 // U-ViT geometry (models/uvit.py:139-205)
@@ -54,6 +55,7 @@ int vaw_attn_bwd_sm100(const void* qkv, const void* o, const void* d_o, const fl
                        int B, int T, int H, int head_dim, cudaStream_t stream);
 
 extern "C" {
+int vaw_align_mse_finish(const float* part, long long nparts, long long n, float* loss, cudaStream_t stream);
 int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream);
 int vaw_attn_fwd(const void* qkv, void* o, float* lse2, int B, int T, int H, int head_dim, cudaStream_t stream);
 int vaw_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, int B, int T, int H,

@@ -22,7 +22,7 @@ RS_DDPM, RS_DDIM, RS_DDIM_REVERSE, RS_MOMENTS = range(4)
 W_CONSTANT, W_LAMBDA, W_MIN_SNR, W_MAX_SNR, W_DEBIAS, W_MIN_DEBIAS, W_MAX_DEBIAS, W_P2, W_TRUNC_SNR, W_SNR, W_INV_SNR = range(11)
 
 (EPI_BF16, EPI_F32, EPI_GELU_TANH, EPI_GELU_ERF, EPI_GATE_RES, EPI_RES, EPI_DGELU_TANH, EPI_DGELU_ERF, EPI_SILU,
- EPI_DSILU) = range(10)
+ EPI_DSILU, EPI_ALIGN_MSE) = range(11)
 
 
 class VawError(RuntimeError):

@@ -27,6 +27,7 @@ class DiTCfg(C.Structure):
 L.register("vaw_dit_param_layout", [C.POINTER(DiTCfg), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p])
 L.register("vaw_dit_workspace_bytes", [C.POINTER(DiTCfg), C.c_void_p])
 L.register("vaw_dit_forward", [C.POINTER(DiTCfg)] + [C.c_void_p] * 9)
+L.register("vaw_dit_forward_align", [C.POINTER(DiTCfg)] + [C.c_void_p] * 11)
 L.register("vaw_dit_backward", [C.POINTER(DiTCfg)] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_void_p])
 L.register("vaw_cast_f32_bf16", [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p])
 
@@ -50,6 +51,10 @@ def sincos_pos_embed_2d(dim, grid):
 
 
 class DiT(FlatEngineModule):
+    # training_losses may hand the teacher features to forward (`align_target=`): the 'mse' alignment loss is then
+    # accumulated in the epilogue of the last projector GEMM and attached to the returned zs (`zs._vaw_align`)
+    supports_fused_align = True
+
     def __init__(self, image_size=32, patch_size=2, in_channels=4, hidden_size=1152, depth=28, num_heads=16,
                  mlp_ratio=4.0, class_dropout_prob=0.1, num_classes=1000, learn_sigma=False, learn_align=False,
                  encoder_depth=8, z_dims=768, projector_dim=2048):
@@ -225,7 +230,7 @@ class DiT(FlatEngineModule):
             drop = force_drop_ids == 1
         return torch.where(drop, self.num_classes, labels)
 
-    def forward(self, x, t, y=None, force_drop_ids=None, **kwargs):
+    def forward(self, x, t, y=None, force_drop_ids=None, align_target=None, **kwargs):
         if not x.is_cuda:
             raise L.VawError("vaw_b200.models.DiT runs on CUDA only (no CPU fallback)")
         if x.shape[1:] != (self.in_channels, self.image_size, self.image_size):
@@ -240,13 +245,21 @@ class DiT(FlatEngineModule):
             y = None
         self._ensure_flat(x.device)
         self._ensure_workspace(x.shape[0], x.device)
-        out, zs = _DiTFunction.apply(self, x.float().contiguous(), t.float().contiguous(), y, self._flat)
+        feat = None
+        if align_target is not None and self.learn_align and align_target.dtype == torch.bfloat16:
+            if align_target.shape != (x.shape[0], self.num_patches, self.z_dims):
+                raise ValueError(f"align_target {tuple(align_target.shape)} does not match the projector output "
+                                 f"{(x.shape[0], self.num_patches, self.z_dims)}")
+            feat = align_target.detach().contiguous()
+        out, zs, align = _DiTFunction.apply(self, x.float().contiguous(), t.float().contiguous(), y, self._flat, feat)
+        if feat is not None:
+            zs._vaw_align = (align, align_target, feat)
         return out, zs
 
 
 class _DiTFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, x, t, y, flat):
+    def forward(ctx, model, x, t, y, flat, feat=None):
         B = x.shape[0]
         cfg = model._cfg(B)
         model._refresh_shadow()
@@ -254,14 +267,22 @@ class _DiTFunction(torch.autograd.Function):
         zs = None
         if model.learn_align:
             zs = torch.empty(B, model.num_patches, model.z_dims, dtype=torch.bfloat16, device=x.device)
-        L.call("vaw_dit_forward", C.byref(cfg), flat.data_ptr(), model._shadow.data_ptr(), model._ws.data_ptr(),
-               x.data_ptr(), t.data_ptr(), L.ptr(y), out.data_ptr(), L.ptr(zs), L.stream_ptr())
+        align = None
+        if feat is not None:
+            align = torch.empty((), dtype=torch.float32, device=x.device)
+            L.call("vaw_dit_forward_align", C.byref(cfg), flat.data_ptr(), model._shadow.data_ptr(),
+                   model._ws.data_ptr(), x.data_ptr(), t.data_ptr(), L.ptr(y), out.data_ptr(), L.ptr(zs),
+                   feat.data_ptr(), align.data_ptr(), L.stream_ptr())
+            ctx.mark_non_differentiable(align)
+        else:
+            L.call("vaw_dit_forward", C.byref(cfg), flat.data_ptr(), model._shadow.data_ptr(), model._ws.data_ptr(),
+                   x.data_ptr(), t.data_ptr(), L.ptr(y), out.data_ptr(), L.ptr(zs), L.stream_ptr())
         model._fwd_serial += 1
         ctx.model, ctx.serial, ctx.batch, ctx.y = model, model._fwd_serial, B, y
-        return out, zs
+        return out, zs, align
 
     @staticmethod
-    def backward(ctx, dout, dzs):
+    def backward(ctx, dout, dzs, _dalign=None):
         model = ctx.model
         if ctx.serial != model._fwd_serial:
             raise L.VawError("DiT backward after a newer forward: the activation workspace was overwritten "
@@ -284,7 +305,7 @@ class _DiTFunction(torch.autograd.Function):
                0 if fresh else 1, ev, L.stream_ptr())
         if model._post_backward is not None:
             model._post_backward()
-        return None, None, None, None, None
+        return None, None, None, None, None, None
 
 
 

@@ -190,18 +190,82 @@ class _AlignMSE(th.autograd.Function):
 
 L.register("vaw_align_mse", [L.C.c_void_p, L.C.c_int, L.C.c_void_p, L.C.c_int, L.C.c_void_p, L.C.c_float,
                              L.C.c_longlong, L.C.c_void_p, L.C.c_void_p, L.C.c_void_p])
+L.register("vaw_align_mse_bwd", [L.C.c_void_p, L.C.c_int, L.C.c_void_p, L.C.c_int, L.C.c_void_p, L.C.c_void_p,
+                                 L.C.c_longlong, L.C.c_void_p])
+L.register("vaw_align_rowwise", [L.C.c_void_p, L.C.c_int, L.C.c_void_p, L.C.c_int, L.C.c_int, L.C.c_void_p, L.C.c_float,
+                                 L.C.c_longlong, L.C.c_int, L.C.c_void_p, L.C.c_void_p, L.C.c_void_p])
+
+
+class _AlignMSEFused(th.autograd.Function):
+    """'mse' alignment loss whose VALUE was already accumulated in the epilogue of the last projector GEMM
+    (vaw_dit_forward_align / VAW_EPI_ALIGN_MSE): this node only carries it into the graph; the backward is one pass
+    dzs = g * 2 (zs - feat) / n with the upstream gradient read from the device."""
+
+    @staticmethod
+    def forward(ctx, zs, feat, loss):
+        ctx.save_for_backward(zs, feat)
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        zs, feat = ctx.saved_tensors
+        dz = th.empty_like(zs)
+        gd_ = g.reshape(1).float().contiguous()
+        L.call("vaw_align_mse_bwd", zs.data_ptr(), L.BF16, feat.data_ptr(), L.BF16, gd_.data_ptr(), dz.data_ptr(),
+               zs.numel(), L.stream_ptr())
+        return dz, None, None
+
+
+class _AlignRowwise(th.autograd.Function):
+    """'cosine' (reference :1008-1009) and 'mse_l2' (:1014-1017): one warp per token row, loss and d zs in one pass."""
+
+    @staticmethod
+    def forward(ctx, zs, feat, kind):
+        L.require_cuda(zs, feat)
+        if zs.shape != feat.shape:
+            raise ValueError(f"align loss: projector output {tuple(zs.shape)} and teacher features {tuple(feat.shape)} "
+                             "must have the same shape")
+        dmap = {th.float32: L.F32, th.bfloat16: L.BF16}
+        zs_c, feat_c = zs.contiguous(), feat.detach().contiguous()
+        if zs_c.dtype not in dmap:
+            zs_c = zs_c.float()
+        if feat_c.dtype not in dmap:
+            feat_c = feat_c.float()
+        D = zs_c.shape[-1]
+        rows = zs_c.numel() // D
+        dz = th.empty_like(zs_c)
+        part = th.empty(rows, dtype=th.float32, device=zs.device)
+        loss = th.empty((), dtype=th.float32, device=zs.device)
+        L.call("vaw_align_rowwise", zs_c.data_ptr(), dmap[zs_c.dtype], feat_c.data_ptr(), dmap[feat_c.dtype], kind,
+               dz.data_ptr(), 1.0, rows, D, part.data_ptr(), loss.data_ptr(), L.stream_ptr())
+        ctx.save_for_backward(dz)
+        ctx.in_dtype = zs.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        out = th.empty_like(dz)
+        s = g.reshape(1).float().contiguous()
+        L.call("vaw_scale_rows", dz.data_ptr(), s.data_ptr(), out.data_ptr(),
+               L.F32 if dz.dtype == th.float32 else L.BF16, 1, dz.numel(), L.stream_ptr())
+        return out.to(ctx.in_dtype), None, None
 
 
 def compute_align_loss(target, output, type, temperature=0.1):
-    """Projection-alignment loss (reference :1007-1046).  'mse' (the default and the benchmarked type) runs the fused
-    kernel; the other types are low-priority variants evaluated with device tensor ops."""
+    """Projection-alignment loss (reference :1007-1046).  'mse' (the default and the benchmarked type), 'cosine' and
+    'mse_l2' run library kernels (value + gradient in one pass); 'nt_xent' needs the [N*T, N*T] similarity matrix
+    (16384^2 logits at the benchmark batch - SURVEY a9 marks it impractical) and stays a plain tensor expression."""
     import torch.nn.functional as F
     if type == "mse":
+        fused = getattr(output, "_vaw_align", None)
+        if fused is not None and fused[1] is target:
+            return _AlignMSEFused.apply(output, fused[2], fused[0])
         return _AlignMSE.apply(output, target)
     if type == "cosine":
-        return -F.cosine_similarity(target.float(), output.float(), dim=-1).mean()
+        return _AlignRowwise.apply(output, target, 0)
     if type == "mse_l2":
-        return F.mse_loss(F.normalize(output.float(), dim=-1), F.normalize(target.float(), dim=-1))
+        return _AlignRowwise.apply(output, target, 1)
     if type == "nt_xent":
         assert temperature > 0, "temperature must be > 0"
         n, tt, d = target.shape
@@ -425,6 +489,11 @@ class GaussianDiffusion:
         t64 = t.to(th.int64).contiguous()
         x_t, _ = self._k1(x0, t64, eps, False)
 
+        if (self.args.learn_align and self.args.align_type == "mse" and th.is_tensor(features)
+                and features.dtype == th.bfloat16 and getattr(getattr(model, "module", model), "supports_fused_align", False)):
+            # REPA with an engine-backed DiT: the alignment loss is accumulated in the epilogue of the GEMM that produces
+            # zs (north-star piece 5); compute_align_loss below then finds the value attached to zs
+            model_kwargs = dict(model_kwargs, align_target=features)
         raw_output = model(x_t, self._scale_timesteps(t64), **model_kwargs)
         sec_out = None
         if isinstance(raw_output, tuple):
