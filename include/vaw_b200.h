@@ -97,6 +97,34 @@ int vaw_reverse_step(const void* model_out, int out_dtype, long long out_stride,
  * y = uncond + scale * (cond - uncond), every op rounded in the tensor's dtype like the eager expression. */
 int vaw_cfg_combine(const void* both, void* y, int dtype, float scale, long long half, vaw_stream_t stream);
 
+/* ---- EDM sampler (tools/cfg_edm.py; the sampler of the shipped recipe, run.sh `--solver heun`) -------------------------
+ * The state is float64 [n] like the reference's; all coefficients are per-step scalars evaluated on the host.
+ * vaw_edm_pre (ablation_sampler :193-194 + Net.forward :52,58): x_hat = a x_cur + c noise (noise nullable: x_hat = a x_cur),
+ * x_in = c_in * float32(x_hat / s_hat) is the denoiser input.  x_hat may be NULL (only x_in wanted). */
+int vaw_edm_pre(const double* x_cur, const double* noise, double a, double c, double s_hat, float c_in, double* x_hat,
+                float* x_in, long long n, vaw_stream_t stream);
+/* vaw_edm_post (Net.forward :62-77 + ablation_sampler :197-207): out = denoiser output (fp32 / bf16, out_stride values per
+ * sample, the first chw are used), x_src = the float64 state the denoiser saw (x_hat or x_prime), s_src = s(t) of it.
+ *   denoised = c_skip x + c_out out (float32; pred VAW_MEAN_START_X: denoised = out)   d = A x_src - Bc denoised (float64)
+ *   mode -1: x_in_next = denoised (Net.forward alone)      mode 0 (Euler / last step): x_out = x_hat + h d
+ *   mode 1 (Heun predictor): d_out = d, x_out = x_prime = x_hat + h d (h = alpha h), x_in_next = c_in_next *
+ *           float32(x_prime / s_next) - the next denoiser input
+ *   mode 2 (Heun corrector): x_out = x_hat + h (c1 d_prev + c2 d)
+ * Every product / sum / quotient is rounded separately in the reference's order. */
+int vaw_edm_post(const void* out, int out_dtype, long long out_stride, const double* x_src, double s_src, float c_skip,
+                 float c_out, int pred, double A, double Bc, int mode, double h, const double* x_hat, const double* d_prev,
+                 double c1, double c2, double* x_out, double* d_out, double s_next, float c_in_next, float* x_in_next,
+                 long long N, long long chw, vaw_stream_t stream);
+/* ---- flow-matching SDE sampler (tools/gaussian_diffusion.py:1206-1257 conversions, :1366-1408 sde_sample) ---------------
+ * coef: HOST array {alpha_t, sigma_t, d_alpha_t, d_sigma_t, 2 sigma_t d_sigma_t} (float32) of the step's time.
+ * drift = vector - 0.5 diffusion score from the model output `out` evaluated at x_eval (mean_type START_X .. VECTOR).
+ *   mode 0: x_out = x_base + drift step (+ sqrt(diffusion) noise sqrt_abs_step when noise != NULL)   [Euler / last step]
+ *   mode 1: same and drift_out = drift                                                              [Heun predictor]
+ *   mode 2: x_out = x_base + 0.5 (drift_prev + drift) step + noise term                             [Heun corrector]   */
+int vaw_flow_sde_step(const void* out, int out_dtype, const float* x_eval, const float* coef, int mean_type, int mode,
+                      const float* x_base, const float* drift_prev, const float* noise, float step, float sqrt_abs_step,
+                      float* x_out, float* drift_out, long long n, vaw_stream_t stream);
+
 /* ---- K2: fused weighted-MSE forward + backward --------------------------------------------------------------
  * Replaces (target - out)**2 -> mean_flat (tools/nn.py:86-90) -> w * raw (tools/gaussian_diffusion.py:911-913)
  * and the autograd backward of that chain (seeded by trainer.py:107-108).  The target is rebuilt from x0/noise

@@ -17,6 +17,8 @@ installed; see oracle/ref_stubs/README.md).  Everything written here is an input
     dit_golden.npz         a tiny DiT (with REPA projector): weights, forward outputs, full training_losses + grads
     vb_golden.npz          training_losses with a learned variance (LEARNED / LEARNED_RANGE x MSE / RESCALED_MSE / KL /
                            RESCALED_KL): terms + the gradient w.r.t. the 2C-channel model output
+    edm_golden.npz         tools/cfg_edm.py: Net (sigma table u, round_sigma, preconditioning) and ablation_sampler (Euler /
+                           Heun x every discretisation / schedule / scaling, churn with pinned noise) around a toy denoiser
     flow_golden.npz        FlowMatching (tools/gaussian_diffusion.py:1151-1418): interpolant, q_sample, compute_target,
                            training_losses (+ gradient) over every path type x prediction type, the vector / score
                            conversions, and sde_sample (euler / heun) with pinned noise
@@ -407,6 +409,61 @@ def vb_golden():
     print("vb_golden.npz", len(out), "arrays")
 
 
+EDM_CASES = [  # (tag, Net kwargs, sampler kwargs)
+    ("heun_edm_eps", dict(pred_type="EPSILON", noise_schedule="linear"), dict(solver="heun")),
+    ("euler_edm_eps", dict(pred_type="EPSILON", noise_schedule="linear"), dict(solver="euler")),
+    ("heun_edm_x0_cos", dict(pred_type="START_X", noise_schedule="cosine"), dict(solver="heun")),
+    ("heun_edm_v_logsnr", dict(pred_type="VELOCITY", noise_schedule="linear_logsnr"), dict(solver="heun")),
+    ("heun_vp", dict(pred_type="EPSILON", noise_schedule="cosine"), dict(solver="heun", discretization="vp", schedule="vp", scaling="vp")),
+    ("heun_ve", dict(pred_type="EPSILON", noise_schedule="linear"), dict(solver="heun", discretization="ve", schedule="ve", scaling="none")),
+    ("euler_iddpm", dict(pred_type="EPSILON", noise_schedule="cosine"), dict(solver="euler", discretization="iddpm", schedule="linear", scaling="none")),
+    ("heun_churn", dict(pred_type="EPSILON", noise_schedule="linear"), dict(solver="heun", S_churn=20, S_min=0.05, S_max=50, S_noise=1.003)),
+    ("heun_alpha", dict(pred_type="VELOCITY", noise_schedule="cosine"), dict(solver="heun", alpha=0.5)),
+]
+
+
+class _ToyDenoiser(torch.nn.Module):
+    """Stands in for the (guided) denoiser inside Net: smooth, depends on x, the integer timestep and the label."""
+
+    def forward(self, x, t, y=None, **kw):
+        tt = torch.sin(t.float() / 100.0).view(-1, 1, 1, 1)
+        yy = (y.float().view(-1, 1, 1, 1) / 10.0) if y is not None else 0.0
+        return (0.3 * x + 0.05 * tt + 0.01 * yy).to(x.dtype)
+
+
+def edm_golden():
+    import warnings
+    warnings.filterwarnings("ignore")
+    import tools.cfg_edm as redm   # noqa: E402  (reference)
+    out = {}
+    g = torch.Generator().manual_seed(51)
+    latents = torch.randn(4, 3, 8, 8, generator=g)
+    labels = torch.tensor([1, 7, 3, 9])
+    noises = torch.randn(12, 4, 3, 8, 8, generator=g, dtype=torch.float64)
+    out.update(latents=latents.numpy(), labels=labels.numpy(), noises=noises.numpy())
+    for sched in ("linear", "cosine", "linear_logsnr"):
+        net = redm.Net(_ToyDenoiser(), img_resolution=8, img_channels=3, noise_schedule=sched)
+        out[f"u::{sched}"] = net.u.numpy()
+        out[f"sigma_minmax::{sched}"] = np.array([net.sigma_min, net.sigma_max])
+        probe = torch.tensor([0.002, 0.01, 0.5, 1.0, 7.3, 80.0, 155.0], dtype=torch.float64)
+        out[f"round_idx::{sched}"] = net.round_sigma(probe, return_index=True).numpy()
+        out[f"round_val::{sched}"] = net.round_sigma(probe).numpy()
+        x = torch.randn(4, 3, 8, 8, generator=g, dtype=torch.float64)
+        out[f"net_x::{sched}"] = x.numpy()
+        for pred in ("EPSILON", "START_X", "VELOCITY"):
+            n2 = redm.Net(_ToyDenoiser(), img_resolution=8, img_channels=3, noise_schedule=sched, pred_type=pred)
+            out[f"net_out::{sched}::{pred}"] = n2(x, torch.tensor(2.5, dtype=torch.float64), labels).numpy()
+    for tag, nkw, skw in EDM_CASES:
+        net = redm.Net(_ToyDenoiser(), img_resolution=8, img_channels=3, **nkw)
+        it = iter(noises)
+        res = redm.ablation_sampler(net, latents, class_labels=labels, randn_like=lambda a: next(it).to(a.dtype),
+                                    num_steps=7, **skw)
+        assert res.dtype == torch.float64
+        out[f"sample::{tag}"] = res.numpy()
+    np.savez_compressed(os.path.join(HERE, "edm_golden.npz"), **out)
+    print("edm_golden.npz", len(out), "arrays")
+
+
 FLOW_CASES = [("START_X", "lambda"), ("EPSILON", "lambda"), ("EPSILON", "min_snr_5"), ("VELOCITY", "lambda"),
               ("VELOCITY", "min_snr_5"), ("VECTOR", "lambda"), ("VECTOR", "constant"), ("SCORE", "constant")]
 
@@ -472,6 +529,9 @@ def flow_golden():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "edm":
+        edm_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "vb":
         vb_golden()
         sys.exit(0)
@@ -499,3 +559,4 @@ if __name__ == "__main__":
     dit_golden()
     flow_golden()
     vb_golden()
+    edm_golden()

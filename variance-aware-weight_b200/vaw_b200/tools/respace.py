@@ -92,4 +92,8 @@ class _WrappedModel:
         new_ts = m[ts]
         if self.rescale_timesteps:
             new_ts = new_ts.float() * (1000.0 / self.original_num_steps)
+        hint = getattr(ts, "_vaw_host_value", None)   # the sampling loops build ts from a host integer: keep it known
+        if hint is not None:                          # on the host so that IntervalCFG need not synchronise
+            v = float(self.timestep_map[int(hint)])
+            new_ts._vaw_host_value = v * (1000.0 / self.original_num_steps) if self.rescale_timesteps else v
         return self.model(x, new_ts, **kwargs)

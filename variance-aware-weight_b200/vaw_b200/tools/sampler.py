@@ -35,17 +35,33 @@ class IntervalCFG(torch.nn.Module):
 
     @staticmethod
     def _format_time(time_tensor, batch_size):
+        hint = getattr(time_tensor, "_vaw_host_value", None)
         if time_tensor.dim() == 0:
-            return time_tensor.expand(batch_size)
-        if time_tensor.numel() == 1:
-            return time_tensor.reshape(1).expand(batch_size)
-        return time_tensor.reshape(batch_size)
+            out = time_tensor.expand(batch_size)
+        elif time_tensor.numel() == 1:
+            out = time_tensor.reshape(1).expand(batch_size)
+        else:
+            out = time_tensor.reshape(batch_size)
+        if hint is not None:
+            out._vaw_host_value = hint
+        return out
 
     def forward(self, sample_tensor, time_tensor, **model_kwargs):
         n = sample_tensor.shape[0]
         time_tensor = self._format_time(time_tensor, n)
         labels = model_kwargs.get("y", None)
-        if not (self.class_cond and labels is not None and self._use_cfg(float(time_tensor.float().mean().item()))):
+        use = False
+        if self.class_cond and labels is not None and abs(self.guidance_scale - 1.0) >= 1e-8:
+            lo, hi = self.interval
+            if not (lo >= 0 and hi > lo):
+                use = True                   # no interval: the decision does not depend on the time at all
+            else:
+                # the samplers of this package build the time tensor from a host scalar and leave it attached
+                # (`_vaw_host_value`): the interval test then costs no device synchronisation; any other caller gets the
+                # reference's `time_tensor.float().mean().item()`
+                tv = getattr(time_tensor, "_vaw_host_value", None)
+                use = self._use_cfg(float(tv) if tv is not None else float(time_tensor.float().mean().item()))
+        if not use:
             return self.model(sample_tensor, time_tensor, **model_kwargs)
         assert labels.shape[0] == n, f"CFG expects label batch size {n}, but got {labels.shape[0]}."
         kw = dict(model_kwargs)
