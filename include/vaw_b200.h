@@ -118,12 +118,13 @@ int vaw_edm_post(const void* out, int out_dtype, long long out_stride, const dou
 /* ---- flow-matching SDE sampler (tools/gaussian_diffusion.py:1206-1257 conversions, :1366-1408 sde_sample) ---------------
  * coef: HOST array {alpha_t, sigma_t, d_alpha_t, d_sigma_t, 2 sigma_t d_sigma_t} (float32) of the step's time.
  * drift = vector - 0.5 diffusion score from the model output `out` evaluated at x_eval (mean_type START_X .. VECTOR).
- *   mode 0: x_out = x_base + drift step (+ sqrt(diffusion) noise sqrt_abs_step when noise != NULL)   [Euler / last step]
+ *   noise term = noise_scale * noise * sqrt_abs_step, noise_scale = sqrt(diffusion) of the step's CURRENT time
+ *   mode 0: x_out = x_base + drift step (+ noise term when noise != NULL)                           [Euler / last step]
  *   mode 1: same and drift_out = drift                                                              [Heun predictor]
  *   mode 2: x_out = x_base + 0.5 (drift_prev + drift) step + noise term                             [Heun corrector]   */
 int vaw_flow_sde_step(const void* out, int out_dtype, const float* x_eval, const float* coef, int mean_type, int mode,
-                      const float* x_base, const float* drift_prev, const float* noise, float step, float sqrt_abs_step,
-                      float* x_out, float* drift_out, long long n, vaw_stream_t stream);
+                      const float* x_base, const float* drift_prev, const float* noise, float step, float noise_scale,
+                      float sqrt_abs_step, float* x_out, float* drift_out, long long n, vaw_stream_t stream);
 
 /* ---- K2: fused weighted-MSE forward + backward --------------------------------------------------------------
  * Replaces (target - out)**2 -> mean_flat (tools/nn.py:86-90) -> w * raw (tools/gaussian_diffusion.py:911-913)

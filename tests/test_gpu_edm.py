@@ -26,16 +26,18 @@ from test_oracle_edm import CASES   # noqa: E402
 
 
 class Toy(torch.nn.Module):
-    """tests/golden/make_golden.py::_ToyDenoiser with sin(t / 100) tabulated on the host (device sin differs in the last
-    bit from the host's; the remaining ops are single IEEE multiplies / adds, identical on both sides)."""
+    """tests/golden/make_golden.py::_ToyDenoiser with sin(t / 100) and y / 10 tabulated on the host (the device's sin
+    differs in the last bit from the host's, and torch's CUDA division by a scalar multiplies by the reciprocal); the
+    remaining ops are single IEEE multiplies / adds, identical on both sides."""
 
     def __init__(self):
         super().__init__()
         self.register_buffer("tab", torch.sin(torch.arange(1000).float() / 100.0))
+        self.register_buffer("ytab", torch.arange(1000).float() / 10.0)
 
     def forward(self, x, t, y=None, **kw):
         tt = self.tab[t.long()].view(-1, 1, 1, 1)
-        yy = (y.float().view(-1, 1, 1, 1) / 10.0) if y is not None else 0.0
+        yy = self.ytab[y.long()].view(-1, 1, 1, 1) if y is not None else 0.0
         return (0.3 * x + 0.05 * tt + 0.01 * yy).to(x.dtype)
 
 
@@ -80,7 +82,8 @@ def test_edm_heun_with_guided_dit_vs_oracle():
     def model_fn(x_in, t):
         calls.append(int(t[0]))
         with torch.no_grad():
-            return cfg(x_in.to(DEV), t.to(DEV), y=y).float().cpu()
+            raw = cfg(x_in.to(DEV), t.to(DEV), y=y)        # outside the guidance interval: the DiT's (out, zs) tuple
+            return (raw[0] if isinstance(raw, tuple) else raw).float().cpu()
     want = oedm.sample(oedm.SigmaTable("cosine"), "EPSILON", model_fn, lat.cpu(), noises, num_steps=6, solver="heun")
     assert torch.isfinite(got).all() and np.array_equal(got.cpu().numpy(), want.numpy())
     assert len(calls) == 11 and any(200 <= c < 800 for c in calls) and any(not (200 <= c < 800) for c in calls)

@@ -107,9 +107,11 @@ template <typename OutT>
 __global__ void __launch_bounds__(256)
 flow_sde_step_kernel(const OutT* __restrict__ out, const float* __restrict__ x_eval, FlowCoef k, int mt, int mode,
                      const float* __restrict__ x_base, const float* __restrict__ drift_prev,
-                     const float* __restrict__ noise, float step, float sqrt_abs_step, float* __restrict__ x_out,
-                     float* __restrict__ drift_out, long long n) {
-  const float sd = sqrtf(k.diff);   // th.sqrt(diffusion): NaN for a negative coefficient, exactly like the reference
+                     const float* __restrict__ noise, float step, float noise_scale, float sqrt_abs_step,
+                     float* __restrict__ x_out, float* __restrict__ drift_out, long long n) {
+  // noise_scale = th.sqrt(diffusion) of the step's CURRENT time (the Heun corrector evaluates its drift at the next
+  // time but re-uses the predictor's noise term); NaN for a negative coefficient, exactly like the reference
+  const float sd = noise_scale;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float d = flow_drift(mt, k, (float)out[i], x_eval[i]);
@@ -167,7 +169,8 @@ extern "C" int vaw_edm_post(const void* out, int out_dtype, long long out_stride
 
 extern "C" int vaw_flow_sde_step(const void* out, int out_dtype, const float* x_eval, const float* coef, int mean_type,
                                  int mode, const float* x_base, const float* drift_prev, const float* noise, float step,
-                                 float sqrt_abs_step, float* x_out, float* drift_out, long long n, cudaStream_t stream) {
+                                 float noise_scale, float sqrt_abs_step, float* x_out, float* drift_out, long long n,
+                                 cudaStream_t stream) {
   VAW_CHECK_ARG(out && x_eval && coef && x_base && x_out && n >= 0, "vaw_flow_sde_step: bad arguments");
   VAW_CHECK_ARG(out_dtype == 0 || out_dtype == 1, "vaw_flow_sde_step: out_dtype must be 0 (f32) or 1 (bf16)");
   VAW_CHECK_ARG(mean_type >= PT_START_X && mean_type <= PT_VECTOR, "vaw_flow_sde_step: mean type %d has no vector form",
@@ -177,10 +180,11 @@ extern "C" int vaw_flow_sde_step(const void* out, int out_dtype, const float* x_
   const FlowCoef k{coef[0], coef[1], coef[2], coef[3], coef[4]};   // HOST array: alpha, sigma, d_alpha, d_sigma, diffusion
   if (out_dtype == 0)
     flow_sde_step_kernel<float><<<grid_of(n), 256, 0, stream>>>((const float*)out, x_eval, k, mean_type, mode, x_base,
-                                                                drift_prev, noise, step, sqrt_abs_step, x_out, drift_out, n);
+                                                                drift_prev, noise, step, noise_scale, sqrt_abs_step, x_out, drift_out, n);
   else
     flow_sde_step_kernel<bf16><<<grid_of(n), 256, 0, stream>>>((const bf16*)out, x_eval, k, mean_type, mode, x_base,
-                                                               drift_prev, noise, step, sqrt_abs_step, x_out, drift_out, n);
+                                                               drift_prev, noise, step, noise_scale, sqrt_abs_step, x_out,
+                                                               drift_out, n);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }

@@ -323,7 +323,7 @@ class _WeightedMSE(th.autograd.Function):
 L.register("vaw_wmse_fwd_bwd_strided", [L.C.c_void_p, L.C.c_int, L.C.c_longlong] + [L.C.c_void_p] * 11 +
            [L.C.c_longlong, L.C.c_void_p, L.C.c_float, L.C.c_int, L.C.c_longlong, L.C.c_longlong, L.C.c_void_p])
 L.register("vaw_flow_sde_step", [L.C.c_void_p, L.C.c_int, L.C.c_void_p, L.C.c_void_p, L.C.c_int, L.C.c_int] +
-           [L.C.c_void_p] * 3 + [L.C.c_float, L.C.c_float, L.C.c_void_p, L.C.c_void_p, L.C.c_longlong, L.C.c_void_p])
+           [L.C.c_void_p] * 3 + [L.C.c_float] * 3 + [L.C.c_void_p, L.C.c_void_p, L.C.c_longlong, L.C.c_void_p])
 L.register("vaw_vb_terms", [L.C.c_void_p, L.C.c_int, L.C.c_longlong] + [L.C.c_void_p] * 4 + [L.C.c_int] +
            [L.C.c_void_p] * 2 + [L.C.c_longlong, L.C.c_void_p, L.C.c_float, L.C.c_int, L.C.c_int, L.C.c_int, L.C.c_float,
                                  L.C.c_longlong, L.C.c_longlong, L.C.c_void_p])
@@ -784,7 +784,7 @@ class FlowMatching:
         x = _f32(noise)
         N, n, mt = x.shape[0], x.numel(), self.model_mean_type.value
 
-        def drift_step(x_eval, t_scalar, mode, x_base, step, sq, rnd=None, d_prev=None, want_drift=False):
+        def drift_step(x_eval, t_scalar, mode, x_base, step, sq, rnd=None, d_prev=None, want_drift=False, nscale=0.0):
             tt = th.full((N,), float(t_scalar.to(th.float32)), dtype=th.float32, device=x.device)
             mo = self.forward_model(model, x_eval, tt, **model_kwargs)
             if mo.dtype not in (th.float32, th.bfloat16):
@@ -794,8 +794,8 @@ class FlowMatching:
             x_out = th.empty_like(x)
             d_out = th.empty_like(x) if want_drift else None
             L.call("vaw_flow_sde_step", mo.data_ptr(), L.BF16 if mo.dtype == th.bfloat16 else L.F32, x_eval.data_ptr(),
-                   coef.ctypes.data, mt, mode, x_base.data_ptr(), L.ptr(d_prev), L.ptr(rnd), float(step), float(sq),
-                   x_out.data_ptr(), L.ptr(d_out), n, L.stream_ptr())
+                   coef.ctypes.data, mt, mode, x_base.data_ptr(), L.ptr(d_prev), L.ptr(rnd), float(step), float(nscale),
+                   float(sq), x_out.data_ptr(), L.ptr(d_out), n, L.stream_ptr())
             return x_out, d_out
 
         with th.no_grad():
@@ -804,11 +804,14 @@ class FlowMatching:
                 step = (nxt - cur).to(th.float32)
                 sq = th.sqrt(th.abs(nxt - cur)).to(th.float32)
                 rnd = th.randn_like(x)
+                # th.sqrt(diffusion) of the CURRENT time scales the noise term of both Heun stages (:1387); a negative
+                # coefficient (cosine path at t = 1 in fp32) gives NaN, like the reference
+                nscale = float(th.sqrt(th.tensor(self._step_coef(cur)[4])))
                 if solver == "euler":
-                    x, _ = drift_step(x, cur, 0, x, step, sq, rnd)
+                    x, _ = drift_step(x, cur, 0, x, step, sq, rnd, nscale=nscale)
                 else:
-                    pred, d_cur = drift_step(x, cur, 1, x, step, sq, rnd, want_drift=True)
-                    x, _ = drift_step(pred, nxt, 2, x, step, sq, rnd, d_prev=d_cur)
+                    pred, d_cur = drift_step(x, cur, 1, x, step, sq, rnd, want_drift=True, nscale=nscale)
+                    x, _ = drift_step(pred, nxt, 2, x, step, sq, rnd, d_prev=d_cur, nscale=nscale)
             cur, nxt = timesteps[-2], timesteps[-1]
             x, _ = drift_step(x, cur, 0, x, (nxt - cur).to(th.float32), 0.0)
         return x
