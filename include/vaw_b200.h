@@ -353,6 +353,13 @@ int vaw_dit_workspace_bytes(const vaw_dit_cfg* cfg, long long* bytes);
  * _scale_timesteps, tools/gaussian_diffusion.py:417-420), y int64 [B]; out bf16 [B,C_out,H,W]; zs bf16 [B*T,z_dim]. */
 int vaw_dit_forward(const vaw_dit_cfg* cfg, const float* P, const void* Pb, void* ws, const float* x_t, const float* t,
                     const long long* y, void* out, void* zs, vaw_stream_t stream);
+/* Forward-only entry for sampling / evaluation (the reference runs its samplers under torch.no_grad(), tools/sampler.py,
+ * tools/cfg_edm.py:109): identical results, but nothing is kept for a backward pass - one set of operand buffers shared
+ * by all blocks, a three-buffer residual ring, no saved pre-activations / branch outputs (a third of the forward's HBM
+ * writes).  ws: vaw_dit_infer_workspace_bytes (DiT-XL/2, B = 128: 1.3 GB instead of the 40 GB training workspace). */
+int vaw_dit_infer_workspace_bytes(const vaw_dit_cfg* cfg, long long* bytes);
+int vaw_dit_forward_infer(const vaw_dit_cfg* cfg, const float* P, const void* Pb, void* ws, const float* x_t,
+                          const float* t, const long long* y, void* out, void* zs, vaw_stream_t stream);
 /* Same, with the alignment loss fused into the last projector GEMM (VAW_EPI_ALIGN_MSE): feat bf16 [B*T, z_dim] are the
  * teacher features, align_loss (device scalar) receives mean((zs - feat)^2).  learn_align configs only. */
 int vaw_dit_forward_align(const vaw_dit_cfg* cfg, const float* P, const void* Pb, void* ws, const float* x_t,

@@ -163,3 +163,34 @@ def test_alignment_loss_fused_into_the_projector_gemm():
     assert abs(terms["align"].item() - want.item()) <= 1e-5 * want.item()
     with pytest.raises(ValueError):
         m(x0, t.float(), y, align_target=feats[:, :5])
+
+
+@pytest.mark.parametrize("align", [False, True])
+def test_forward_only_entry_matches_training_forward(align):
+    """torch.no_grad() forwards (the samplers) take vaw_dit_forward_infer: one shared set of operand buffers, a three-buffer
+    residual ring, no saved pre-activations / branch outputs.  Same kernels on the same values -> bit-identical outputs,
+    a far smaller workspace, and a training forward whose backward is still pending keeps its activations."""
+    torch.manual_seed(4)
+    m = DiT(image_size=32, patch_size=2, in_channels=4, hidden_size=384, depth=4, num_heads=6, class_dropout_prob=0.0,
+            num_classes=10, learn_align=align, encoder_depth=2, z_dims=48, projector_dim=64).to(DEV).train()
+    dezero(m)
+    B = 8
+    x = torch.randn(B, 4, 32, 32, device=DEV); t = torch.rand(B, device=DEV) * 999; y = torch.randint(0, 10, (B,), device=DEV)
+    out, zs = m(x, t, y)                       # training forward, backward pending
+    with torch.no_grad():
+        o2, z2 = m(x * 0.5, t, y)              # a different sampling forward in between
+        o1, z1 = m(x, t, y)
+    assert torch.equal(o1, out) and not torch.equal(o2, out)
+    if align:
+        assert torch.equal(z1, zs)
+    assert m._ws_inf.numel() * 8 < m._ws.numel()
+    g = torch.randn_like(out)
+    out.backward(g)                            # the stash of the training forward was not overwritten
+    g1 = m._gflat.clone()
+    for p in m.parameters():
+        p.grad = None
+    m(x, t, y)[0].backward(g)
+    assert torch.equal(g1, m._gflat)
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m(x, t, y)[0], out)

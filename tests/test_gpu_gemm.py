@@ -146,6 +146,10 @@ def test_tma_store_epilogues_every_tile_config(tile_n, cta_group, M, N, K):
         o.fill_(float("nan")); o2.fill_(float("nan"))
         _rg(A, B, 0, 0, M, N, K, epi, out=o, out2=o2, bias=bias, tile_n=tile_n, cta_group=cta_group)
         assert relerr(o, acc) < 3e-3 and relerr(o2, fn(pre)) < 4e-3, epi
+    # forward-only callers drop the saved pre-activation: out = NULL, out2 unchanged
+    o2b = torch.full_like(o2, float("nan"))
+    _rg(A, B, 0, 0, M, N, K, L.EPI_SILU, out=None, out2=o2b, bias=bias, tile_n=tile_n, cta_group=cta_group)
+    assert torch.equal(o2b, o2)
     # residual epilogues: resid in / out2 + y out through TMA in 16-column halves (ragged sample boundaries included)
     rps = {128: 64, 300: 100, 512: 256}[M]
     resid = torch.randn(M, N, device=DEV); gate = torch.randn(M // rps, N, device=DEV)
@@ -154,6 +158,10 @@ def test_tma_store_epilogues_every_tile_config(tile_n, cta_group, M, N, K):
     _rg(A, B, 0, 0, M, N, K, L.EPI_GATE_RES, out=o, out2=xo, bias=bias, resid=resid, gate=gate, rows_per_sample=rps,
         tile_n=tile_n, cta_group=cta_group)
     assert relerr(o, acc) < 3e-3 and relerr(xo, resid + gate.repeat_interleave(rps, 0) * pre) < 2e-3
+    xo_b = torch.full_like(xo, float("nan"))       # without the branch output y (forward-only)
+    _rg(A, B, 0, 0, M, N, K, L.EPI_GATE_RES, out=None, out2=xo_b, bias=bias, resid=resid, gate=gate, rows_per_sample=rps,
+        tile_n=tile_n, cta_group=cta_group)
+    assert torch.equal(xo_b, xo)
     xo.fill_(float("nan"))
     _rg(A, B, 0, 0, M, N, K, L.EPI_RES, out2=xo, bias=bias, resid=resid, tile_n=tile_n, cta_group=cta_group)
     assert relerr(xo, resid + pre) < 2e-3

@@ -172,6 +172,44 @@ void carve(const vaw_dit_cfg& c, void* base, Ws& w) {
   w.bytes = k.cur;
 }
 
+// Forward-only layout (sampling / evaluation): nothing is kept for a backward pass, so every block re-uses ONE set of
+// operand buffers, the residual stream cycles through three buffers, and the tensors only the backward reads (saved
+// pre-activations, branch outputs) are not written at all.  DiT-XL/2 at B = 128: 1.3 GB instead of 40 GB, and a third of
+// the forward's HBM writes gone.
+void carve_infer(const vaw_dit_cfg& c, void* base, Ws& w) {
+  Carver k{reinterpret_cast<uint8_t*>(base)};
+  const long long B = c.B, D = c.D, M = (long long)c.B * c.T, Hd = c.hidden;
+  const long long Kp = (long long)c.C_in * c.P * c.P, PPC = (long long)c.P * c.P * c.C_out;
+  memset(&w, 0, sizeof(w));
+  w.patches = k.take<bf16>(M * Kp);
+  w.freq = k.take<bf16>(B * c.freq_dim);
+  w.t_h = k.take<bf16>(B * D);
+  w.c_silu = k.take<bf16>(B * D);
+  w.t_emb = k.take<float>(B * D);
+  w.c = k.take<float>(B * D);
+  w.mod_all = k.take<float>(B * c.depth * 6 * D);
+  w.mod_final = k.take<float>(B * 2 * D);
+  float* ring[3] = {k.take<float>(M * D), k.take<float>(M * D), k.take<float>(M * D)};
+  for (int i = 0; i <= 2 * c.depth; ++i) w.x[i] = ring[i % 3];
+  BlockWs b{};
+  b.mean1 = k.take<float>(M); b.rstd1 = k.take<float>(M); b.mean2 = b.mean1; b.rstd2 = b.rstd1;
+  b.lse = k.take<float>(B * c.H * c.T);
+  b.xn1 = k.take<bf16>(M * D); b.qkv = k.take<bf16>(M * 3 * D); b.attn_o = k.take<bf16>(M * D);
+  b.xn2 = b.xn1;
+  b.h_act = k.take<bf16>(M * Hd);
+  for (int i = 0; i < c.depth; ++i) w.blk[i] = b;   // y_attn / y_mlp / h_pre stay null: not stored
+  w.meanf = b.mean1; w.rstdf = b.rstd1;
+  w.xnf = b.xn1;
+  w.out_tok = k.take<bf16>(M * PPC);
+  const long long pd = c.learn_align ? c.proj_dim : 0;
+  w.xa = c.learn_align ? b.xn1 : nullptr;
+  w.z1 = k.take<bf16>(M * pd);
+  w.z2 = k.take<bf16>(M * pd);
+  w.align_parts = c.learn_align ? ((M + 31) / 32) * ((c.z_dim + 31) / 32) : 0;
+  w.align_part = k.take<float>(w.align_parts);
+  w.bytes = k.cur;
+}
+
 int check_cfg(const vaw_dit_cfg* c) {
   VAW_CHECK_ARG(c, "dit: null config");
   VAW_CHECK_ARG(c->B > 0 && c->T > 0 && c->D > 0 && c->H > 0 && c->depth > 0 && c->depth <= kMaxDepth,
@@ -219,7 +257,7 @@ extern "C" int vaw_dit_workspace_bytes(const vaw_dit_cfg* cfg, long long* bytes)
 // table_rows == 0) -> out [B,C_out,H,W] bf16 and, with learn_align, zs [B*T, z_dim] bf16.
 static int dit_forward_impl(const vaw_dit_cfg* cfg, const float* P, const void* Pb_, void* ws_, const float* x_t,
                             const float* t, const long long* y, void* out, void* zs, const void* feat, float* align_loss,
-                            cudaStream_t s) {
+                            cudaStream_t s, bool infer = false) {
   TRY(check_cfg(cfg));
   VAW_CHECK_ARG(P && Pb_ && ws_ && x_t && t && out, "vaw_dit_forward: null pointer");
   const vaw_dit_cfg& c = *cfg;
@@ -228,7 +266,8 @@ static int dit_forward_impl(const vaw_dit_cfg* cfg, const float* P, const void* 
   Layout L;
   compute_layout(c, L);
   Ws w;
-  carve(c, ws_, w);
+  if (infer) carve_infer(c, ws_, w);
+  else carve(c, ws_, w);
   const bf16* Pb = reinterpret_cast<const bf16*>(Pb_);
   const int B = c.B, T = c.T, D = c.D, M = B * T, Hd = c.hidden, hd = D / c.H;
   const int Kp = c.C_in * c.P * c.P, PPC = c.P * c.P * c.C_out;
@@ -298,6 +337,23 @@ static int dit_forward_impl(const vaw_dit_cfg* cfg, const float* P, const void* 
 extern "C" int vaw_dit_forward(const vaw_dit_cfg* cfg, const float* P, const void* Pb_, void* ws_, const float* x_t,
                                const float* t, const long long* y, void* out, void* zs, cudaStream_t s) {
   return dit_forward_impl(cfg, P, Pb_, ws_, x_t, t, y, out, zs, nullptr, nullptr, s);
+}
+
+// Forward-only entry (sampling / evaluation, torch.no_grad()): same arithmetic and results as vaw_dit_forward, but on
+// the compact workspace of carve_infer - no activation stash.  The training workspace is not touched.
+extern "C" int vaw_dit_infer_workspace_bytes(const vaw_dit_cfg* cfg, long long* bytes) {
+  TRY(check_cfg(cfg));
+  VAW_CHECK_ARG(bytes, "vaw_dit_infer_workspace_bytes: null output");
+  Ws w;
+  carve_infer(*cfg, nullptr, w);
+  *bytes = w.bytes;
+  return VAW_OK;
+}
+
+extern "C" int vaw_dit_forward_infer(const vaw_dit_cfg* cfg, const float* P, const void* Pb_, void* ws_,
+                                     const float* x_t, const float* t, const long long* y, void* out, void* zs,
+                                     cudaStream_t s) {
+  return dit_forward_impl(cfg, P, Pb_, ws_, x_t, t, y, out, zs, nullptr, nullptr, s, true);
 }
 
 extern "C" int vaw_dit_forward_align(const vaw_dit_cfg* cfg, const float* P, const void* Pb_, void* ws_,

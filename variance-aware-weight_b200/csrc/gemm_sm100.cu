@@ -264,7 +264,9 @@ __device__ __forceinline__ void epilogue_vec4(const EpiParams& p, int row, int c
     pk.x = pack_bf16(v.x, v.y);
     pk.y = pack_bf16(v.z, v.w);
     const bool dry = (p.dbg & 32) != 0;   // experiment: all the math, no global stores
-    if (!dry || pk.x == 0x7fc17fc2u) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + o) = pk;
+    // p.out may be null for the epilogues with a second output (forward-only use: nobody reads the saved pre-activation /
+    // branch output)
+    if (p.out && (!dry || pk.x == 0x7fc17fc2u)) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + o) = pk;
     if constexpr (EPI == EPI_GELU_TANH || EPI == EPI_GELU_ERF || EPI == EPI_SILU) {
       // activation of the bf16-rounded pre-activation (what the next Linear sees in the reference)
       const float2 h0 = unpack_bf16(pk.x), h1 = unpack_bf16(pk.y);
@@ -666,7 +668,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&om.c, stg_b + (TmaEpi<EPI>::two ? 0 : slot * 2048), col0, grow);
+            if (!TmaEpi<EPI>::two || p.out) tma_store_2d(&om.c, stg_b + (TmaEpi<EPI>::two ? 0 : slot * 2048), col0, grow);
             if (TmaEpi<EPI>::two) tma_store_2d(&om.c2, stg_b + 2048, col0, grow);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -1038,7 +1040,10 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
   const int epi = a->epilogue;
   const long long ldo = a->ldo ? a->ldo : a->N;
   VAW_CHECK_ARG(ldo % 8 == 0, "vaw_gemm_bf16: ldo must be a multiple of 8");
-  const bool needs_out = (epi != EPI_RES);
+  // the epilogues with a second output may drop the first (the saved pre-activation / branch output only the backward
+  // pass reads): forward-only callers pass out = NULL and save its HBM writes
+  const bool needs_out = !(epi == EPI_RES || epi == EPI_GATE_RES || epi == EPI_GELU_TANH || epi == EPI_GELU_ERF ||
+                           epi == EPI_SILU);
   VAW_CHECK_ARG(!needs_out || a->out, "vaw_gemm_bf16: missing out");
   const bool needs_out2 = (epi == EPI_GELU_TANH || epi == EPI_GELU_ERF || epi == EPI_GATE_RES || epi == EPI_RES ||
                            epi == EPI_SILU);
@@ -1184,7 +1189,7 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
   }
   if (epi == EPI_BF16 || epi == EPI_GELU_TANH || epi == EPI_GELU_ERF || epi == EPI_SILU) {
     VAW_CHECK_ARG((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "vaw_gemm_bf16: out must be 16-byte aligned");
-    rc = make_out_tmap(&om.c, a->out, a->M, a->N, ldo);
+    if (a->out) rc = make_out_tmap(&om.c, a->out, a->M, a->N, ldo);
     if (rc) return rc;
     if (epi != EPI_BF16) {
       VAW_CHECK_ARG(a->out2 && (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0,

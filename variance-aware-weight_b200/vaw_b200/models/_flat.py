@@ -53,7 +53,7 @@ class FlatEngineModule(nn.Module):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         drop = {"_flat": None, "_shadow": None, "_gflat": None, "_ws": None, "_events": None, "_post_backward": None,
-                "_slot_cache": None, "_ws_batch": -1, "_shadow_version": -1}
+                "_slot_cache": None, "_ws_batch": -1, "_shadow_version": -1, "_ws_inf": None, "_ws_inf_batch": -1}
         for k, v in self.__dict__.items():
             new.__dict__[k] = drop[k] if k in drop else copy.deepcopy(v, memo)
         return new

@@ -28,6 +28,8 @@ L.register("vaw_dit_param_layout", [C.POINTER(DiTCfg), C.c_void_p, C.c_void_p, C
 L.register("vaw_dit_workspace_bytes", [C.POINTER(DiTCfg), C.c_void_p])
 L.register("vaw_dit_forward", [C.POINTER(DiTCfg)] + [C.c_void_p] * 9)
 L.register("vaw_dit_forward_align", [C.POINTER(DiTCfg)] + [C.c_void_p] * 11)
+L.register("vaw_dit_infer_workspace_bytes", [C.POINTER(DiTCfg), C.c_void_p])
+L.register("vaw_dit_forward_infer", [C.POINTER(DiTCfg)] + [C.c_void_p] * 9)
 L.register("vaw_dit_backward", [C.POINTER(DiTCfg)] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_void_p])
 L.register("vaw_cast_f32_bf16", [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p])
 
@@ -244,6 +246,8 @@ class DiT(FlatEngineModule):
         else:
             y = None
         self._ensure_flat(x.device)
+        if not torch.is_grad_enabled():
+            return self._forward_infer(x.float().contiguous(), t.float().contiguous(), y)
         self._ensure_workspace(x.shape[0], x.device)
         feat = None
         if align_target is not None and self.learn_align and align_target.dtype == torch.bfloat16:
@@ -255,6 +259,32 @@ class DiT(FlatEngineModule):
         if feat is not None:
             zs._vaw_align = (align, align_target, feat)
         return out, zs
+
+
+def _dit_forward_infer(self, x, t, y):
+    """torch.no_grad() forward (the samplers): vaw_dit_forward_infer on a compact workspace of its own - no activation
+    stash, and a training forward whose backward is still pending keeps its saved activations."""
+    B = x.shape[0]
+    cfg = self._cfg(B)
+    if self._ws_inf is None or self._ws_inf_batch != B or self._ws_inf.device != x.device:
+        nbytes = C.c_longlong()
+        L.call("vaw_dit_infer_workspace_bytes", C.byref(cfg), C.byref(nbytes))
+        self._ws_inf = None
+        self._ws_inf = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
+        self._ws_inf_batch = B
+    self._refresh_shadow()
+    out = torch.empty(B, self.out_channels, self.image_size, self.image_size, dtype=torch.bfloat16, device=x.device)
+    zs = None
+    if self.learn_align:
+        zs = torch.empty(B, self.num_patches, self.z_dims, dtype=torch.bfloat16, device=x.device)
+    L.call("vaw_dit_forward_infer", C.byref(cfg), self._flat.data_ptr(), self._shadow.data_ptr(), self._ws_inf.data_ptr(),
+           x.data_ptr(), t.data_ptr(), L.ptr(y), out.data_ptr(), L.ptr(zs), L.stream_ptr())
+    return out, zs
+
+
+DiT._forward_infer = _dit_forward_infer
+DiT._ws_inf = None
+DiT._ws_inf_batch = -1
 
 
 class _DiTFunction(torch.autograd.Function):
