@@ -71,6 +71,31 @@ int vaw_qsample_target(const float* x0, const float* noise, const long long* t, 
                        const float* tab_sigma, const float* tab_c0, const float* tab_c1, float* x_t, float* target,
                        int mean_type, long long N, long long chw, vaw_stream_t stream);
 
+/* ---- K1 / K2 with the noise drawn in-kernel -------------------------------------------------------------
+ * Bit-compatible with the tensors torch.randn_like / torch.randint produce from the same CUDA generator state (seed,
+ * offset): the kernels walk ATen's Philox4x32-10 subsequence / element mapping (DistributionTemplates.h), so the noise
+ * of training_losses (tools/gaussian_diffusion.py:849-850), the timesteps of sample_t (:810-816) and the draw of
+ * sample_from_latent (tools/trainer.py:21-25) never exist as tensors in HBM.  The caller advances the generator by
+ * vaw_philox_offset_increment(numel) per draw, exactly what ATen's kernels would have consumed.
+ * vaw_qsample_philox: x0 [N, chw], or latent [N, 2 chw] (mean | std) from which x0 = (mean + std * eps1) * latent_scale
+ * is rebuilt with the draw at offset_latent; noise at offset_noise; x_start_out / noise_out / target nullable. */
+int vaw_philox_offset_increment(long long numel, unsigned long long* increment);
+int vaw_qsample_philox(const float* x0, const float* latent, float latent_scale, unsigned long long seed,
+                       unsigned long long offset_latent, unsigned long long offset_noise, const long long* t,
+                       const float* tab_alpha, const float* tab_sigma, const float* tab_c0, const float* tab_c1,
+                       float* x_start_out, float* noise_out, float* x_t, float* target, int mean_type, long long N,
+                       long long chw, vaw_stream_t stream);
+/* out[i] = low + (curand4 value % (high - low)), the stream of torch.randint(low, high, (n,), device=cuda) */
+int vaw_randint_philox(unsigned long long seed, unsigned long long offset, long long low, long long high, long long* out,
+                       long long n, vaw_stream_t stream);
+/* K2 (vaw_wmse_fwd_bwd_strided) that re-draws each noise element instead of reading a noise tensor; x0 may be NULL for
+ * the EPSILON / SCORE targets. */
+int vaw_wmse_fwd_bwd_philox(const void* out, int out_dtype, long long out_stride, const float* x0, unsigned long long seed,
+                            unsigned long long offset_noise, const long long* t, const float* tab_alpha,
+                            const float* tab_sigma, const float* tab_c0, const float* tab_c1, const float* w_tab,
+                            float* mse, void* grad_out, long long grad_stride, float gscale, int mean_type, long long N,
+                            long long chw, vaw_stream_t stream);
+
 /* ---- K8: fused reverse-process step ------------------------------------------------------------
  * Replaces the elementwise tail of GaussianDiffusion.p_mean_variance (tools/gaussian_diffusion.py:278-384) followed
  * by p_sample (:455-506), ddim_sample (:603-651) or ddim_reverse_sample (:653-689), and the 8 per-call table uploads

@@ -170,6 +170,80 @@ def test_seeded_draw_order_noise_then_t():
         assert torch.equal(rec[0][1], tt) and torch.equal(rec[0][0], rec[1][0]) and torch.equal(a["mse"], b["mse"])
 
 
+@pytest.mark.parametrize("N,mean", [(64, "epsilon"), (5, "velocity"), (600, "epsilon"), (3, "previous_x")])
+def test_in_kernel_philox_matches_torch_generator_stream(N, mean):
+    """with noise=None the Gaussian noise (and t=None: the timesteps) are drawn INSIDE K1 / K2 from the
+    device generator.  They must be the very tensors torch.randn_like / torch.randint would have produced, and the
+    generator must end where it would have ended: the implicit call equals the explicit one bit for bit (x_t, t, mse, the
+    gradient), and the next torch draw after either call is identical.  N = 600 latents is 2.4 M elements: more than one
+    Philox call per thread plus a ragged tail of ATen's grid."""
+    import ctypes as C
+    from vaw_b200 import _lib as L
+    d = gd.create_gaussian_diffusion(noise_schedule="cosine", mean_type=mean, weight_type="lambda" if mean != "previous_x" else "constant")
+    x0 = torch.randn(N, 4, 32, 32, device=DEV)
+    out = torch.randn(N, 4, 32, 32, device=DEV)
+    rec = []
+    def run(**kw):
+        o = out.clone().requires_grad_(True)
+        def model(x, ts, **k):
+            rec.append((x.clone(), ts.clone()))
+            return o
+        terms = d.training_losses(model, x0, **kw)
+        terms["loss"].sum().backward()
+        return terms["mse"].detach().clone(), o.grad.clone(), torch.rand(7, device=DEV)
+    torch.manual_seed(1234)
+    a = run()
+    torch.manual_seed(1234)
+    noise = torch.randn_like(x0)
+    t = torch.randint(0, d.num_timesteps, (N,), device=DEV)
+    b = run(t=t, noise=noise)
+    assert torch.equal(rec[0][0], rec[1][0]), "x_t differs: in-kernel noise != torch.randn_like"
+    assert torch.equal(rec[0][1], rec[1][1]), "timesteps differ: in-kernel randint != torch.randint"
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert torch.equal(a[2], b[2]), "the generator did not end at the same offset"
+    # the raw draws through the C ABI, against the tensors themselves
+    torch.manual_seed(99)
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    seed, off = gen.initial_seed(), gen.get_offset()
+    want = torch.randn_like(x0)
+    got, xt = torch.empty_like(x0), torch.empty_like(x0)
+    ta, ts_, c0, c1, _ = d._tables(x0.device)
+    L.call("vaw_qsample_philox", x0.data_ptr(), None, 1.0, seed, 0, off, t.data_ptr(), ta.data_ptr(), ts_.data_ptr(),
+           L.ptr(c0), L.ptr(c1), None, got.data_ptr(), xt.data_ptr(), None, d.model_mean_type.value, N, 4096, L.stream_ptr())
+    assert torch.equal(got, want)
+    inc = C.c_ulonglong()
+    L.call("vaw_philox_offset_increment", x0.numel(), C.byref(inc))
+    assert gen.get_offset() == off + inc.value
+
+
+def test_deferred_latent_fuses_sample_from_latent_into_k1():
+    """trainer.py:21-25 + gaussian_diffusion.py:849-854 as one kernel: sample_from_latent(..., defer=True) hands the
+    8-channel latent to training_losses, which draws eps1, noise and t in the reference's order.  Equal, bit for bit, to
+    the two-step path under the same seed - for the eps objective (x_start never materialised) and for one that needs it."""
+    from vaw_b200.tools import trainer as vtr
+    lat = torch.randn(48, 8, 32, 32, device=DEV)
+    lat[:, 4:] = lat[:, 4:].abs() * 0.3
+    for mean in ("epsilon", "start_x"):
+        d = gd.create_gaussian_diffusion(noise_schedule="linear", mean_type=mean, weight_type="lambda")
+        out = torch.randn(48, 4, 32, 32, device=DEV)
+        seen = []
+        def run(defer):
+            o = out.clone().requires_grad_(True)
+            def model(x, ts, **k):
+                seen.append((x.clone(), ts.clone()))
+                return o
+            torch.manual_seed(7)
+            x_start = vtr.sample_from_latent(lat, 0.18215, defer=defer)
+            terms = d.training_losses(model, x_start)
+            terms["loss"].mean().backward()
+            return terms["mse"].detach().clone(), o.grad.clone(), torch.rand(3, device=DEV)
+        a, b = run(True), run(False)
+        assert torch.equal(seen[-2][0], seen[-1][0]) and torch.equal(seen[-2][1], seen[-1][1])
+        assert all(torch.equal(u, v) for u, v in zip(a, b))
+    x = vtr.sample_from_latent(lat, 0.5, defer=True)
+    assert x.shape == (48, 4, 32, 32) and x.tensor().shape == (48, 4, 32, 32)
+
+
 def test_align_loss_kernel_vs_torch():
     torch.manual_seed(4)
     zs = (torch.randn(4, 64, 48, device=DEV)).bfloat16().requires_grad_(True)

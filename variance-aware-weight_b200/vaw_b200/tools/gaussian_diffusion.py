@@ -329,6 +329,85 @@ L.register("vaw_vb_terms", [L.C.c_void_p, L.C.c_int, L.C.c_longlong] + [L.C.c_vo
                                  L.C.c_longlong, L.C.c_longlong, L.C.c_void_p])
 
 
+_U64 = L.C.c_ulonglong
+L.register("vaw_philox_offset_increment", [L.C.c_longlong, L.C.c_void_p])
+L.register("vaw_qsample_philox", [L.C.c_void_p, L.C.c_void_p, L.C.c_float, _U64, _U64, _U64] + [L.C.c_void_p] * 9 +
+           [L.C.c_int, L.C.c_longlong, L.C.c_longlong, L.C.c_void_p])
+L.register("vaw_randint_philox", [_U64, _U64, L.C.c_longlong, L.C.c_longlong, L.C.c_void_p, L.C.c_longlong, L.C.c_void_p])
+L.register("vaw_wmse_fwd_bwd_philox", [L.C.c_void_p, L.C.c_int, L.C.c_longlong, L.C.c_void_p, _U64, _U64] +
+           [L.C.c_void_p] * 8 + [L.C.c_longlong, L.C.c_float, L.C.c_int, L.C.c_longlong, L.C.c_longlong, L.C.c_void_p])
+
+
+class DeferredLatent:
+    """What `vaw_b200.tools.trainer.sample_from_latent(latent, scale, defer=True)` returns: the 8-channel (mean | std)
+    latent and its scale, NOT yet sampled.  `training_losses` accepts it as `x_start` and draws eps1 inside K1 (same
+    generator stream as the reference's `mean + std * randn_like(mean)`, trainer.py:21-25), so neither eps1 nor - for the
+    eps objective - x_start itself is ever written to HBM.  `.tensor()` materialises it the ordinary way."""
+
+    def __init__(self, latent, latent_scale=1.0):
+        if latent.dim() < 2 or latent.shape[1] % 2:
+            raise ValueError("latent must be [N, 2C, ...] (mean | std along the channels)")
+        self.latent, self.latent_scale = latent, float(latent_scale)
+        self.shape = th.Size((latent.shape[0], latent.shape[1] // 2, *latent.shape[2:]))
+        self.device, self.is_cuda, self.dtype = latent.device, latent.is_cuda, th.float32
+
+    def tensor(self):
+        from .trainer import sample_from_latent
+        return sample_from_latent(self.latent, self.latent_scale)
+
+
+class _PhiloxDraws:
+    """Bookkeeping of the device generator for draws made inside our kernels: hands out (seed, offset) pairs and advances
+    torch's generator by exactly what ATen's own kernels would have consumed (vaw_philox_offset_increment)."""
+
+    def __init__(self, device):
+        idx = device.index if device.index is not None else th.cuda.current_device()
+        self.gen = th.cuda.default_generators[idx]
+        self.seed = int(self.gen.initial_seed())
+
+    def take(self, numel):
+        off = int(self.gen.get_offset())
+        inc = _U64()
+        L.call("vaw_philox_offset_increment", int(numel), L.C.byref(inc))
+        self.gen.set_offset(off + int(inc.value))
+        return off
+
+
+class _WeightedMSEPhilox(th.autograd.Function):
+    """K2 for a step whose noise was drawn inside K1: the eps each element needs is re-drawn from (seed, offset)."""
+
+    @staticmethod
+    def forward(ctx, out, x0, t, coef, mean_code, seed, offset, chw):
+        L.require_cuda(out)
+        N = out.shape[0]
+        o = out.contiguous()
+        if o.dtype not in (th.float32, th.bfloat16):
+            o = o.float()
+        stride = o[0].numel() if N else chw
+        code = L.F32 if o.dtype == th.float32 else L.BF16
+        mse = th.empty(N, dtype=th.float32, device=out.device)
+        g = None
+        if out.requires_grad:
+            g = th.empty_like(o) if stride == chw else th.zeros_like(o)
+        ta, ts, c0, c1, wt = coef
+        L.call("vaw_wmse_fwd_bwd_philox", o.data_ptr(), code, stride, L.ptr(x0), seed, offset, L.ptr(t), ta.data_ptr(),
+               ts.data_ptr(), L.ptr(c0), L.ptr(c1), L.ptr(wt), mse.data_ptr(), L.ptr(g), stride, 1.0, mean_code, N, chw,
+               L.stream_ptr())
+        ctx.g, ctx.in_dtype, ctx.code = g, out.dtype, code
+        return mse
+
+    @staticmethod
+    def backward(ctx, gm):
+        g = ctx.g
+        if g is None:
+            return (None,) * 8
+        res = th.empty_like(g)
+        s = gm.float().contiguous()
+        L.call("vaw_scale_rows", g.data_ptr(), s.data_ptr(), res.data_ptr(), ctx.code, g.shape[0], g[0].numel(),
+               L.stream_ptr())
+        return (res.to(ctx.in_dtype),) + (None,) * 7
+
+
 class _VbTerm(th.autograd.Function):
     """terms['vb'] = _vb_terms_bpd(...)["output"] (reference :775-808) with d vb_n / d out from the same pass.
     detach_mean=True is the learned-variance term of the MSE objective (:896-906: the bound must not move the mean
@@ -486,14 +565,53 @@ class GaussianDiffusion:
         """Reference :834-930.  Returns {"mse": [N], "loss": [N], ("align": scalar)} (fp32)."""
         if model_kwargs is None:
             model_kwargs = {}
-        if noise is None:
-            noise = th.randn_like(x_start)      # RNG order as in the reference: noise first ...
-        if t is None:
-            t = self.sample_t(x_start)          # ... then the timesteps (:849-852)
-        assert noise.shape == x_start.shape
-        x0, eps = _f32(x_start), _f32(noise)
+        deferred = x_start if isinstance(x_start, DeferredLatent) else None
+        philox = None
+        if deferred is not None and (noise is not None or not deferred.is_cuda or th.cuda.is_current_stream_capturing()):
+            x_start, deferred = deferred.tensor(), None       # explicit noise / capture: the ordinary two-step path
+        if (noise is None and x_start.is_cuda and self.args.time_dist[0] == "uniform"
+                and not th.cuda.is_current_stream_capturing()):
+            # The noise (and the timesteps, and a deferred latent's eps1) are drawn INSIDE the kernels from the device
+            # generator, in the reference's order (eps1, noise, t) and bit-identical to randn_like / randint (SURVEY 8f-2)
+            philox = _PhiloxDraws(x_start.device)
+            numel = int(np.prod(x_start.shape))
+            off_latent = philox.take(numel) if deferred is not None else 0
+            off_noise = philox.take(numel)
+            N = x_start.shape[0]
+            if t is None:
+                t = th.empty(N, dtype=th.int64, device=x_start.device)
+                if N:
+                    L.call("vaw_randint_philox", philox.seed, philox.take(N), 0, self.num_timesteps, t.data_ptr(), N,
+                           L.stream_ptr())
+        else:
+            if noise is None:
+                noise = th.randn_like(x_start)  # RNG order as in the reference: noise first ...
+            if t is None:
+                t = self.sample_t(x_start)      # ... then the timesteps (:849-852)
         t64 = t.to(th.int64).contiguous()
-        x_t, _ = self._k1(x0, t64, eps, False)
+        if philox is not None:
+            learned_ = self.model_var_type in (ModelVarType.LEARNED, ModelVarType.LEARNED_RANGE)
+            needs_x0 = self.model_mean_type not in (ModelMeanType.EPSILON, ModelMeanType.SCORE) or learned_ or self.loss_type.is_vb()
+            ta, ts, c0, c1, _ = self._tables(x_start.device)
+            chw = int(np.prod(x_start.shape[1:]))
+            x_t = th.empty(tuple(x_start.shape), dtype=th.float32, device=x_start.device)
+            if deferred is not None:
+                lat = _f32(deferred.latent)
+                x0 = th.empty_like(x_t) if needs_x0 else None
+                src = (None, lat.data_ptr(), deferred.latent_scale)
+            else:
+                x0 = _f32(x_start)
+                src = (x0.data_ptr(), None, 1.0)
+            if x_t.numel():
+                L.call("vaw_qsample_philox", src[0], src[1], src[2], philox.seed, off_latent, off_noise, t64.data_ptr(),
+                       ta.data_ptr(), ts.data_ptr(), L.ptr(c0), L.ptr(c1),
+                       x0.data_ptr() if (deferred is not None and x0 is not None) else None, None, x_t.data_ptr(), None,
+                       self.model_mean_type.value, x_t.shape[0], chw, L.stream_ptr())
+            eps = None
+        else:
+            assert noise.shape == x_start.shape
+            x0, eps = _f32(x_start), _f32(noise)
+            x_t, _ = self._k1(x0, t64, eps, False)
 
         if (self.args.learn_align and self.args.align_type == "mse" and th.is_tensor(features)
                 and features.dtype == th.bfloat16 and getattr(getattr(model, "module", model), "supports_fused_align", False)):
@@ -512,7 +630,7 @@ class GaussianDiffusion:
         if learned:
             assert model_output.shape == (B, C * 2, *x_t.shape[2:])
         else:
-            assert model_output.shape == x_start.shape
+            assert model_output.shape == x_t.shape
 
         terms = {}
         if self.loss_type.is_vb():
@@ -530,8 +648,13 @@ class GaussianDiffusion:
             scale = self.num_timesteps / 1000.0 if self.loss_type == LossType.RESCALED_MSE else 1.0
             terms["vb"] = _VbTerm.apply(model_output, x0, x_t, t64, self._reverse_table(x0.device), self.num_timesteps,
                                         self.model_mean_type.value, self.model_var_type.value, True, scale)
-        terms["mse"] = _WeightedMSE.apply(model_output, x0, eps, t64, self._tables(x0.device),
-                                          self.model_mean_type.value)
+        if philox is not None:
+            terms["mse"] = _WeightedMSEPhilox.apply(model_output, x0, t64, self._tables(x_t.device),
+                                                    self.model_mean_type.value, philox.seed, off_noise,
+                                                    int(np.prod(x_t.shape[1:])))
+        else:
+            terms["mse"] = _WeightedMSE.apply(model_output, x0, eps, t64, self._tables(x0.device),
+                                              self.model_mean_type.value)
         if self.args.learn_align:
             assert self.gamma > 0, "Gamma must be greater than 0 for align loss"
             terms["align"] = compute_align_loss(features, sec_out, self.args.align_type)

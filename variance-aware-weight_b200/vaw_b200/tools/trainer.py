@@ -16,10 +16,17 @@ from .. import _lib as L
 L.register("vaw_sample_from_latent", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_float, C.c_void_p])
 
 
-def sample_from_latent(latent, latent_scale=1.0):
+def sample_from_latent(latent, latent_scale=1.0, defer=False):
     """latent [N, 2C, H, W] = (mean | std): returns (mean + std * randn_like(mean)) * latent_scale.  The noise is drawn
-    with torch.randn_like on the device, as the reference does, so a seeded run sees the same Philox stream."""
+    with torch.randn_like on the device, as the reference does, so a seeded run sees the same Philox stream.
+
+    defer=True returns a `DeferredLatent` instead: `GaussianDiffusion.training_losses` accepts it as `x_start` and
+    draws the same eps1 INSIDE its q_sample kernel (same generator stream, same values), so neither eps1 nor, for the
+    eps objective, x_start itself is written to HBM."""
     L.require_cuda(latent)
+    if defer:
+        from .gaussian_diffusion import DeferredLatent
+        return DeferredLatent(latent, latent_scale)
     if latent.dim() < 2 or latent.shape[1] % 2:
         raise ValueError("sample_from_latent expects [N, 2C, ...] moments")
     lat = latent.contiguous().float()
