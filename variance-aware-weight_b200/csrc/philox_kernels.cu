@@ -125,7 +125,7 @@ wmse_philox_kernel(const OutT* __restrict__ out, long long out_stride, const flo
                    unsigned long long seed, unsigned long long off_noise, long long G, const long long* __restrict__ t,
                    const float* __restrict__ tab_a, const float* __restrict__ tab_s, const float* __restrict__ tab_c0,
                    const float* __restrict__ tab_c1, const float* __restrict__ w_tab, float* __restrict__ mse,
-                   OutT* __restrict__ grad, long long grad_stride, float gscale, int mean_type, long long chw) {
+                   OutT* __restrict__ grad, long long grad_stride, float gscale, int mean_type, long long chw, int vec) {
   const long long n = blockIdx.x;
   const long long ti = t ? t[n] : n;
   const float a = __ldg(tab_a + ti), s = __ldg(tab_s + ti);
@@ -138,7 +138,7 @@ wmse_philox_kernel(const OutT* __restrict__ out, long long out_stride, const flo
   const OutT* on = out + n * out_stride;
   OutT* gn = grad ? grad + n * grad_stride : nullptr;
   float acc = 0.f;
-  for (long long i = threadIdx.x; i < chw; i += blockDim.x) {
+  auto one = [&](long long i) {
     const long long li = n * chw + i;
     const float o = (float)on[i];
     const float x = need_x0 ? x0[li] : 0.f;
@@ -147,6 +147,16 @@ wmse_philox_kernel(const OutT* __restrict__ out, long long out_stride, const flo
     const float d = tg - o;
     acc += d * d;
     if (gn) gn[i] = (OutT)(-g * d);
+  };
+  if (vec) {
+    // same thread -> element assignment and the same accumulation order as K2's 128-bit path (wmse_fwd_bwd_kernel), so
+    // a step with in-kernel noise returns bit-identical losses to the step fed the equivalent noise tensor
+    for (long long i4 = threadIdx.x; i4 < (chw >> 2); i4 += blockDim.x) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) one(4 * i4 + k);
+    }
+  } else {
+    for (long long i = threadIdx.x; i < chw; i += blockDim.x) one(i);
   }
   __shared__ float red[8];
   acc = warp_sum(acc);
@@ -238,14 +248,19 @@ extern "C" int vaw_wmse_fwd_bwd_philox(const void* out, int out_dtype, long long
   int rc = aten_grid(N * chw, &grid);
   if (rc) return rc;
   const long long G = 256LL * grid;
+  // mirrors the vector-path condition of vaw_wmse_fwd_bwd_strided (which decides the summation order)
+  const uintptr_t f32_ptrs = (uintptr_t)x0;
+  const uintptr_t out_ptrs = (uintptr_t)out | (uintptr_t)grad_out;
+  const int vec = (chw % 4 == 0) && ((f32_ptrs & 15) == 0) && ((out_ptrs & (out_dtype == 0 ? 15 : 7)) == 0) &&
+                  (out_stride % 4 == 0) && (grad_stride % 4 == 0);
   if (out_dtype == 0)
     wmse_philox_kernel<float><<<(unsigned)N, 256, 0, stream>>>((const float*)out, out_stride, x0, seed, offset_noise, G, t,
                                                               tab_alpha, tab_sigma, tab_c0, tab_c1, w_tab, mse,
-                                                              (float*)grad_out, grad_stride, gscale, mean_type, chw);
+                                                              (float*)grad_out, grad_stride, gscale, mean_type, chw, vec);
   else
     wmse_philox_kernel<bf16><<<(unsigned)N, 256, 0, stream>>>((const bf16*)out, out_stride, x0, seed, offset_noise, G, t,
                                                              tab_alpha, tab_sigma, tab_c0, tab_c1, w_tab, mse,
-                                                             (bf16*)grad_out, grad_stride, gscale, mean_type, chw);
+                                                             (bf16*)grad_out, grad_stride, gscale, mean_type, chw, vec);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }
