@@ -15,8 +15,11 @@ L.register("vaw_attn_bwd", [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p])
 L.register("vaw_attn_bwd_ws", [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p])
 
 
+# T in (256, 264]: tensor cores on the leading 256 tokens + the border strip (attention_border.cu): 258 = U-ViT's
+# sequence, 257 = the ViT teacher's; 265 falls back to the mma.sync kernels
 @pytest.mark.parametrize("B,T,H,hd", [(2, 256, 3, 64), (2, 256, 2, 72), (3, 258, 2, 64), (2, 64, 2, 72), (1, 100, 1, 64),
-                                      (1, 1, 1, 64), (2, 17, 2, 72), (64, 256, 16, 72)])
+                                      (1, 1, 1, 64), (2, 17, 2, 72), (64, 256, 16, 72), (2, 257, 12, 64), (2, 258, 3, 72),
+                                      (1, 264, 2, 64), (1, 265, 1, 64), (64, 258, 12, 64)])
 def test_forward_backward(B, T, H, hd):
     torch.manual_seed(0)
     qkv = (torch.randn(B, T, 3, H, hd, device=DEV) * 0.7).bfloat16()
@@ -83,7 +86,7 @@ def test_unsupported_head_dim_fails_loudly():
         L.call("vaw_attn_fwd", x.data_ptr(), x.data_ptr(), x.data_ptr(), 1, 16, 1, 48, L.stream_ptr())
 
 
-@pytest.mark.parametrize("B,T,H,hd", [(2, 100, 2, 72), (1, 256, 3, 64), (2, 37, 1, 72)])
+@pytest.mark.parametrize("B,T,H,hd", [(2, 100, 2, 72), (1, 256, 3, 64), (2, 37, 1, 72), (2, 258, 2, 64), (1, 257, 2, 72)])
 def test_attention_outputs_stay_inside_their_buffers(B, T, H, hd):
     """Guard bands around o, lse and dqkv (TMA stores clip at the tensor bounds; ragged T exercises the clipping)."""
     torch.manual_seed(3)

@@ -77,7 +77,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                    const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_do_t,
                    const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ CUtensorMap tm_dq_t,
                    const bf16* __restrict__ o, const bf16* __restrict__ d_o, const float* __restrict__ lse2,
-                   bf16* __restrict__ dqkv, int T, int H, float scale, float scale_log2e,
+                   bf16* __restrict__ dqkv, int T, int Ta, int H, float scale, float scale_log2e,
                    const float* __restrict__ delta_in, unsigned long long* __restrict__ trace) {
   using S = BSmem<HD>;
   constexpr bool kTail = S::kTail;
@@ -247,15 +247,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       float nl2 = -INFINITY, delta = 0.f;
       if (q < T) {
         if (delta_in) {   // precomputed by attn_delta_kernel (coalesced, full bandwidth)
-          delta = delta_in[((long long)b * H + h) * T + q];
+          delta = delta_in[((long long)b * H + h) * Ta + q];
         } else {
-          const long long off = (((long long)b * T + q) * H + h) * HD;
+          const long long off = (((long long)b * Ta + q) * H + h) * HD;
           const uint4* po = reinterpret_cast<const uint4*>(o + off);
           const uint4* pd = reinterpret_cast<const uint4*>(d_o + off);
 #pragma unroll
           for (int i = 0; i < HD / 8; ++i) delta += dot8(__ldg(po + i), __ldg(pd + i));
         }
-        nl2 = -lse2[((long long)b * H + h) * T + q];
+        nl2 = -lse2[((long long)b * H + h) * Ta + q];
       }
       s_nl2[q] = nl2;
       s_delta[q] = delta;
@@ -478,16 +478,16 @@ unsigned long long* g_attn_trace = nullptr;   // debug: device buffer of 128 sta
 
 template <int HD>
 int launch_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, float* delta_ws, int B,
-                  int T, int H, cudaStream_t stream) {
+                  int T, int Ta, int H, cudaStream_t stream) {
   using S = BSmem<HD>;
   CUtensorMap tq, tqt, td, tdt;
-  int rc = make_head_map(&tq, qkv, B, T, 3 * H, HD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (!rc) rc = make_head_map(&tqt, qkv, B, T, 3 * H, HD, 16, 64, CU_TENSOR_MAP_SWIZZLE_32B);
-  if (!rc) rc = make_head_map(&td, d_o, B, T, H, HD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (!rc) rc = make_head_map(&tdt, d_o, B, T, H, HD, 16, 64, CU_TENSOR_MAP_SWIZZLE_32B);
+  int rc = make_head_map(&tq, qkv, B, T, Ta, 3 * H, HD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!rc) rc = make_head_map(&tqt, qkv, B, T, Ta, 3 * H, HD, 16, 64, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (!rc) rc = make_head_map(&td, d_o, B, T, Ta, H, HD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!rc) rc = make_head_map(&tdt, d_o, B, T, Ta, H, HD, 16, 64, CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap tg, tgt;
-  if (!rc) rc = make_head_map(&tg, dqkv, B, T, 3 * H, HD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (!rc) rc = make_head_map(&tgt, dqkv, B, T, 3 * H, HD, 16, 64, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (!rc) rc = make_head_map(&tg, dqkv, B, T, Ta, 3 * H, HD, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!rc) rc = make_head_map(&tgt, dqkv, B, T, Ta, 3 * H, HD, 16, 64, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
@@ -495,18 +495,18 @@ int launch_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* 
     configured = true;
   }
   if (delta_ws) {
-    const long long n = (long long)B * T * H;
+    const long long n = (long long)B * Ta * H;   // every token of every sample, the border rows included
     if (256 % H == 0)
       attn_delta_coalesced_kernel<HD><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const bf16*)o, (const bf16*)d_o,
-                                                                                     delta_ws, T, H, n);
+                                                                                     delta_ws, Ta, H, n);
     else
-      attn_delta_kernel<HD><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const bf16*)o, (const bf16*)d_o, delta_ws, T,
+      attn_delta_kernel<HD><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const bf16*)o, (const bf16*)d_o, delta_ws, Ta,
                                                                            H, n);
     VAW_LAUNCH_CHECK();
   }
   const float scale = 1.0f / sqrtf((float)HD);
   attn_bwd_tc_kernel<HD><<<dim3(H, B), kBwdThreads, S::kBytes, stream>>>(
-      tq, tqt, td, tdt, tg, tgt, (const bf16*)o, (const bf16*)d_o, lse2, (bf16*)dqkv, T, H, scale, scale * 1.4426950408889634f,
+      tq, tqt, td, tdt, tg, tgt, (const bf16*)o, (const bf16*)d_o, lse2, (bf16*)dqkv, T, Ta, H, scale, scale * 1.4426950408889634f,
       delta_ws, g_attn_trace);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
@@ -524,8 +524,13 @@ int vaw_attn_bwd_sm100(const void* qkv, const void* o, const void* d_o, const fl
                        int B, int T, int H, int head_dim, cudaStream_t stream) {
   const uintptr_t al = reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(o) |
                        reinterpret_cast<uintptr_t>(d_o) | reinterpret_cast<uintptr_t>(dqkv);
-  if (T > kMaxT || (al & 15) != 0) return VAW_ERR_UNSUPPORTED;
-  if (head_dim == 64) return launch_bwd_tc<64>(qkv, o, d_o, lse2, dqkv, delta_ws, B, T, H, stream);
-  if (head_dim == 72) return launch_bwd_tc<72>(qkv, o, d_o, lse2, dqkv, delta_ws, B, T, H, stream);
-  return VAW_ERR_UNSUPPORTED;
+  if ((al & 15) != 0 || (head_dim != 64 && head_dim != 72)) return VAW_ERR_UNSUPPORTED;
+  // T in (256, 264]: the tensor-core kernel on the leading 256 tokens with the FINAL log-sum-exp and Delta (so its
+  // probabilities are the true ones), then the border strip (attention_border.cu).  Needs the Delta scratch.
+  if (T > kMaxT && !(vaw_attn_border_supported(T) && delta_ws)) return VAW_ERR_UNSUPPORTED;
+  const int Tc = T > kMaxT ? kMaxT : T;
+  int rc = head_dim == 64 ? launch_bwd_tc<64>(qkv, o, d_o, lse2, dqkv, delta_ws, B, Tc, T, H, stream)
+                          : launch_bwd_tc<72>(qkv, o, d_o, lse2, dqkv, delta_ws, B, Tc, T, H, stream);
+  if (rc == VAW_OK && T > kMaxT) rc = vaw_attn_border_bwd(qkv, d_o, lse2, delta_ws, dqkv, B, T, H, head_dim, stream);
+  return rc;
 }

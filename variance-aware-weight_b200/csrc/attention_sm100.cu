@@ -89,7 +89,7 @@ struct Smem {
 template <int HD>
 __global__ void __launch_bounds__(256, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_tail,
-                   bf16* __restrict__ o, float* __restrict__ lse2, int T, int H, float scale_log2e) {
+                   bf16* __restrict__ o, float* __restrict__ lse2, int T, int Ta, int H, float scale_log2e) {
   using S = Smem<HD>;
   constexpr bool kTail = S::kTail;
   // TMEM columns after the softmax (S occupied [0, 256)): each key half rewrites its own S columns in place with P
@@ -227,8 +227,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
   // ---- epilogue: half 0 writes head columns [0, 32) (+ the tail), half 1 columns [32, 64) ----
   const int row = q0 + lane_row;
   const float inv = 1.f / sum;
-  if (row < T && half == 0) lse2[((long long)b * H + h) * T + row] = mx * scale_log2e + log2f(sum);
-  bf16* orow = o + (((long long)b * T + row) * H + h) * HD;
+  if (row < T && half == 0) lse2[((long long)b * H + h) * Ta + row] = mx * scale_log2e + log2f(sum);
+  bf16* orow = o + (((long long)b * Ta + row) * H + h) * HD;
   {
     uint32_t v[32];
     tmem_ld32(trow + kOCol + half * 32, v);
@@ -265,12 +265,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
 
 // ---- host ------------------------------------------------------------------------------------------------------------
 template <int HD>
-int launch_fwd_tc(const void* qkv, void* o, float* lse2, int B, int T, int H, cudaStream_t stream) {
+int launch_fwd_tc(const void* qkv, void* o, float* lse2, int B, int T, int Ta, int H, cudaStream_t stream) {
   using S = Smem<HD>;
   CUtensorMap tm_main, tm_tail;
-  int rc = make_head_map(&tm_main, qkv, B, T, 3 * H, HD, 64, kTile, CU_TENSOR_MAP_SWIZZLE_128B);
+  int rc = make_head_map(&tm_main, qkv, B, T, Ta, 3 * H, HD, 64, kTile, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = make_head_map(&tm_tail, qkv, B, T, 3 * H, HD, 16, kTile, CU_TENSOR_MAP_SWIZZLE_32B);
+  rc = make_head_map(&tm_tail, qkv, B, T, Ta, 3 * H, HD, 16, kTile, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
@@ -279,7 +279,7 @@ int launch_fwd_tc(const void* qkv, void* o, float* lse2, int B, int T, int H, cu
   }
   const float scale = 1.0f / sqrtf((float)HD);
   dim3 grid((T + kTile - 1) / kTile, H, B);
-  attn_fwd_tc_kernel<HD><<<grid, 256, S::kBytes, stream>>>(tm_main, tm_tail, (bf16*)o, lse2, T, H,
+  attn_fwd_tc_kernel<HD><<<grid, 256, S::kBytes, stream>>>(tm_main, tm_tail, (bf16*)o, lse2, T, Ta, H,
                                                             scale * 1.4426950408889634f);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
@@ -289,9 +289,14 @@ int launch_fwd_tc(const void* qkv, void* o, float* lse2, int B, int T, int H, cu
 
 // internal entry (vaw_internal.h): returns VAW_ERR_UNSUPPORTED when the shape is outside this kernel's range
 int vaw_attn_fwd_sm100(const void* qkv, void* o, float* lse2, int B, int T, int H, int head_dim, cudaStream_t stream) {
-  if (T > kMaxKeys || (reinterpret_cast<uintptr_t>(qkv) & 15) != 0 || (reinterpret_cast<uintptr_t>(o) & 15) != 0)
-    return VAW_ERR_UNSUPPORTED;
-  if (head_dim == 64) return launch_fwd_tc<64>(qkv, o, lse2, B, T, H, stream);
-  if (head_dim == 72) return launch_fwd_tc<72>(qkv, o, lse2, B, T, H, stream);
-  return VAW_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) != 0 || (reinterpret_cast<uintptr_t>(o) & 15) != 0) return VAW_ERR_UNSUPPORTED;
+  if (head_dim != 64 && head_dim != 72) return VAW_ERR_UNSUPPORTED;
+  if (T > kMaxKeys && !vaw_attn_border_supported(T)) return VAW_ERR_UNSUPPORTED;
+  // T in (256, 264] (U-ViT: 258, the ViT teacher: 257): tensor cores on the leading 256 tokens of every sample, then
+  // the L-shaped border strip on CUDA cores (attention_border.cu)
+  const int Tc = T > kMaxKeys ? kMaxKeys : T;
+  int rc = head_dim == 64 ? launch_fwd_tc<64>(qkv, o, lse2, B, Tc, T, H, stream)
+                          : launch_fwd_tc<72>(qkv, o, lse2, B, Tc, T, H, stream);
+  if (rc == VAW_OK && T > kMaxKeys) rc = vaw_attn_border_fwd(qkv, o, lse2, B, T, H, head_dim, stream);
+  return rc;
 }

@@ -54,6 +54,12 @@ int vaw_attn_fwd_sm100(const void* qkv, void* o, float* lse2, int B, int T, int 
 int vaw_attn_bwd_sm100(const void* qkv, const void* o, const void* d_o, const float* lse2, void* dqkv, float* delta_ws,
                        int B, int T, int H, int head_dim, cudaStream_t stream);
 
+// sequences slightly longer than the tensor-core tile (attention_border.cu): T in (256, 264]
+int vaw_attn_border_supported(int T);
+int vaw_attn_border_fwd(const void* qkv, void* o, float* lse2, int B, int T, int H, int head_dim, cudaStream_t stream);
+int vaw_attn_border_bwd(const void* qkv, const void* d_o, const float* lse2, const float* delta, void* dqkv, int B, int T,
+                        int H, int head_dim, cudaStream_t stream);
+
 extern "C" {
 int vaw_align_mse_finish(const float* part, long long nparts, long long n, float* loss, cudaStream_t stream);
 int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream);

@@ -138,15 +138,17 @@ inline PFN_encodeTiled encode_fn() {
 
 // 4-D bf16 map over a packed activation [B, T, S, hd] (S = slots per token: 3*H for qkv, H for o / dO):
 // dims (hd, S, T, B); box (cols, 1, rows, 1).  Out-of-range columns / rows read as zero.
-inline int make_head_map(CUtensorMap* map, const void* base, int B, int T, int slots, int hd, int box_cols, int box_rows,
-                  CUtensorMapSwizzle swz) {
+// T = rows per sample the kernel may touch (TMA clips loads / stores there), Ta = rows per sample in memory (the batch
+// stride): Ta > T addresses the leading T tokens of longer sequences (attention_border.cu handles the rest)
+inline int make_head_map(CUtensorMap* map, const void* base, int B, int T, int Ta, int slots, int hd, int box_cols,
+                         int box_rows, CUtensorMapSwizzle swz) {
   PFN_encodeTiled fn = encode_fn();
   if (!fn) {
     vaw_set_error("cuTensorMapEncodeTiled entry point not available");
     return VAW_ERR_CUDA;
   }
   cuuint64_t dims[4] = {(cuuint64_t)hd, (cuuint64_t)slots, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)hd * 2, (cuuint64_t)slots * hd * 2, (cuuint64_t)T * slots * hd * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)hd * 2, (cuuint64_t)slots * hd * 2, (cuuint64_t)Ta * slots * hd * 2};
   cuuint32_t box[4] = {(cuuint32_t)box_cols, 1u, (cuuint32_t)box_rows, 1u};
   cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
