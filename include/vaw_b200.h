@@ -254,6 +254,12 @@ typedef struct vaw_gemm_args {
 } vaw_gemm_args;
 
 int vaw_gemm_bf16(const vaw_gemm_args* args, vaw_stream_t stream);
+/* Weight gradient of a Linear fed one row per SAMPLE (adaLN-Zero modulation, models/dit.py:118-124; TimestepEmbedder
+ * :41-79): out[M, N] fp32 (ldo) (+)= A^T B with A [K, M] (lda) and B [K, N] (ldb) bf16, K = batch size.  All epilogue
+ * (1 GFLOP for 32 MB of output at DiT-XL/2): warp-level MMAs out of shared memory, fragments stored directly.  Returns
+ * VAW_ERR_UNSUPPORTED for operands that are not 16-byte aligned / lda, ldb not multiples of 8 (use vaw_gemm_bf16). */
+int vaw_wgrad_smallk(const void* A, long long lda, const void* B, long long ldb, float* out, long long ldo, int M, int N,
+                     int K, int accumulate, vaw_stream_t stream);
 
 /* ---- K4: flash-style attention ------------------------------------------------------------------------------------
  * Replaces F.scaled_dot_product_attention inside timm Attention (models/dit.py:126) / models/uvit.py:72-75 and its

@@ -235,3 +235,27 @@ def test_outputs_stay_inside_their_buffers(epi):
         _rg(A, B, 0, 0, M, N, K, L.EPI_F32, out=o, bias=bias)
         check(b1)
         assert relerr(o, A.float() @ B.float().t() + bias) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(6912, 1152, 64), (768, 384, 8), (300, 130, 5), (256, 256, 200), (128, 128, 16)])
+@pytest.mark.parametrize("accumulate", [0, 1])
+def test_wgrad_smallk_vs_torch(M, N, K, accumulate):
+    """vaw_wgrad_smallk: dW = A^T B over K = batch rows (the adaLN / timestep-embedder weight gradients), ragged M / N,
+    K not a multiple of 16, overwrite and accumulate; bit-reproducible."""
+    import ctypes as C
+    L.register("vaw_wgrad_smallk", [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
+                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p])
+    torch.manual_seed(M + K)
+    lda, ldb = (M + 7) // 8 * 8 + 8, (N + 7) // 8 * 8
+    A = torch.randn(K, lda, device=DEV).bfloat16(); B = torch.randn(K, ldb, device=DEV).bfloat16()
+    ldo = N + (N & 1)
+    base = torch.randn(M, ldo, device=DEV)
+    out = base.clone()
+    L.call("vaw_wgrad_smallk", A.data_ptr(), lda, B.data_ptr(), ldb, out.data_ptr(), ldo, M, N, K, accumulate, L.stream_ptr())
+    want = A[:, :M].float().t() @ B[:, :N].float() + (base[:, :N] if accumulate else 0)
+    assert relerr(out[:, :N], want) < 1e-5
+    if ldo > N:
+        assert torch.equal(out[:, N:], base[:, N:])      # the padding column is not touched
+    out2 = base.clone()
+    L.call("vaw_wgrad_smallk", A.data_ptr(), lda, B.data_ptr(), ldb, out2.data_ptr(), ldo, M, N, K, accumulate, L.stream_ptr())
+    assert torch.equal(out, out2)

@@ -210,6 +210,14 @@ void carve_infer(const vaw_dit_cfg& c, void* base, Ws& w) {
   w.bytes = k.cur;
 }
 
+// dW[M, N] (+)= A^T B over K = batch rows: the short-K kernel when the layout allows, the general GEMM otherwise
+int wgrad_over_batch(const bf16* A, long long lda, const bf16* Bm, long long ldb, float* out, int M, int N, int K, int acc,
+                     cudaStream_t s) {
+  const int rc = vaw_wgrad_smallk(A, lda, Bm, ldb, out, N, M, N, K, acc, s);
+  if (rc != VAW_ERR_UNSUPPORTED) return rc;
+  return G(A, lda, 1, Bm, ldb, 1, M, N, K, VAW_EPI_F32).out(out).acc(acc).run(s);
+}
+
 int check_cfg(const vaw_dit_cfg* c) {
   VAW_CHECK_ARG(c, "dit: null config");
   VAW_CHECK_ARG(c->B > 0 && c->T > 0 && c->D > 0 && c->H > 0 && c->depth > 0 && c->depth <= kMaxDepth,
@@ -476,8 +484,7 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
       TRY(vaw_dit_block_finish(pa(i), w.part_b, w.part_c, w.part_d, B, ch, D, mod, ldm, dmod, dmod_b,
                                Gd + L.off[pb + B_FC2_B], Gd + L.off[pb + B_PROJ_B],
                                Gd + L.off[P_ADA_B] + (long long)i * 6 * D, acc, s));
-      TRY(G(dmod_b, ldm, 1, w.c_silu, D, 1, 6 * D, D, B, VAW_EPI_F32)
-              .out(Gd + L.off[P_ADA_W] + (long long)i * 6 * D * D).acc(acc).run(s));
+      TRY(wgrad_over_batch(dmod_b, ldm, w.c_silu, D, Gd + L.off[P_ADA_W] + (long long)i * 6 * D * D, 6 * D, D, B, acc, s));
     }
     if (events && events[i]) VAW_CUDA_TRY(cudaEventRecord(reinterpret_cast<cudaEvent_t>(events[i]), s));
   }
@@ -486,7 +493,7 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
   const int NA = c.depth * 6 * D;
   TRY(vaw_cast_f32_bf16(w.dmod_final, w.dmod_final_b, (long long)B * 2 * D, s));
   TRY(vaw_colsum_f32_small(w.dmod_final, 2LL * D, B, 2 * D, Gd + L.off[P_FADA_B], acc, s));
-  TRY(G(w.dmod_final_b, 2LL * D, 1, w.c_silu, D, 1, 2 * D, D, B, VAW_EPI_F32).out(Gd + L.off[P_FADA_W]).acc(acc).run(s));
+  TRY(wgrad_over_batch(w.dmod_final_b, 2LL * D, w.c_silu, D, Gd + L.off[P_FADA_W], 2 * D, D, B, acc, s));
   TRY(G(w.dmod_all_b, NA, 0, Pb + L.off[P_ADA_W], D, 1, B, D, NA, VAW_EPI_F32).out(w.dcs)
           .autosplit(w.split_ws, w.split_elems).run(s));
   TRY(G(w.dmod_final_b, 2LL * D, 0, Pb + L.off[P_FADA_W], D, 1, B, D, 2 * D, VAW_EPI_F32).out(w.dcs).acc(1).run(s));
@@ -494,10 +501,10 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
   TRY(vaw_cond_bwd(w.dcs, w.c, w.dc, w.dc_b, B * D, s));
   if (c.table_rows) TRY(vaw_embedding_grad(w.dc, y, Gd + L.off[P_YTAB], c.table_rows, B, D, acc, s));
   TRY(vaw_colsum_f32_small(w.dc, D, B, D, Gd + L.off[P_T2_B], acc, s));
-  TRY(G(w.dc_b, D, 1, w.t_h, D, 1, D, D, B, VAW_EPI_F32).out(Gd + L.off[P_T2_W]).acc(acc).run(s));
+  TRY(wgrad_over_batch(w.dc_b, D, w.t_h, D, Gd + L.off[P_T2_W], D, D, B, acc, s));
   TRY(G(w.dc_b, D, 0, Pb + L.off[P_T2_W], D, 1, B, D, D, VAW_EPI_DSILU).out(w.dth).aux(w.t_h_pre).run(s));
   TRY(vaw_colsum_bf16(w.dth, D, B, D, w.cpart, 8, Gd + L.off[P_T0_B], acc, s));
-  TRY(G(w.dth, D, 1, w.freq, c.freq_dim, 1, D, c.freq_dim, B, VAW_EPI_F32).out(Gd + L.off[P_T0_W]).acc(acc).run(s));
+  TRY(wgrad_over_batch(w.dth, D, w.freq, c.freq_dim, Gd + L.off[P_T0_W], D, c.freq_dim, B, acc, s));
   // ---- patch embedding: x[0] = patches W^T + b + pos ----
   TRY(vaw_gate_bwd(w.dx, nullptr, nullptr, 0, w.dy, w.part, T, B, ch, M, D, s));
   TRY(vaw_finish_all(w.part, 0, B, ch, D, nullptr, 0, Gd + L.off[P_XEMB_B], acc, s));

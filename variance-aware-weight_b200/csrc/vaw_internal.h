@@ -61,6 +61,8 @@ int vaw_attn_border_bwd(const void* qkv, const void* d_o, const float* lse2, con
                         int H, int head_dim, cudaStream_t stream);
 
 extern "C" {
+int vaw_wgrad_smallk(const void* A, long long lda, const void* B, long long ldb, float* out, long long ldo, int M, int N,
+                     int K, int accumulate, cudaStream_t stream);
 int vaw_align_mse_finish(const float* part, long long nparts, long long n, float* loss, cudaStream_t stream);
 int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream);
 int vaw_attn_fwd(const void* qkv, void* o, float* lse2, int B, int T, int H, int head_dim, cudaStream_t stream);
