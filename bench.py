@@ -430,6 +430,8 @@ def run_native(args, rank, world, local_rank):
         n0 = L.launch_count()
         ms_dev = timed(lambda i: step(dev_x[i % pool], dev_y[i % pool], px_of(i)), args.steps)
         launches = int(L.launch_count() - n0)
+        if graphed is not None:   # kernels replayed from the graph do not pass through the library's launch counter
+            launches += graphed.launches_per_replay * args.steps
     clocks = clk.summary()
     if world > 1:
         assert_ranks_agree(model, sampler, dist, dev)

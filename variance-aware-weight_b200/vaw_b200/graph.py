@@ -56,8 +56,10 @@ class GraphedTrainingLosses:
         torch.cuda.current_stream(dev).wait_stream(side)
         self._clear_grads()                 # captured in overwrite mode: a replay REPLACES the gradients
         self.graph = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
         with torch.cuda.graph(self.graph):
             self._terms = self._run()
+        self.launches_per_replay = L.launch_count() - n0   # library kernels inside one replay (accounting, bench.py)
         self._terms = {k: v.detach() for k, v in self._terms.items()}
         self._saved_grads = None
 
