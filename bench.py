@@ -75,6 +75,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-leg", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="config 2: eager launches instead of the CUDA graph")
+    ap.add_argument("--no-shard", action="store_true", help="N > 1: all-reduce + replicated AdamW instead of the sharded optimizer")
     a = ap.parse_args()
     c = dict(CONFIGS[a.config])
     if a.model and c["family"] == "dit":
@@ -313,11 +314,13 @@ def build_native(args, dev):
     return model, diffusion, teacher
 
 
-def assert_ranks_agree(model, sampler, dist, dev):
+def assert_ranks_agree(model, sampler, dist, dev, net_or_model=None):
     """After an optimizer step every rank must hold bit-identical parameters (identical all-reduced gradients ->
     identical AdamW) and an identical sampler history (every rank applies the same gathered update, resample.py:76-79).
     Exact integer checksums over the raw bit patterns, compared across ranks; outside the timed region."""
     import torch
+    if hasattr(net_or_model, "gather_master"):
+        net_or_model.gather_master()          # sharded optimizer: complete the fp32 master before comparing it
     sums = [model._flat.detach().view(torch.int32).to(torch.int64).sum()]
     if getattr(sampler, "_hist_dev", None) is not None:
         sums.append(sampler._hist_dev.view(torch.int64).sum())
@@ -350,14 +353,16 @@ def run_native(args, rank, world, local_rank):
     cfg = args.cfg
     B = cfg["batch"]
     model, diffusion, teacher = build_native(args, dev)
-    net = DataParallel(model) if world > 1 else model
+    # N > 1: gradients reduce-scattered per block, AdamW on 1/N of the large tensors per rank, bf16 shadows all-gathered
+    # (vaw_b200.parallel.ShardedGradSync); --no-shard keeps all-reduce + replicated AdamW
+    net = DataParallel(model, shard_optimizer=not args.no_shard) if world > 1 else model
     sampler = rs.create_named_schedule_sampler(cfg["sampler"], diffusion)
     loss_aware = cfg["sampler"] == "loss-second-moment"
     if loss_aware:
         hist, counts = synthetic_history(0)
         sampler.load_history(hist, counts, dev)
         sampler.ragged_batches = False     # every rank passes B samples: no size exchange, no host sync
-    opt = FusedAdamW(model, lr=1e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0)
+    opt = FusedAdamW(net, lr=1e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0)
 
     # synthetic data: a small pool of batches, resident in HBM (value) and in pinned host memory (e2e)
     pool = 4
@@ -423,7 +428,7 @@ def run_native(args, rank, world, local_rank):
         step(dev_x[i % pool], dev_y[i % pool], px_of(i))
         if i == 0 and world > 1:
             torch.cuda.synchronize()
-            assert_ranks_agree(model, sampler, dist, dev)
+            assert_ranks_agree(model, sampler, dist, dev, net)
     torch.cuda.synchronize()
 
     with ClockSampler(local_rank) as clk:
@@ -434,7 +439,7 @@ def run_native(args, rank, world, local_rank):
             launches += graphed.launches_per_replay * args.steps
     clocks = clk.summary()
     if world > 1:
-        assert_ranks_agree(model, sampler, dist, dev)
+        assert_ranks_agree(model, sampler, dist, dev, net)
 
     # end-to-end: batch from pinned host memory every step, loss read back every step
     def e2e_step(i):
@@ -471,6 +476,8 @@ def run_native(args, rank, world, local_rank):
         line["config"]["cuda_graph"] = "K1 -> forward -> K2 -> backward replayed as one CUDA graph per step"
     if world > 1:
         line["rank_consistency"] = "flat parameters and sampler history bit-identical on all ranks after step 1 and after the timed region"
+        line["config"]["data_parallel"] = ("all-reduce + replicated AdamW" if (args.no_shard or getattr(net, "_shard_sync", None) is None)
+                                           else "reduce-scatter + 1/N AdamW + bf16 all-gather (sharded optimizer)")
 
     if rank == 0 and not args.no_kernel_leg:
         line["roofline"] = kernel_leg(args, dev, peaks)

@@ -362,6 +362,13 @@ int vaw_adamw_step_amp(float* p, const float* g, float* m, float* v, void* p_bf1
                        double beta1, double beta2, double eps, double weight_decay, long long step, double grad_scale,
                        double ema_decay, const float* clip_coef, const float* inv_scale, const float* found_inf,
                        vaw_stream_t stream);
+/* The same update over a list of element ranges of the flat buffers in ONE launch: ranges = DEVICE array of n_ranges
+ * (offset, count) pairs (multiples of 4), max_count = the largest count.  Used by the sharded data-parallel optimizer
+ * (every rank updates its 1/W slice of each block's weights plus the replicated small tensors). */
+int vaw_adamw_step_ranges(float* p, const float* g, float* m, float* v, void* p_bf16, float* ema, const long long* ranges,
+                          int n_ranges, long long max_count, double lr, double beta1, double beta2, double eps,
+                          double weight_decay, long long step, double grad_scale, double ema_decay,
+                          const float* clip_coef, const float* inv_scale, const float* found_inf, vaw_stream_t stream);
 /* Global L2 norm of the flat gradient buffer and the clip_grad_norm_ coefficient (tools/trainer.py:60-62), kept on the
  * device: out[0] = ||grad_scale * g||, out[1] = min(1, max_norm / (out[0] + 1e-6)); pass out + 1 as clip_coef above.
  * part: 1024 floats of scratch. */

@@ -67,6 +67,60 @@ def _uvit_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _shard_worker(rank, world, port, q):
+    """DataParallel(shard_optimizer=True): reduce-scatter + 1/W AdamW + bf16 all-gather must leave every rank with the
+    parameters (fp32 master after gather_master, bf16 shadow, moments of the owned slices) that all-reduce + replicated
+    AdamW produces - bit for bit at two ranks (a two-term average has one rounding whichever collective computes it)."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "variance-aware-weight_b200"), os.path.join(ROOT, "tests")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from gpu_util import dezero
+        from vaw_b200.models.dit import DiT
+        from vaw_b200.optim import DataParallel, FusedAdamW
+        from vaw_b200.tools import gaussian_diffusion as gd
+        d = gd.create_gaussian_diffusion(noise_schedule="cosine")
+        B = 4
+        g = torch.Generator().manual_seed(11)
+        data = [(torch.randn(world * B, 4, 16, 16, generator=g), torch.randint(0, 10, (world * B,), generator=g),
+                 torch.randn(world * B, 4, 16, 16, generator=g), torch.randint(0, 1000, (world * B,), generator=g))
+                for _ in range(3)]
+        sl = slice(rank * B, (rank + 1) * B)
+        results = {}
+        for shard in (False, True):
+            torch.manual_seed(5)
+            m = DiT(image_size=16, patch_size=2, in_channels=4, hidden_size=128, depth=3, num_heads=2,
+                    class_dropout_prob=0.0, num_classes=10, learn_align=False).to(dev).train()
+            dezero(m)
+            net = DataParallel(m, device_ids=[rank], shard_optimizer=shard)
+            assert (net._shard_sync is not None) == shard
+            opt = FusedAdamW(net, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.01)
+            losses = []
+            for X, Y, E, T in data:
+                terms = d.training_losses(net, X[sl].to(dev), None, t=T[sl].to(dev), model_kwargs={"y": Y[sl].to(dev)},
+                                          noise=E[sl].to(dev))
+                terms["loss"].mean().backward()
+                opt.step(); opt.zero_grad()
+                losses.append(terms["loss"].detach().clone())
+            shadow = m._shadow.clone()
+            sd = {k: v.detach().clone() for k, v in net.state_dict().items()}     # gathers the fp32 master when sharded
+            results[shard] = (losses, shadow, sd, m._flat.detach().clone())
+        la, sa, da, fa = results[False]
+        lb, sb, db, fb = results[True]
+        assert all(torch.equal(x, y) for x, y in zip(la, lb)), "losses differ between the two modes"
+        assert torch.equal(sa, sb), "bf16 shadows differ"
+        assert torch.equal(fa, fb), "fp32 master differs after gather_master"
+        assert all(torch.equal(da[k], db[k]) for k in da)
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()[-1800:]))
+    finally:
+        dist.destroy_process_group()
+
+
 def _worker(rank, world, port, q):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "variance-aware-weight_b200"), os.path.join(ROOT, "tests")]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -146,3 +200,8 @@ def test_two_gpu_data_parallel_parity():
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_gpu_uvit_data_parallel_parity():
     _run(_uvit_worker, 30000)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_optimizer_equals_all_reduce_path():
+    _run(_shard_worker, 30400)

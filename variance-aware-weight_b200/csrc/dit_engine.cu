@@ -23,7 +23,10 @@ enum ParamId : int {
   P_XEMB_W = 0, P_XEMB_B, P_T0_W, P_T0_B, P_T2_W, P_T2_B, P_YTAB, P_POS, P_FADA_W, P_FADA_B, P_FLIN_W, P_FLIN_B,
   P_PR0_W, P_PR0_B, P_PR2_W, P_PR2_B, P_PR4_W, P_PR4_B, P_ADA_W, P_ADA_B, P_BLOCK0
 };
-enum BlockParam : int { B_QKV_W = 0, B_QKV_B, B_PROJ_W, B_PROJ_B, B_FC1_W, B_FC1_B, B_FC2_W, B_FC2_B, B_COUNT };
+// The four weight matrices of a block are contiguous and its four bias vectors follow: the data-parallel wrapper
+// reduce-scatters the former (the optimizer state is sharded over ranks) and all-reduces the latter (a few KB, kept
+// replicated because the forward reads biases from the fp32 master buffer) - one collective each per block.
+enum BlockParam : int { B_QKV_W = 0, B_PROJ_W, B_FC1_W, B_FC2_W, B_QKV_B, B_PROJ_B, B_FC1_B, B_FC2_B, B_COUNT };
 
 struct Layout {
   long long off[P_BLOCK0 + kMaxDepth * B_COUNT];
@@ -53,11 +56,12 @@ void compute_layout(const vaw_dit_cfg& c, Layout& L) {
   const long long pd = c.learn_align ? c.proj_dim : 0, zd = c.learn_align ? c.z_dim : 0;
   add(pd * D); add(pd); add(pd * pd); add(pd); add(zd * pd); add(zd);  // projectors.{0,2,4}
   add((long long)c.depth * 6 * D * D); add((long long)c.depth * 6 * D);  // all blocks' adaLN_modulation.1, stacked
-  for (int i = 0; i < c.depth; ++i) {
-    add(3 * D * D); add(3 * D);                          // attn.qkv
-    add(D * D); add(D);                                  // attn.proj
-    add((long long)c.hidden * D); add(c.hidden);         // mlp.fc1
-    add(D * (long long)c.hidden); add(D);                // mlp.fc2
+  for (int i = 0; i < c.depth; ++i) {   // order of BlockParam
+    add(3 * D * D);                                      // attn.qkv.weight
+    add(D * D);                                          // attn.proj.weight
+    add((long long)c.hidden * D);                        // mlp.fc1.weight
+    add(D * (long long)c.hidden);                        // mlp.fc2.weight
+    add(3 * D); add(D); add(c.hidden); add(D);           // the four biases
   }
   L.n = n;
   L.total = cur;

@@ -180,20 +180,19 @@ __global__ void colsum_f32_small_kernel(const float* __restrict__ a, long long l
 
 // Fused AdamW over the flat parameter buffer (torch.optim.AdamW semantics, decoupled weight decay) that also
 // refreshes the bf16 shadow used by the GEMMs and optionally the EMA copy (trainer.py:12-18).
-__global__ void __launch_bounds__(256)
-adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-             bf16* __restrict__ p_bf16, float* __restrict__ ema, long long n, float lr, float beta1, float beta2,
-             float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, float ema_decay,
-             const float* __restrict__ clip_coef, const float* __restrict__ inv_scale,
-             const float* __restrict__ found_inf) {
+__device__ __forceinline__ void adamw_span(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                           float* __restrict__ v, bf16* __restrict__ p_bf16, float* __restrict__ ema,
+                                           long long n, long long first, long long stride, float lr, float beta1,
+                                           float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale,
+                                           float ema_decay, const float* __restrict__ clip_coef,
+                                           const float* __restrict__ inv_scale, const float* __restrict__ found_inf) {
   // GradScaler semantics without a host round trip (trainer.py:124-129): a step whose gradients held an inf / nan is
   // skipped as a whole - parameters, moments, the bf16 shadow and the EMA copy stay as they were
   if (found_inf && __ldg(found_inf) != 0.f) return;
   if (clip_coef) grad_scale *= __ldg(clip_coef);   // device-side clip_grad_norm_ coefficient (vaw_grad_clip_coef)
   if (inv_scale) grad_scale *= __ldg(inv_scale);   // 1 / loss scale, kept on the device by torch's GradScaler
   const long long n4 = n >> 2;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+  for (long long i = first; i < n4; i += stride) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
     const float4 gv = ldg_stream_f4(reinterpret_cast<const float4*>(g) + i);
     float4 mv = reinterpret_cast<float4*>(m)[i];
@@ -228,6 +227,31 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
       reinterpret_cast<float4*>(ema)[i] = e;
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             bf16* __restrict__ p_bf16, float* __restrict__ ema, long long n, float lr, float beta1, float beta2,
+             float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, float ema_decay,
+             const float* __restrict__ clip_coef, const float* __restrict__ inv_scale,
+             const float* __restrict__ found_inf) {
+  adamw_span(p, g, m, v, p_bf16, ema, n, (long long)blockIdx.x * blockDim.x + threadIdx.x,
+             (long long)gridDim.x * blockDim.x, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale, ema_decay, clip_coef,
+             inv_scale, found_inf);
+}
+
+// The same update over a LIST of element ranges of the flat buffers in one launch (blockIdx.y = range): the sharded
+// data-parallel optimizer owns ~60 slices per rank plus the replicated small tensors; one launch instead of ~120.
+__global__ void __launch_bounds__(256)
+adamw_ranges_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                    bf16* __restrict__ p_bf16, float* __restrict__ ema, const long long* __restrict__ ranges, float lr,
+                    float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale,
+                    float ema_decay, const float* __restrict__ clip_coef, const float* __restrict__ inv_scale,
+                    const float* __restrict__ found_inf) {
+  const long long off = ranges[2 * blockIdx.y], n = ranges[2 * blockIdx.y + 1];
+  adamw_span(p + off, g + off, m + off, v + off, p_bf16 ? p_bf16 + off : nullptr, ema ? ema + off : nullptr, n,
+             (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, lr, beta1, beta2, eps,
+             wd, bc1, bc2_sqrt, grad_scale, ema_decay, clip_coef, inv_scale, found_inf);
 }
 
 // Global gradient norm of the flat gradient buffer and the clip_grad_norm_ coefficient (trainer.py:60-62 ->
@@ -527,6 +551,26 @@ extern "C" int vaw_adamw_step_amp(float* p, const float* g, float* m, float* v, 
                                                     (float)beta2, (float)eps, (float)weight_decay, (float)bc1,
                                                     (float)sqrt(bc2), (float)grad_scale, (float)ema_decay, clip_coef,
                                                     inv_scale, found_inf);
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+// ranges: DEVICE array of n_ranges (offset, count) pairs in elements; offsets and counts multiples of 4
+extern "C" int vaw_adamw_step_ranges(float* p, const float* g, float* m, float* v, void* p_bf16, float* ema,
+                                     const long long* ranges, int n_ranges, long long max_count, double lr, double beta1,
+                                     double beta2, double eps, double weight_decay, long long step, double grad_scale,
+                                     double ema_decay, const float* clip_coef, const float* inv_scale,
+                                     const float* found_inf, cudaStream_t stream) {
+  VAW_CHECK_ARG(p && g && m && v && ranges && n_ranges >= 0 && n_ranges <= 65535 && step >= 1 && max_count >= 0,
+                "vaw_adamw_step_ranges: bad arguments");
+  if (n_ranges == 0 || max_count == 0) return VAW_OK;
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  unsigned gx = grid_for(max_count / 4);
+  if (gx > 256) gx = 256;
+  adamw_ranges_kernel<<<dim3(gx, (unsigned)n_ranges), 256, 0, stream>>>(
+      p, g, m, v, (bf16*)p_bf16, ema, ranges, (float)lr, (float)beta1, (float)beta2, (float)eps, (float)weight_decay,
+      (float)bc1, (float)sqrt(bc2), (float)grad_scale, (float)ema_decay, clip_coef, inv_scale, found_inf);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }

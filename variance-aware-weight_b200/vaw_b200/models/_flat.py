@@ -44,6 +44,7 @@ class FlatEngineModule(nn.Module):
         self._fwd_serial = 0
         self._events = None
         self._post_backward = None
+        self._before_cast = None   # DataParallel(shard_optimizer=True): completes the fp32 master before it is re-cast
         self._slot_cache = None
 
     def __deepcopy__(self, memo):
@@ -53,7 +54,8 @@ class FlatEngineModule(nn.Module):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         drop = {"_flat": None, "_shadow": None, "_gflat": None, "_ws": None, "_events": None, "_post_backward": None,
-                "_slot_cache": None, "_ws_batch": -1, "_shadow_version": -1, "_ws_inf": None, "_ws_inf_batch": -1}
+                "_slot_cache": None, "_ws_batch": -1, "_shadow_version": -1, "_ws_inf": None, "_ws_inf_batch": -1,
+                "_before_cast": None}
         for k, v in self.__dict__.items():
             new.__dict__[k] = drop[k] if k in drop else copy.deepcopy(v, memo)
         return new
@@ -90,6 +92,8 @@ class FlatEngineModule(nn.Module):
         # (tools/trainer.py:12-18 `target_dict[key].data.copy_`).  That model only ever runs in eval mode, so an eval
         # forward always re-casts (one 6 B/param pass, ~2 % of a DiT-XL sampling forward); training keeps the check.
         if v != self._shadow_version or not self.training:
+            if self._before_cast is not None:
+                self._before_cast()
             L.call("vaw_cast_f32_bf16", self._flat.data_ptr(), self._shadow.data_ptr(), self._flat.numel(), L.stream_ptr())
             self._shadow_version = v
 

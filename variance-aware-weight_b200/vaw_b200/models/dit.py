@@ -164,8 +164,9 @@ class DiT(FlatEngineModule):
             slots.append((b.adaLN_modulation[1].weight, off[18] + i * 6 * D * D))
             slots.append((b.adaLN_modulation[1].bias, off[19] + i * 6 * D))
             base = 20 + 8 * i
-            for j, p in enumerate((b.attn.qkv.weight, b.attn.qkv.bias, b.attn.proj.weight, b.attn.proj.bias,
-                                   b.mlp.fc1.weight, b.mlp.fc1.bias, b.mlp.fc2.weight, b.mlp.fc2.bias)):
+            # engine order (csrc/dit_engine.cu BlockParam): the four weight matrices, then the four biases
+            for j, p in enumerate((b.attn.qkv.weight, b.attn.proj.weight, b.mlp.fc1.weight, b.mlp.fc2.weight,
+                                   b.attn.qkv.bias, b.attn.proj.bias, b.mlp.fc1.bias, b.mlp.fc2.bias)):
                 slots.append((p, off[base + j]))
         return slots, total
 
@@ -189,6 +190,20 @@ class DiT(FlatEngineModule):
                               (off[19] + i * 6 * D, off[19] + (i + 1) * 6 * D)])
         tail = [(0, off[18])]
         return per_block, tail, total
+
+    def block_shard_ranges(self):
+        """For the sharded-optimizer data-parallel mode: per block, the contiguous ranges of LARGE tensors (the four
+        weight matrices; the block's slice of the stacked adaLN weight) whose gradients are reduce-scattered, and the
+        SMALL ones (the four biases; the adaLN bias slice) that stay replicated (all-reduced)."""
+        off, num, total = self._layout()
+        D = self.hidden_size
+        big, small = [], []
+        for i in range(self.depth):
+            base = 20 + 8 * i
+            big.append([(off[base], off[base + 4]), (off[18] + i * 6 * D * D, off[18] + (i + 1) * 6 * D * D)])
+            small.append([(off[base + 4], off[base + 7] + num[base + 7]), (off[19] + i * 6 * D, off[19] + (i + 1) * 6 * D)])
+        tail = [(0, off[18])]
+        return big, small, tail, total
 
     # ------------------------------------------------------------------------------------------------
     def initialize_weights(self):

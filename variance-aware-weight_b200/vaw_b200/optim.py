@@ -20,12 +20,24 @@ from contextlib import nullcontext
 import torch
 
 from . import _lib as L
-from .parallel import FlatGradSync, dist_ready
+from .parallel import FlatGradSync, ShardedGradSync, dist_ready
 
 _PTR, _LL, _D = C.c_void_p, C.c_longlong, C.c_double
 L.register("vaw_adamw_step", [_PTR] * 6 + [_LL] + [_D] * 5 + [_LL, _D, _D, _PTR, _PTR])
 L.register("vaw_adamw_step_amp", [_PTR] * 6 + [_LL] + [_D] * 5 + [_LL, _D, _D, _PTR, _PTR, _PTR, _PTR])
+L.register("vaw_adamw_step_ranges", [_PTR] * 7 + [C.c_int, _LL] + [_D] * 5 + [_LL, _D, _D, _PTR, _PTR, _PTR, _PTR])
 L.register("vaw_grad_clip_coef", [_PTR, _LL, _D, _D, _PTR, _PTR, _PTR])
+
+
+def _intersect(ranges_a, ranges_b):
+    """Intersection of two lists of half-open element ranges."""
+    out = []
+    for a0, a1 in ranges_a:
+        for b0, b1 in ranges_b:
+            lo, hi = max(a0, b0), min(a1, b1)
+            if hi > lo:
+                out.append((lo, hi))
+    return sorted(out)
 
 
 def _unwrap(model):
@@ -54,6 +66,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self._group_ranges = None
         self._flat_ptr = None
         self._loaded = None
+        self._shard_ranges = None
         if params is None:
             params = [p for p in model.parameters() if p.requires_grad]
         # the param-group keys of torch.optim.AdamW, so that a state_dict saved here loads into torch's AdamW with the
@@ -161,6 +174,13 @@ class FusedAdamW(torch.optim.Optimizer):
                    self._norm_ws.data_ptr(), self.grad_norm.data_ptr(), L.stream_ptr())
             clip = self.grad_norm.data_ptr() + 4
         ema_decay = float(self.ema_decay if self.ema_decay is not None else 0.0)
+        shard = getattr(self.model, "_shard_sync", None)
+        if shard is not None:
+            if max_grad_norm:
+                raise L.VawError("FusedAdamW: gradient clipping needs the full gradient on every rank; it is not "
+                                 "available with DataParallel(shard_optimizer=True)")
+            self._step_sharded(shard, flat, gflat, shadow, grad_scale, ema_decay, inv_scale, found_inf)
+            return loss
         for g, ranges in zip(self.param_groups, self._group_ranges):
             if g.get("amsgrad") or g.get("maximize") or not g.get("decoupled_weight_decay", True):
                 raise L.VawError("FusedAdamW implements torch.optim.AdamW's default update only "
@@ -178,6 +198,33 @@ class FusedAdamW(torch.optim.Optimizer):
         m = _unwrap(self.model)
         m._shadow_version = sum(p._version for p, _ in m._slot_cache)
         return loss
+
+    def _step_sharded(self, shard, flat, gflat, shadow, grad_scale, ema_decay, inv_scale, found_inf):
+        """DataParallel(shard_optimizer=True): update this rank's slice of every reduce-scattered range and the
+        replicated ranges in ONE launch per param group, then complete the bf16 shadows from their owners."""
+        if self._shard_ranges is None or self._shard_ranges[0] is not shard:
+            owned, repl = shard.owned_ranges()
+            mine = sorted(owned + repl)
+            per_group = []
+            for ranges in self._group_ranges:
+                sel = _intersect([(a, b) for a, b in ranges], mine)
+                t = torch.tensor([[a, b - a] for a, b in sel], dtype=torch.int64, device=flat.device).reshape(-1, 2)
+                per_group.append((t, len(sel), max([b - a for a, b in sel], default=0)))
+            self._shard_ranges = (shard, per_group)
+        for g, (t, n, mx) in zip(self.param_groups, self._shard_ranges[1]):
+            if g.get("amsgrad") or g.get("maximize") or not g.get("decoupled_weight_decay", True):
+                raise L.VawError("FusedAdamW implements torch.optim.AdamW's default update only")
+            if n == 0:
+                continue
+            b1, b2 = g["betas"]
+            L.call("vaw_adamw_step_ranges", flat.data_ptr(), gflat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                   shadow.data_ptr(), self.ema.data_ptr() if self.ema is not None else None, t.data_ptr(), n, mx,
+                   float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]), self.step_count,
+                   float(grad_scale), ema_decay, None, L.ptr(inv_scale), L.ptr(found_inf), L.stream_ptr())
+        self._step_t.fill_(float(self.step_count))
+        self.model._after_sharded_step(shadow)
+        m = _unwrap(self.model)
+        m._shadow_version = sum(p._version for p, _ in m._slot_cache)
 
     # -------------------------------------------------------------------------------------------------
     def state_dict(self):
@@ -228,10 +275,19 @@ class DataParallel(torch.nn.Module):
     with backward through the engine's per-block events (DiT and U-ViT); a module without per-block ranges gets one
     whole-buffer bucket after backward."""
 
-    def __init__(self, module, process_group=None, device_ids=None, output_device=None, **_ddp_kwargs):
+    def __init__(self, module, process_group=None, device_ids=None, output_device=None, shard_optimizer=False,
+                 **_ddp_kwargs):
+        """shard_optimizer=True (NCCL, models with `block_shard_ranges`, FusedAdamW): reduce-scatter the large tensors'
+        gradients, update 1/W of them per rank, all-gather the bf16 shadows (parallel.ShardedGradSync).  The fp32
+        `.data` of a large parameter is then complete on its owning ranks only until `gather_master()` - which
+        `state_dict()` and every eval forward call for you; gradients of the large tensors are per-rank slices, so code
+        that reads `.grad` itself (clip_grad_norm_, another optimizer) needs the default mode."""
         super().__init__()
         self.module = module
         self._sync = None
+        self._shard = bool(shard_optimizer)
+        self._shard_sync = None
+        self._master_stale = False
         self._group = process_group
         self._events = None
         first = next(module.parameters())
@@ -246,6 +302,20 @@ class DataParallel(torch.nn.Module):
         with torch.no_grad():
             dist.broadcast(m._flat.data, 0, group=self._group)
         m._shadow_version = -1
+        if self._shard and hasattr(m, "block_shard_ranges"):
+            big, small, tail, total = m.block_shard_ranges()
+            buckets = [[("rs", b, e) for b, e in big[i]] + [("ar", b, e) for b, e in small[i]]
+                       for i in reversed(range(len(big)))] + [[("ar", b, e) for b, e in tail]]
+            n_blocks = len(big)
+            ev = [torch.cuda.Event() for _ in range(n_blocks + 1)]
+            for e in ev:
+                e.record()
+            m._events = ev
+            self._events = list(reversed(ev[:n_blocks])) + [ev[n_blocks]]
+            self._sync = self._shard_sync = ShardedGradSync(m._gflat, buckets, self._group)
+            m._post_backward = self._after_backward
+            m._before_cast = self.gather_master
+            return
         if hasattr(m, "block_grad_ranges"):
             per_block, tail, total = m.block_grad_ranges()
             # gradients become final block L-1 first ... block 0, then the embedders / final layer / projectors
@@ -275,6 +345,23 @@ class DataParallel(torch.nn.Module):
         if self._sync is None:
             return nullcontext()
         return self._sync.no_sync()
+
+    # ---- sharded-optimizer mode ----------------------------------------------------------------------------
+    def _after_sharded_step(self, shadow):
+        """Called by FusedAdamW after it updated this rank's slices: complete the bf16 shadows (what the next forward's
+        GEMMs read) from their owners; the fp32 master copies are completed lazily."""
+        self._shard_sync.all_gather(shadow, order="forward")
+        self._master_stale = True
+
+    def gather_master(self):
+        """Complete the fp32 master parameters of the sharded tensors on every rank (collective: call on all ranks)."""
+        if self._shard_sync is not None and self._master_stale:
+            self._shard_sync.all_gather(self.module._flat.data)
+            self._master_stale = False
+
+    def state_dict(self, *a, **k):
+        self.gather_master()
+        return super().state_dict(*a, **k)
 
     def wait_grads(self):
         if self._sync is not None:

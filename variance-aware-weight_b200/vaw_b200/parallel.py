@@ -129,6 +129,75 @@ class FlatGradSync:
             torch.cuda.current_stream().wait_stream(self.stream)
 
 
+class ShardedGradSync(FlatGradSync):
+    """Data parallelism with the optimizer state sharded over ranks (ZeRO-1 style) on the flat buffers.
+
+    The LARGE tensors of a bucket (a block's weight matrices) are reduce-scattered: rank r receives the average of its
+    1/W slice only, updates that slice (fp32 master, moments, bf16 shadow) and the bf16 shadows are all-gathered before
+    the next forward.  The SMALL tensors (biases - the forward reads them from the fp32 master buffer) and the tail
+    (embedders, final layer, projectors) stay replicated: all-reduced and updated on every rank.  Against all-reduce +
+    replicated AdamW this moves 0.75x the bytes over NVLink (2.7 GB reduce-scatter + 1.35 GB bf16 all-gather instead of a
+    2 x 2.7 GB all-reduce), takes the second half of it out of the backward pass, and divides the AdamW pass by W.
+    The fp32 master copy of a large tensor is complete only on its owners until `gather_master()`.
+
+    buckets: in completion order, each a list of (kind, begin, end) with kind 'rs' or 'ar'."""
+
+    def __init__(self, gflat, buckets, process_group=None):
+        if not (dist_ready() and dist.get_backend(process_group) == "nccl" and gflat.is_cuda):
+            raise RuntimeError("the sharded optimizer mode needs CUDA tensors and the NCCL backend")
+        self.kinds = [[(k, int(b), int(e)) for k, b, e in bk if e > b] for bk in buckets]
+        super().__init__(gflat, [[(b, e) for _, b, e in bk] for bk in self.kinds], process_group)
+        self.rank = dist.get_rank(process_group)
+        W = self.world
+        for bk in self.kinds:
+            for k, b, e in bk:
+                if k == "rs" and ((e - b) % (4 * W) or b % 4):
+                    raise RuntimeError(f"reduce-scatter range [{b}, {e}) does not split into {W} float4-aligned slices")
+        self.gather_stream = torch.cuda.Stream()
+
+    def _slice(self, b, e):
+        n = (e - b) // self.world
+        return b + self.rank * n, b + (self.rank + 1) * n
+
+    def owned_ranges(self):
+        """Element ranges this rank updates: its slice of every reduce-scattered range, and every all-reduced range."""
+        owned, replicated = [], []
+        for bk in self.kinds:
+            for k, b, e in bk:
+                (owned if k == "rs" else replicated).append(self._slice(b, e) if k == "rs" else (b, e))
+        return owned, replicated
+
+    def launch(self, events=None):
+        if not self.enabled or self.world == 1:
+            return
+        with torch.cuda.stream(self.stream):
+            for i, bk in enumerate(self.kinds):
+                if events is not None and events[i] is not None:
+                    self.stream.wait_event(events[i])
+                else:
+                    self.stream.wait_stream(torch.cuda.default_stream())
+                for k, b, e in bk:
+                    if k == "ar":
+                        dist.all_reduce(self.gflat[b:e], op=dist.ReduceOp.AVG, group=self.group)
+                    else:
+                        lo, hi = self._slice(b, e)
+                        dist.reduce_scatter_tensor(self.gflat[lo:hi], self.gflat[b:e], op=dist.ReduceOp.AVG, group=self.group)
+
+    def all_gather(self, buf, order=None, wait=True):
+        """Complete `buf` (the bf16 shadow, or the fp32 master) from the owners' slices, in place, on a side stream that
+        starts after everything enqueued so far (the optimizer step)."""
+        cur = torch.cuda.current_stream()
+        self.gather_stream.wait_stream(cur)
+        with torch.cuda.stream(self.gather_stream):
+            for bk in (reversed(self.kinds) if order == "forward" else self.kinds):
+                for k, b, e in bk:
+                    if k == "rs":
+                        lo, hi = self._slice(b, e)
+                        dist.all_gather_into_tensor(buf[b:e], buf[lo:hi], group=self.group)
+        if wait:
+            cur.wait_stream(self.gather_stream)
+
+
 def shard_seed(base_seed: int, rank: int) -> int:
     """Per-rank RNG seed rule of the reference (tools/utils.py:62-69): seed + rank."""
     return int(base_seed) + int(rank)
