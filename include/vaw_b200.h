@@ -391,6 +391,11 @@ int vaw_dit_workspace_bytes(const vaw_dit_cfg* cfg, long long* bytes);
  * _scale_timesteps, tools/gaussian_diffusion.py:417-420), y int64 [B]; out bf16 [B,C_out,H,W]; zs bf16 [B*T,z_dim]. */
 int vaw_dit_forward(const vaw_dit_cfg* cfg, const float* P, const void* Pb, void* ws, const float* x_t, const float* t,
                     const long long* y, void* out, void* zs, vaw_stream_t stream);
+/* vaw_dit_forward gated by events: wait_events = depth + 1 cudaEvent_t (NULL entries allowed); [0] is waited on before
+ * the stacked adaLN weights are read, [1 + i] before block i's weights.  The sharded data-parallel optimizer records them
+ * as the all-gather of each block's bf16 weights completes, so the gathers of later blocks overlap earlier blocks. */
+int vaw_dit_forward_ev(const vaw_dit_cfg* cfg, const float* P, const void* Pb, void* ws, const float* x_t, const float* t,
+                       const long long* y, void* out, void* zs, void** wait_events, vaw_stream_t stream);
 /* Forward-only entry for sampling / evaluation (the reference runs its samplers under torch.no_grad(), tools/sampler.py,
  * tools/cfg_edm.py:109): identical results, but nothing is kept for a backward pass - one set of operand buffers shared
  * by all blocks, a three-buffer residual ring, no saved pre-activations / branch outputs (a third of the forward's HBM

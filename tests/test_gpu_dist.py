@@ -104,6 +104,7 @@ def _shard_worker(rank, world, port, q):
                 terms["loss"].mean().backward()
                 opt.step(); opt.zero_grad()
                 losses.append(terms["loss"].detach().clone())
+            torch.cuda.synchronize(dev)   # the sharded mode's bf16 all-gather runs on its own stream until the next forward
             shadow = m._shadow.clone()
             sd = {k: v.detach().clone() for k, v in net.state_dict().items()}     # gathers the fp32 master when sharded
             results[shard] = (losses, shadow, sd, m._flat.detach().clone())

@@ -269,7 +269,7 @@ extern "C" int vaw_dit_workspace_bytes(const vaw_dit_cfg* cfg, long long* bytes)
 // table_rows == 0) -> out [B,C_out,H,W] bf16 and, with learn_align, zs [B*T, z_dim] bf16.
 static int dit_forward_impl(const vaw_dit_cfg* cfg, const float* P, const void* Pb_, void* ws_, const float* x_t,
                             const float* t, const long long* y, void* out, void* zs, const void* feat, float* align_loss,
-                            cudaStream_t s, bool infer = false) {
+                            cudaStream_t s, bool infer = false, void** wait_events = nullptr) {
   TRY(check_cfg(cfg));
   VAW_CHECK_ARG(P && Pb_ && ws_ && x_t && t && out, "vaw_dit_forward: null pointer");
   const vaw_dit_cfg& c = *cfg;
@@ -285,6 +285,12 @@ static int dit_forward_impl(const vaw_dit_cfg* cfg, const float* P, const void* 
   const int Kp = c.C_in * c.P * c.P, PPC = c.P * c.P * c.C_out;
   const long long ldm = (long long)c.depth * 6 * D;
 
+  // wait_events (sharded data-parallel optimizer): [0] = the stacked adaLN weights' bf16 shadow is complete, [1 + i] =
+  // block i's.  The all-gathers of the later blocks run under the earlier blocks' compute.
+  auto wait_for = [&](int k) -> int {
+    if (wait_events && wait_events[k]) VAW_CUDA_TRY(cudaStreamWaitEvent(s, reinterpret_cast<cudaEvent_t>(wait_events[k]), 0));
+    return VAW_OK;
+  };
   // patch embedding + pos_embed -> x[0]
   TRY(vaw_patchify_in(x_t, w.patches, B, c.C_in, c.img_h, c.img_w, c.P, s));
   TRY(G(w.patches, Kp, 0, Pb + L.off[P_XEMB_W], Kp, 0, M, D, Kp, VAW_EPI_RES)
@@ -296,6 +302,7 @@ static int dit_forward_impl(const vaw_dit_cfg* cfg, const float* P, const void* 
   TRY(G(w.t_h, D, 0, Pb + L.off[P_T2_W], D, 0, B, D, D, VAW_EPI_F32).out(w.t_emb).bias(P + L.off[P_T2_B]).run(s));
   TRY(vaw_cond_combine(w.t_emb, c.table_rows ? P + L.off[P_YTAB] : nullptr, y, w.c, w.c_silu, B, D, s));
   // adaLN modulation of every block (one GEMM) and of the final layer
+  TRY(wait_for(0));
   TRY(G(w.c_silu, D, 0, Pb + L.off[P_ADA_W], D, 0, B, c.depth * 6 * D, D, VAW_EPI_F32)
           .out(w.mod_all).bias(P + L.off[P_ADA_B]).run(s));
   TRY(G(w.c_silu, D, 0, Pb + L.off[P_FADA_W], D, 0, B, 2 * D, D, VAW_EPI_F32)
@@ -308,6 +315,7 @@ static int dit_forward_impl(const vaw_dit_cfg* cfg, const float* P, const void* 
     float* x_in = w.x[2 * i];
     float* x_mid = w.x[2 * i + 1];
     float* x_out = w.x[2 * i + 2];
+    TRY(wait_for(1 + i));
     TRY(vaw_ln_fwd(x_in, mod, mod + D, ldm, T, nullptr, nullptr, b.xn1, b.mean1, b.rstd1, M, D, kLnEps, s));
     TRY(G(b.xn1, D, 0, Pb + L.off[pb + B_QKV_W], D, 0, M, 3 * D, D, VAW_EPI_BF16)
             .out(b.qkv).bias(P + L.off[pb + B_QKV_B]).run(s));
@@ -349,6 +357,14 @@ static int dit_forward_impl(const vaw_dit_cfg* cfg, const float* P, const void* 
 extern "C" int vaw_dit_forward(const vaw_dit_cfg* cfg, const float* P, const void* Pb_, void* ws_, const float* x_t,
                                const float* t, const long long* y, void* out, void* zs, cudaStream_t s) {
   return dit_forward_impl(cfg, P, Pb_, ws_, x_t, t, y, out, zs, nullptr, nullptr, s);
+}
+
+// vaw_dit_forward with per-block wait events: depth + 1 cudaEvent_t (or NULL entries) that gate the first read of the
+// stacked adaLN weights ([0]) and of each block's weights ([1 + i]) - see parallel.ShardedGradSync.
+extern "C" int vaw_dit_forward_ev(const vaw_dit_cfg* cfg, const float* P, const void* Pb_, void* ws_, const float* x_t,
+                                  const float* t, const long long* y, void* out, void* zs, void** wait_events,
+                                  cudaStream_t s) {
+  return dit_forward_impl(cfg, P, Pb_, ws_, x_t, t, y, out, zs, nullptr, nullptr, s, false, wait_events);
 }
 
 // Forward-only entry (sampling / evaluation, torch.no_grad()): same arithmetic and results as vaw_dit_forward, but on

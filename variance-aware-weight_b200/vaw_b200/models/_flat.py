@@ -55,7 +55,7 @@ class FlatEngineModule(nn.Module):
         memo[id(self)] = new
         drop = {"_flat": None, "_shadow": None, "_gflat": None, "_ws": None, "_events": None, "_post_backward": None,
                 "_slot_cache": None, "_ws_batch": -1, "_shadow_version": -1, "_ws_inf": None, "_ws_inf_batch": -1,
-                "_before_cast": None}
+                "_before_cast": None, "_fwd_wait": None}
         for k, v in self.__dict__.items():
             new.__dict__[k] = drop[k] if k in drop else copy.deepcopy(v, memo)
         return new

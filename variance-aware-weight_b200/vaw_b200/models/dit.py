@@ -28,6 +28,7 @@ L.register("vaw_dit_param_layout", [C.POINTER(DiTCfg), C.c_void_p, C.c_void_p, C
 L.register("vaw_dit_workspace_bytes", [C.POINTER(DiTCfg), C.c_void_p])
 L.register("vaw_dit_forward", [C.POINTER(DiTCfg)] + [C.c_void_p] * 9)
 L.register("vaw_dit_forward_align", [C.POINTER(DiTCfg)] + [C.c_void_p] * 11)
+L.register("vaw_dit_forward_ev", [C.POINTER(DiTCfg)] + [C.c_void_p] * 10)
 L.register("vaw_dit_infer_workspace_bytes", [C.POINTER(DiTCfg), C.c_void_p])
 L.register("vaw_dit_forward_infer", [C.POINTER(DiTCfg)] + [C.c_void_p] * 9)
 L.register("vaw_dit_backward", [C.POINTER(DiTCfg)] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_void_p])
@@ -191,6 +192,11 @@ class DiT(FlatEngineModule):
         tail = [(0, off[18])]
         return per_block, tail, total
 
+    def stacked_range(self):
+        """Element range of the stacked adaLN weights of all blocks (read by one GEMM at the top of the forward)."""
+        off, num, _ = self._layout()
+        return off[18], off[18] + num[18]
+
     def block_shard_ranges(self):
         """For the sharded-optimizer data-parallel mode: per block, the contiguous ranges of LARGE tensors (the four
         weight matrices; the block's slice of the stacked adaLN weight) whose gradients are reduce-scattered, and the
@@ -261,6 +267,10 @@ class DiT(FlatEngineModule):
         else:
             y = None
         self._ensure_flat(x.device)
+        pending = self._fwd_wait     # sharded optimizer: events of the in-flight all-gather of the bf16 weights
+        if pending is not None and (not torch.is_grad_enabled() or align_target is not None):
+            torch.cuda.current_stream().wait_event(pending[-1])   # paths without per-block gating wait for all of it
+            self._fwd_wait = pending = None
         if not torch.is_grad_enabled():
             return self._forward_infer(x.float().contiguous(), t.float().contiguous(), y)
         self._ensure_workspace(x.shape[0], x.device)
@@ -298,6 +308,7 @@ def _dit_forward_infer(self, x, t, y):
 
 
 DiT._forward_infer = _dit_forward_infer
+DiT._fwd_wait = None
 DiT._ws_inf = None
 DiT._ws_inf_batch = -1
 
@@ -319,6 +330,12 @@ class _DiTFunction(torch.autograd.Function):
                    model._ws.data_ptr(), x.data_ptr(), t.data_ptr(), L.ptr(y), out.data_ptr(), L.ptr(zs),
                    feat.data_ptr(), align.data_ptr(), L.stream_ptr())
             ctx.mark_non_differentiable(align)
+        elif model._fwd_wait is not None:
+            evs = model._fwd_wait
+            model._fwd_wait = None
+            arr = (C.c_void_p * len(evs))(*[e.cuda_event for e in evs])
+            L.call("vaw_dit_forward_ev", C.byref(cfg), flat.data_ptr(), model._shadow.data_ptr(), model._ws.data_ptr(),
+                   x.data_ptr(), t.data_ptr(), L.ptr(y), out.data_ptr(), L.ptr(zs), arr, L.stream_ptr())
         else:
             L.call("vaw_dit_forward", C.byref(cfg), flat.data_ptr(), model._shadow.data_ptr(), model._ws.data_ptr(),
                    x.data_ptr(), t.data_ptr(), L.ptr(y), out.data_ptr(), L.ptr(zs), L.stream_ptr())

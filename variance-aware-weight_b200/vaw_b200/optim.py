@@ -350,13 +350,20 @@ class DataParallel(torch.nn.Module):
     def _after_sharded_step(self, shadow):
         """Called by FusedAdamW after it updated this rank's slices: complete the bf16 shadows (what the next forward's
         GEMMs read) from their owners; the fp32 master copies are completed lazily."""
-        self._shard_sync.all_gather(shadow, order="forward")
+        m = self.module
+        lo, hi = m.stacked_range() if hasattr(m, "stacked_range") else (0, 0)
+        # the stacked adaLN weights are read by ONE GEMM at the top of the forward: gather them first; then block 0, 1, ...
+        # each with its own event, which the engine's forward waits on right before the block (vaw_dit_forward_ev)
+        events = self._shard_sync.all_gather(shadow, wait=False, first=lambda b, e: lo <= b and e <= hi)
+        m._fwd_wait = events if len(events) == m.depth + 1 else None
+        if m._fwd_wait is None:
+            torch.cuda.current_stream().wait_stream(self._shard_sync.gather_stream)
         self._master_stale = True
 
     def gather_master(self):
         """Complete the fp32 master parameters of the sharded tensors on every rank (collective: call on all ranks)."""
         if self._shard_sync is not None and self._master_stale:
-            self._shard_sync.all_gather(self.module._flat.data)
+            self._shard_sync.all_gather(self.module._flat.data, wait=True)
             self._master_stale = False
 
     def state_dict(self, *a, **k):

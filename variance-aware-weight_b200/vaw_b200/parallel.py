@@ -183,19 +183,45 @@ class ShardedGradSync(FlatGradSync):
                         lo, hi = self._slice(b, e)
                         dist.reduce_scatter_tensor(self.gflat[lo:hi], self.gflat[b:e], op=dist.ReduceOp.AVG, group=self.group)
 
-    def all_gather(self, buf, order=None, wait=True):
+    def all_gather(self, buf, wait=True, first=None):
         """Complete `buf` (the bf16 shadow, or the fp32 master) from the owners' slices, in place, on a side stream that
-        starts after everything enqueued so far (the optimizer step)."""
+        starts after everything enqueued so far (the optimizer step).  Buckets are gathered in FORWARD order (the reverse
+        of their completion order in backward); ranges for which `first(b, e)` is true go before everything else.
+        wait=False returns one CUDA event per step of that schedule instead of blocking the current stream:
+        [after the `first` ranges, after bucket L-1 (= block 0), ..., after bucket 0's predecessor ...]."""
         cur = torch.cuda.current_stream()
         self.gather_stream.wait_stream(cur)
+        events = []
+
+        def gather(b, e):
+            lo, hi = self._slice(b, e)
+            dist.all_gather_into_tensor(buf[b:e], buf[lo:hi], group=self.group)
+
         with torch.cuda.stream(self.gather_stream):
-            for bk in (reversed(self.kinds) if order == "forward" else self.kinds):
+            order = list(reversed(self.kinds))
+            if first is not None:
+                for bk in order:
+                    for k, b, e in bk:
+                        if k == "rs" and first(b, e):
+                            gather(b, e)
+                if not wait:
+                    ev = torch.cuda.Event()
+                    ev.record(self.gather_stream)
+                    events.append(ev)
+            for bk in order:
+                did = False
                 for k, b, e in bk:
-                    if k == "rs":
-                        lo, hi = self._slice(b, e)
-                        dist.all_gather_into_tensor(buf[b:e], buf[lo:hi], group=self.group)
+                    if k == "rs" and not (first is not None and first(b, e)):
+                        gather(b, e)
+                        did = True
+                if did and not wait:
+                    ev = torch.cuda.Event()
+                    ev.record(self.gather_stream)
+                    events.append(ev)
         if wait:
             cur.wait_stream(self.gather_stream)
+            return None
+        return events
 
 
 def shard_seed(base_seed: int, rank: int) -> int:
