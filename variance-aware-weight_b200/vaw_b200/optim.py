@@ -254,6 +254,10 @@ class FusedAdamW(torch.optim.Optimizer):
         of the flat EMA buffer; load them into a model copy with load_state_dict(..., strict=False)."""
         if self.ema is None:
             raise L.VawError("FusedAdamW was built without ema_decay")
+        shard = getattr(self.model, "_shard_sync", None)
+        if shard is not None:
+            # sharded mode keeps the EMA of a reduce-scattered range on its owner only: complete it (a collective)
+            shard.all_gather(self.ema, wait=True)
         m = _unwrap(self.model)
         by_id = {id(p): o for p, o in m._slot_cache}
         return {k: self.ema[by_id[id(p)]:by_id[id(p)] + p.numel()].view(p.shape)
