@@ -27,7 +27,8 @@ def main():
     dev = torch.device("cuda", 0)
     B = int(os.environ.get("B", 128))
     torch.manual_seed(0)
-    m = DiT_models["DiT-XL/2"](image_size=32, patch_size=2, in_channels=4, num_classes=1000).to(dev)
+    m = DiT_models["DiT-XL"](image_size=32, patch_size=2, in_channels=4, class_dropout_prob=0.1, num_classes=1000,
+                          learn_sigma=False).to(dev)
     x = torch.randn(B, 4, 32, 32, device=dev)
     t = torch.rand(B, device=dev) * 1000
     y = torch.randint(0, 1000, (B,), device=dev)

@@ -50,6 +50,60 @@ def test_forward_backward(B, T, H, hd):
             assert (got - g).norm().item() <= 1.2e-2 * g.norm().item() + 1e-4 * scale * g.numel() ** 0.5
 
 
+@pytest.mark.parametrize("T,hd,peak_key", [(256, 72, 200), (256, 64, 77), (130, 72, 129), (258, 64, 150)])
+def test_forward_rows_whose_maximum_is_far_above_the_estimate(T, hd, peak_key):
+    """The single-pass softmax takes its reference point from the first 32 keys of each half; a row whose true maximum is
+    more than 2^80 above that estimate makes the CTA fall back to the exact two-pass path.  Half the heads get such rows
+    (a key far outside the first chunks with a huge logit), the others stay on the fast path: both must match SDPA."""
+    torch.manual_seed(5)
+    B, H = 2, 4
+    qkv = (torch.randn(B, T, 3, H, hd, device=DEV) * 0.5).bfloat16()
+    # head 1 and 3: key `peak_key` is aligned with every query of rows 3.. and 40x longer -> logit ~ +150 nats there
+    for h in (1, 3):
+        qkv[:, 3:, 1, h] *= 0.05                                   # all other keys: tiny logits
+        qkv[:, 3:, 0, h] = (torch.ones(hd, device=DEV) * 4.0).bfloat16()
+        qkv[:, peak_key, 1, h] = (torch.ones(hd, device=DEV) * 5.0).bfloat16()
+    o = torch.full((B, T, H, hd), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, T, device=DEV)
+    L.call("vaw_attn_fwd", qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, H, hd, L.stream_ptr())
+    q, k, v = [qkv[:, :, i].float().permute(0, 2, 1, 3) for i in range(3)]
+    s = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
+    gap = (s.max(-1).values - s[..., :32].max(-1).values) * 1.4426950408889634
+    assert gap[:, 1].max().item() > 100 and gap[:, 0].max().item() < 40      # the construction does what it says
+    ref = F.scaled_dot_product_attention(q, k, v)
+    assert not torch.isnan(o.float()).any()
+    assert relerr(o.permute(0, 2, 1, 3), ref) < 6e-3
+    assert relerr(lse, torch.logsumexp(s, -1) * 1.4426950408889634) < 1e-3
+
+
+def test_exact_softmax_switch_gives_the_same_result_in_a_subprocess():
+    """VAW_ATTN_EXACT=1 forces the two-pass softmax for every CTA (read once per process): same outputs to bf16
+    rounding (the reference point of the exponentials differs, nothing else)."""
+    import os, subprocess, sys
+    code = (
+        "import sys, ctypes as C, torch; sys.path[:0] = %r\n"
+        "from vaw_b200 import _lib as L\n"
+        "L.register('vaw_attn_fwd', [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p])\n"
+        "B, T, H, hd = 3, 256, 4, 72\n"
+        "torch.manual_seed(1)\n"
+        "qkv = (torch.randn(B, T, 3, H, hd, device='cuda') * 0.7).bfloat16()\n"
+        "o = torch.empty(B, T, H, hd, device='cuda', dtype=torch.bfloat16); lse = torch.empty(B, H, T, device='cuda')\n"
+        "L.call('vaw_attn_fwd', qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, H, hd, L.stream_ptr())\n"
+        "torch.save((o.cpu(), lse.cpu()), sys.argv[1])\n"
+        "print('ok')\n" % ([os.path.dirname(os.path.abspath(L.__file__)) + "/..", os.path.dirname(os.path.abspath(__file__))],))
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for exact in ("0", "1"):
+            path = os.path.join(d, f"o{exact}.pt")
+            r = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, VAW_ATTN_EXACT=exact),
+                               capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+            outs.append(torch.load(path))
+    (o0, l0), (o1, l1) = outs
+    assert relerr(o0, o1) < 4e-3 and relerr(l0, l1) < 1e-5
+
+
 @pytest.mark.parametrize("legacy", ["0", "1"])
 def test_both_attention_paths_in_a_subprocess(legacy):
     """The mma.sync kernels stay in the library for T > 256 (U-ViT); VAW_ATTN_LEGACY=1 forces them for every shape so

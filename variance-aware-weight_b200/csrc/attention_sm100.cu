@@ -7,9 +7,10 @@
 //      and the whole K and V of the head into shared memory.  head_dim 72 is split 64 + 16: a SWIZZLE_128B box for the
 //      first 64 columns and a SWIZZLE_32B box for columns 64..79, of which 72..79 are zero-filled by the TMA unit.
 //   2. S = Q K^T  [128 x Nk] fp32 in TMEM columns [0, Nk): 4 (+1) tcgen05.mma (K = 16 each), both operands K-major.
-//   3. softmax: two threads per query row (TMEM lane = row), one per 128-key half; two passes over the half row with
-//      tcgen05.ld (max, then exp2 / sum, exchanged through shared memory); P is written back as packed bf16 pairs with
-//      tcgen05.st in place of the S columns the same thread has already consumed.
+//   3. softmax: two threads per query row (TMEM lane = row), one per 128-key half; ONE pass over the half row with
+//      tcgen05.ld (exp2 / sum relative to an estimated row maximum, see the kernel; a CTA that meets a row outside the
+//      safe range recomputes S and runs the exact max-then-exp two-pass version); P is written back as packed bf16
+//      pairs with tcgen05.st in place of the S columns the same thread has already consumed.
 //   4. O = P V  [128 x hd]: A operand read from TMEM (P), B = V from shared memory (MN-major), accumulator in the
 //      TMEM columns the softmax freed.
 //   5. epilogue: O / rowsum -> bf16 -> out[b, t, h, :]; L2[q] = max*c + log2(rowsum) (log2-domain, see attention.cu).
@@ -89,7 +90,7 @@ struct Smem {
 template <int HD>
 __global__ void __launch_bounds__(256, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_tail,
-                   bf16* __restrict__ o, float* __restrict__ lse2, int T, int Ta, int H, float scale_log2e) {
+                   bf16* __restrict__ o, float* __restrict__ lse2, int T, int Ta, int H, float scale_log2e, int exact) {
   using S = Smem<HD>;
   constexpr bool kTail = S::kTail;
   // TMEM columns after the softmax (S occupied [0, 256)): each key half rewrites its own S columns in place with P
@@ -136,71 +137,90 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  bool first_mma = true;
 
-  // ---- S = Q K^T ----
-  if (threadIdx.x == 0) {
-    mbar_wait(bar_qk, 0);
-    tc_fence_after();
-    const uint32_t id = idesc_bf16(nk, 0);
-    const uint32_t aq = smem_u32(smem + S::kQm), ak = smem_u32(smem + S::kKm);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) tc_mma_ss(tmem, desc_sw128(aq + k * 32), desc_sw128(ak + k * 32), id, k ? 1u : 0u);
-    if (kTail) tc_mma_ss(tmem, desc_sw32(smem_u32(smem + S::kQt)), desc_sw32(smem_u32(smem + S::kKt)), id, 1u);
-    tc_commit(bar_s);
-  }
-  __syncwarp();
-
-  // ---- softmax: two threads per query row (TMEM lane = threadIdx.x & 127), each owning one half of the keys ----
+  // ---- softmax roles: two threads per query row (TMEM lane = threadIdx.x & 127), each owning one half of the keys ----
   const int lane_row = threadIdx.x & 127;        // query row inside the tile == TMEM lane
   const int half = threadIdx.x >> 7;             // 0: key chunks 0..3, 1: key chunks 4..7
   const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const int nchunks = (nk + 31) >> 5;
   const int c_lo = half * 4, c_hi = min(nchunks, half * 4 + 4);
-  mbar_wait(bar_s, 0);
-  __syncwarp();
-  tc_fence_after();
-  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-  {
-    uint32_t va[32], vb[32];
-    if (c_lo < c_hi) tmem_ld32(trow + c_lo * 32, va);
-    for (int c = c_lo; c < c_hi; c += 2) {     // chunk c in va, chunk c + 1 in vb; the next load overlaps the math
-      tmem_ld_wait();
-      if (c + 1 < c_hi) tmem_ld32(trow + (c + 1) * 32, vb);
-      row_max_chunk(va, c * 32, T, mx0, mx1, mx2, mx3);
-      if (c + 1 < c_hi) {
-        tmem_ld_wait();
-        if (c + 2 < c_hi) tmem_ld32(trow + (c + 2) * 32, va);
-        row_max_chunk(vb, (c + 1) * 32, T, mx0, mx1, mx2, mx3);
-      }
+  float mx = 0.f, sum = 0.f;
+
+  // Reading S out of TMEM is the softmax's bottleneck (tcgen05.ld bandwidth), so the row is normally read ONCE: the
+  // reference point of the exponentials is the maximum over the first 32-key chunk of each half instead of the row
+  // maximum.  softmax is invariant to the reference point, and bf16 / fp32 have the exponent range for
+  // 2^(s - ref) up to 2^kSafe; rows whose true maximum lies further above the estimate (never seen with real
+  // activations, but inputs are arbitrary) make the CTA recompute S and take the exact two-pass path (attempt 1).
+  constexpr float kSafe = 80.f;
+  for (int attempt = exact ? 1 : 0;; ++attempt) {
+    // ---- S = Q K^T ----
+    if (threadIdx.x == 0) {
+      if (first_mma) mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      const uint32_t id = idesc_bf16(nk, 0);
+      const uint32_t aq = smem_u32(smem + S::kQm), ak = smem_u32(smem + S::kKm);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tc_mma_ss(tmem, desc_sw128(aq + k * 32), desc_sw128(ak + k * 32), id, k ? 1u : 0u);
+      if (kTail) tc_mma_ss(tmem, desc_sw32(smem_u32(smem + S::kQt)), desc_sw32(smem_u32(smem + S::kKt)), id, 1u);
+      tc_commit(bar_s);
     }
-  }
-  float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-  s_max[half * kTile + lane_row] = mx;
-  __syncthreads();
-  mx = fmaxf(s_max[lane_row], s_max[kTile + lane_row]);
-  const float mneg = -mx * scale_log2e;
-  float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-  {
+    __syncwarp();
+    mbar_wait(bar_s, first_mma ? 0 : 1);
+    first_mma = false;
+    __syncwarp();
+    tc_fence_after();
+
     uint32_t va[32], vb[32], pk[16];
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
     if (c_lo < c_hi) tmem_ld32(trow + c_lo * 32, va);
+    if (attempt == 0) {          // estimate: this half's first chunk, which stays in registers for the exp pass
+      tmem_ld_wait();
+      if (c_lo < c_hi) row_max_chunk(va, c_lo * 32, T, mx0, mx1, mx2, mx3);
+    } else {                     // exact: a full pass for the maximum, then the first chunk again
+      for (int c = c_lo; c < c_hi; c += 2) {     // chunk c in va, chunk c + 1 in vb; the next load overlaps the math
+        tmem_ld_wait();
+        if (c + 1 < c_hi) tmem_ld32(trow + (c + 1) * 32, vb);
+        row_max_chunk(va, c * 32, T, mx0, mx1, mx2, mx3);
+        if (c + 1 < c_hi) {
+          tmem_ld_wait();
+          if (c + 2 < c_hi) tmem_ld32(trow + (c + 2) * 32, va);
+          row_max_chunk(vb, (c + 1) * 32, T, mx0, mx1, mx2, mx3);
+        }
+      }
+      if (c_lo < c_hi) tmem_ld32(trow + c_lo * 32, va);
+    }
+    mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+    s_max[half * kTile + lane_row] = mx;
+    __syncthreads();
+    mx = fmaxf(s_max[lane_row], s_max[kTile + lane_row]);
+    const float mneg = -mx * scale_log2e;
+    float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+    mx0 = mx1 = mx2 = mx3 = -INFINITY;           // attempt 0: the true maximum of this thread's keys, for the range check
     for (int c = c_lo; c < c_hi; c += 2) {
       tmem_ld_wait();
       if (c + 1 < c_hi) tmem_ld32(trow + (c + 1) * 32, vb);
+      if (attempt == 0) row_max_chunk(va, c * 32, T, mx0, mx1, mx2, mx3);
       softmax_chunk(va, pk, c * 32, T, scale_log2e, mneg, sum0, sum1, sum2, sum3);
       tmem_st16(trow + half * kPHiCol + (c - c_lo) * 16, pk);
       if (c + 1 < c_hi) {
         tmem_ld_wait();
         if (c + 2 < c_hi) tmem_ld32(trow + (c + 2) * 32, va);
+        if (attempt == 0) row_max_chunk(vb, (c + 1) * 32, T, mx0, mx1, mx2, mx3);
         softmax_chunk(vb, pk, (c + 1) * 32, T, scale_log2e, mneg, sum0, sum1, sum2, sum3);
         tmem_st16(trow + half * kPHiCol + (c + 1 - c_lo) * 16, pk);
       }
     }
+    s_sum[half * kTile + lane_row] = (sum0 + sum1) + (sum2 + sum3);
+    // !(x <= kSafe) also catches NaN scores: they take the exact path like everything unusual
+    const float top = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+    const bool bad = attempt == 0 && c_lo < c_hi && !(fmaf(top, scale_log2e, mneg) <= kSafe);
+    tmem_st_wait();
+    tc_fence_before();
+    const int redo = __syncthreads_or(bad);
+    sum = s_sum[lane_row] + s_sum[kTile + lane_row];
+    if (!redo) break;
   }
-  s_sum[half * kTile + lane_row] = (sum0 + sum1) + (sum2 + sum3);
-  tmem_st_wait();
-  tc_fence_before();
-  __syncthreads();
-  const float sum = s_sum[lane_row] + s_sum[kTile + lane_row];
 
   // ---- O = P V ----  (warp 0 walks the loop with warp-uniform descriptors; lane 0 issues)
   if (warp == 0) {
@@ -279,8 +299,10 @@ int launch_fwd_tc(const void* qkv, void* o, float* lse2, int B, int T, int Ta, i
   }
   const float scale = 1.0f / sqrtf((float)HD);
   dim3 grid((T + kTile - 1) / kTile, H, B);
+  // VAW_ATTN_EXACT=1: always the two-pass softmax (A/B timing of the single-pass path; results agree either way)
+  static const int exact = getenv("VAW_ATTN_EXACT") && atoi(getenv("VAW_ATTN_EXACT")) != 0;
   attn_fwd_tc_kernel<HD><<<grid, 256, S::kBytes, stream>>>(tm_main, tm_tail, (bf16*)o, lse2, T, Ta, H,
-                                                            scale * 1.4426950408889634f);
+                                                            scale * 1.4426950408889634f, exact);
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }

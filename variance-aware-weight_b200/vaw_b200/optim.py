@@ -202,28 +202,39 @@ class FusedAdamW(torch.optim.Optimizer):
     def _step_sharded(self, shard, flat, gflat, shadow, grad_scale, ema_decay, inv_scale, found_inf):
         """DataParallel(shard_optimizer=True): update this rank's slice of every reduce-scattered range and the
         replicated ranges in ONE launch per param group, then complete the bf16 shadows from their owners."""
+        m = _unwrap(self.model)
+        lo, hi = m.stacked_range() if hasattr(m, "stacked_range") else (0, 0)
         if self._shard_ranges is None or self._shard_ranges[0] is not shard:
             owned, repl = shard.owned_ranges()
             mine = sorted(owned + repl)
             per_group = []
             for ranges in self._group_ranges:
                 sel = _intersect([(a, b) for a, b in ranges], mine)
-                t = torch.tensor([[a, b - a] for a, b in sel], dtype=torch.int64, device=flat.device).reshape(-1, 2)
-                per_group.append((t, len(sel), max([b - a for a, b in sel], default=0)))
+                # the stacked adaLN weights are what the next forward reads first: their slices are updated by a launch
+                # of their own so that their all-gather runs under the update of everything else
+                parts = []
+                for part in ([r for r in sel if lo <= r[0] and r[1] <= hi], [r for r in sel if not (lo <= r[0] and r[1] <= hi)]):
+                    t = torch.tensor([[a, b - a] for a, b in part], dtype=torch.int64, device=flat.device).reshape(-1, 2)
+                    parts.append((t, len(part), max([b - a for a, b in part], default=0)))
+                per_group.append(parts)
             self._shard_ranges = (shard, per_group)
-        for g, (t, n, mx) in zip(self.param_groups, self._shard_ranges[1]):
-            if g.get("amsgrad") or g.get("maximize") or not g.get("decoupled_weight_decay", True):
-                raise L.VawError("FusedAdamW implements torch.optim.AdamW's default update only")
-            if n == 0:
-                continue
-            b1, b2 = g["betas"]
-            L.call("vaw_adamw_step_ranges", flat.data_ptr(), gflat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                   shadow.data_ptr(), self.ema.data_ptr() if self.ema is not None else None, t.data_ptr(), n, mx,
-                   float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]), self.step_count,
-                   float(grad_scale), ema_decay, None, L.ptr(inv_scale), L.ptr(found_inf), L.stream_ptr())
+        first_done = None
+        for phase in (0, 1):
+            for g, parts in zip(self.param_groups, self._shard_ranges[1]):
+                if g.get("amsgrad") or g.get("maximize") or not g.get("decoupled_weight_decay", True):
+                    raise L.VawError("FusedAdamW implements torch.optim.AdamW's default update only")
+                t, n, mx = parts[phase]
+                if n == 0:
+                    continue
+                b1, b2 = g["betas"]
+                L.call("vaw_adamw_step_ranges", flat.data_ptr(), gflat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                       shadow.data_ptr(), self.ema.data_ptr() if self.ema is not None else None, t.data_ptr(), n, mx,
+                       float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]), self.step_count,
+                       float(grad_scale), ema_decay, None, L.ptr(inv_scale), L.ptr(found_inf), L.stream_ptr())
+            if phase == 0 and hi > lo:
+                first_done = shard.gather_first(shadow, lambda b, e: lo <= b and e <= hi)
         self._step_t.fill_(float(self.step_count))
-        self.model._after_sharded_step(shadow)
-        m = _unwrap(self.model)
+        self.model._after_sharded_step(shadow, first_done)
         m._shadow_version = sum(p._version for p, _ in m._slot_cache)
 
     # -------------------------------------------------------------------------------------------------
@@ -351,14 +362,15 @@ class DataParallel(torch.nn.Module):
         return self._sync.no_sync()
 
     # ---- sharded-optimizer mode ----------------------------------------------------------------------------
-    def _after_sharded_step(self, shadow):
+    def _after_sharded_step(self, shadow, first_done=None):
         """Called by FusedAdamW after it updated this rank's slices: complete the bf16 shadows (what the next forward's
         GEMMs read) from their owners; the fp32 master copies are completed lazily."""
         m = self.module
         lo, hi = m.stacked_range() if hasattr(m, "stacked_range") else (0, 0)
         # the stacked adaLN weights are read by ONE GEMM at the top of the forward: gather them first; then block 0, 1, ...
         # each with its own event, which the engine's forward waits on right before the block (vaw_dit_forward_ev)
-        events = self._shard_sync.all_gather(shadow, wait=False, first=lambda b, e: lo <= b and e <= hi)
+        events = self._shard_sync.all_gather(shadow, wait=False, first=lambda b, e: lo <= b and e <= hi,
+                                             first_done=first_done)
         m._fwd_wait = events if len(events) == m.depth + 1 else None
         if m._fwd_wait is None:
             torch.cuda.current_stream().wait_stream(self._shard_sync.gather_stream)

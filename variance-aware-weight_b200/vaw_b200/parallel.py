@@ -167,57 +167,90 @@ class ShardedGradSync(FlatGradSync):
                 (owned if k == "rs" else replicated).append(self._slice(b, e) if k == "rs" else (b, e))
         return owned, replicated
 
+    @contextmanager
+    def _one_launch(self):
+        """Collectives of ONE kind issued inside become a single NCCL group (one kernel launch): c10d's coalescing
+        manager; plain back-to-back calls if this torch does not have it."""
+        try:
+            from torch.distributed.distributed_c10d import _coalescing_manager
+        except ImportError:  # pragma: no cover
+            yield
+            return
+        with _coalescing_manager(group=self.group):
+            yield
+
     def launch(self, events=None):
+        """Per bucket (gated by its event): the reduce-scatters of its large tensors as one launch.  The small
+        replicated tensors of ALL buckets (biases; a few MB in total, each all-reduce latency-bound) are averaged by one
+        grouped all-reduce after the last bucket instead of two ~100 us collectives per block on the critical tail."""
         if not self.enabled or self.world == 1:
             return
         with torch.cuda.stream(self.stream):
+            deferred = []
             for i, bk in enumerate(self.kinds):
                 if events is not None and events[i] is not None:
                     self.stream.wait_event(events[i])
                 else:
                     self.stream.wait_stream(torch.cuda.default_stream())
-                for k, b, e in bk:
-                    if k == "ar":
+                rs = [(b, e) for k, b, e in bk if k == "rs"]
+                deferred += [(b, e) for k, b, e in bk if k == "ar"]
+                if rs:
+                    with self._one_launch():
+                        for b, e in rs:
+                            lo, hi = self._slice(b, e)
+                            dist.reduce_scatter_tensor(self.gflat[lo:hi], self.gflat[b:e], op=dist.ReduceOp.AVG,
+                                                       group=self.group)
+            if deferred:
+                with self._one_launch():
+                    for b, e in deferred:
                         dist.all_reduce(self.gflat[b:e], op=dist.ReduceOp.AVG, group=self.group)
-                    else:
-                        lo, hi = self._slice(b, e)
-                        dist.reduce_scatter_tensor(self.gflat[lo:hi], self.gflat[b:e], op=dist.ReduceOp.AVG, group=self.group)
 
-    def all_gather(self, buf, wait=True, first=None):
+    def _gather(self, buf, ranges):
+        with self._one_launch():
+            for b, e in ranges:
+                lo, hi = self._slice(b, e)
+                dist.all_gather_into_tensor(buf[b:e], buf[lo:hi], group=self.group)
+
+    def gather_first(self, buf, first):
+        """Start completing `buf` with the reduce-scattered ranges for which first(b, e) holds (one launch), after
+        everything enqueued so far on the current stream; returns the event that marks their completion.  Lets the
+        optimizer update and publish the tensors the forward reads first while it is still updating the rest."""
+        self.gather_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.gather_stream):
+            self._gather(buf, [(b, e) for bk in reversed(self.kinds) for k, b, e in bk if k == "rs" and first(b, e)])
+            ev = torch.cuda.Event()
+            ev.record(self.gather_stream)
+        return ev
+
+    def all_gather(self, buf, wait=True, first=None, first_done=None):
         """Complete `buf` (the bf16 shadow, or the fp32 master) from the owners' slices, in place, on a side stream that
         starts after everything enqueued so far (the optimizer step).  Buckets are gathered in FORWARD order (the reverse
-        of their completion order in backward); ranges for which `first(b, e)` is true go before everything else.
+        of their completion order in backward); ranges for which `first(b, e)` is true go before everything else (or
+        were already started by gather_first(), whose event is passed as `first_done`).
         wait=False returns one CUDA event per step of that schedule instead of blocking the current stream:
-        [after the `first` ranges, after bucket L-1 (= block 0), ..., after bucket 0's predecessor ...]."""
+        [after the `first` ranges, after bucket L-1 (= block 0), after bucket L-2, ...]."""
         cur = torch.cuda.current_stream()
         self.gather_stream.wait_stream(cur)
         events = []
-
-        def gather(b, e):
-            lo, hi = self._slice(b, e)
-            dist.all_gather_into_tensor(buf[b:e], buf[lo:hi], group=self.group)
-
+        order = list(reversed(self.kinds))
         with torch.cuda.stream(self.gather_stream):
-            order = list(reversed(self.kinds))
-            if first is not None:
+            if wait:      # nobody consumes it piecewise: one launch for everything
+                self._gather(buf, [(b, e) for bk in order for k, b, e in bk if k == "rs"])
+            else:
+                if first_done is not None:
+                    events.append(first_done)
+                elif first is not None:
+                    self._gather(buf, [(b, e) for bk in order for k, b, e in bk if k == "rs" and first(b, e)])
+                    ev = torch.cuda.Event()
+                    ev.record(self.gather_stream)
+                    events.append(ev)
                 for bk in order:
-                    for k, b, e in bk:
-                        if k == "rs" and first(b, e):
-                            gather(b, e)
-                if not wait:
-                    ev = torch.cuda.Event()
-                    ev.record(self.gather_stream)
-                    events.append(ev)
-            for bk in order:
-                did = False
-                for k, b, e in bk:
-                    if k == "rs" and not (first is not None and first(b, e)):
-                        gather(b, e)
-                        did = True
-                if did and not wait:
-                    ev = torch.cuda.Event()
-                    ev.record(self.gather_stream)
-                    events.append(ev)
+                    rest = [(b, e) for k, b, e in bk if k == "rs" and not (first is not None and first(b, e))]
+                    if rest:
+                        self._gather(buf, rest)
+                        ev = torch.cuda.Event()
+                        ev.record(self.gather_stream)
+                        events.append(ev)
         if wait:
             cur.wait_stream(self.gather_stream)
             return None
