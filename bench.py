@@ -506,7 +506,7 @@ def block_gemm_calls(batch, D, dev, tokens=256, family="dit"):
     from vaw_b200 import _lib as L
     M, Hd, T = batch * tokens, 4 * D, tokens
     dit = family == "dit"
-    EPI_RESID = L.EPI_GATE_RES if dit else L.EPI_RES          # adaLN gate + residual (DiT) / plain residual (U-ViT)
+    EPI_RESID = L.EPI_RES                                     # U-ViT: plain residual in the proj / fc2 epilogues
     EPI_ACT = L.EPI_GELU_TANH if dit else L.EPI_GELU_ERF
     EPI_DACT = L.EPI_DGELU_TANH if dit else L.EPI_DGELU_ERF
     bf = lambda *s: torch.randn(*s, device=dev).bfloat16()
@@ -533,9 +533,12 @@ def block_gemm_calls(batch, D, dev, tokens=256, family="dit"):
 
     calls = [
         mk(xn, D, 0, Wqkv, D, 0, M, 3 * D, D, L.EPI_BF16, qkv, bias_=bias[3 * D]),                       # qkv
-        mk(attn_o, D, 0, Wproj, D, 0, M, D, D, EPI_RESID, y_bf if dit else None, x_out, bias[D], x_res, gate if dit else None),   # proj
+        # DiT: proj / fc2 are plain bf16-output GEMMs, the gated residual update runs in the next LayerNorm pass
+        (mk(attn_o, D, 0, Wproj, D, 0, M, D, D, L.EPI_BF16, y_bf, bias_=bias[D]) if dit else
+         mk(attn_o, D, 0, Wproj, D, 0, M, D, D, EPI_RESID, None, x_out, bias[D], x_res, None)),          # proj
         mk(xn, D, 0, Wfc1, D, 0, M, Hd, D, EPI_ACT, h_pre, h_act, bias[Hd]),                              # fc1
-        mk(h_act, Hd, 0, Wfc2, Hd, 0, M, D, Hd, EPI_RESID, y_bf if dit else None, x_out, bias[D], x_res, gate if dit else None),  # fc2
+        (mk(h_act, Hd, 0, Wfc2, Hd, 0, M, D, Hd, L.EPI_BF16, y_bf, bias_=bias[D]) if dit else
+         mk(h_act, Hd, 0, Wfc2, Hd, 0, M, D, Hd, EPI_RESID, None, x_out, bias[D], x_res, None)),         # fc2
         mk(dy, D, 1, h_act, Hd, 1, D, Hd, M, L.EPI_F32, gWfc2, split=True),                               # wgrad fc2
         mk(dy, D, 0, Wfc2, Hd, 1, M, Hd, D, EPI_DACT, dh, aux=h_pre),                                     # dgrad fc2
         mk(dh, Hd, 1, xn, D, 1, Hd, D, M, L.EPI_F32, gWfc1, split=True),                                  # wgrad fc1

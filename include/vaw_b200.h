@@ -281,6 +281,13 @@ int vaw_attn_bwd_ws(const void* qkv, const void* o, const void* d_o, const float
 int vaw_ln_fwd(const float* x, const float* shift, const float* scale, long long ld_mod, int rows_per_sample,
                const float* weight, const float* bias, void* y, float* mean, float* rstd, int M, int D, float eps,
                vaw_stream_t stream);
+/* Residual update of the previous branch fused into the LayerNorm + modulate of the next one (models/dit.py:133-137:
+ * x = x + gate.unsqueeze(1) * branch, then modulate(norm(x), shift, scale)), one pass over the row:
+ *   x_out[r, :] = x[r, :] + gate[r / rows_per_sample, :] * branch[r, :]      (branch bf16 [M, D], gate fp32 row stride ld_gate)
+ *   y[r, :]     = LN(x_out[r, :]) * (1 + scale[n, :]) + shift[n, :]          (bf16), mean / rstd [M] as vaw_ln_fwd */
+int vaw_ln_fwd_res(const float* x, const void* branch, const float* gate, long long ld_gate, float* x_out,
+                   const float* shift, const float* scale, long long ld_mod, int rows_per_sample, void* y, float* mean,
+                   float* rstd, int M, int D, float eps, vaw_stream_t stream);
 int vaw_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
                long long ld_mod, const float* weight, float* dx_io, int add_into, float* part, int rows_per_group,
                int groups, int chunks, int M, int D, vaw_stream_t stream);

@@ -20,6 +20,46 @@ L.register("vaw_finish_group", [P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_lo
 L.register("vaw_finish_all", [P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_longlong, P, C.c_int, P])
 
 
+L.register("vaw_ln_fwd_res", [P] * 3 + [C.c_longlong] + [P] * 3 + [C.c_longlong, C.c_int] + [P] * 3 + [C.c_int, C.c_int, C.c_float, P])
+
+
+@pytest.mark.parametrize("B,T,D", [(4, 256, 1152), (3, 258, 768), (5, 64, 384), (2, 100, 132), (2, 64, 2048), (1, 1, 128)])
+def test_layernorm_fwd_with_the_previous_branch_folded_in(B, T, D):
+    """vaw_ln_fwd_res: x_out = x + gate * branch (fp32, one fma per element: bit-exact against torch.addcmul on the same
+    bf16 branch), then LayerNorm + modulate of x_out - the same numbers vaw_ln_fwd gives on x_out."""
+    torch.manual_seed(B * 7 + D)
+    M = B * T
+    x = torch.randn(M, D, device=DEV) * 1.5 + 0.3
+    branch = torch.randn(M, D, device=DEV).bfloat16()
+    mod = torch.randn(B, 6 * D, device=DEV) * 0.3                    # [.., gate at 2D, shift at 3D, scale at 4D, ..]
+    gate, shift, scale = mod[:, 2 * D:3 * D], mod[:, 3 * D:4 * D], mod[:, 4 * D:5 * D]
+    pad = 1024
+    xo_buf = torch.full((M * D + 2 * pad,), 7.0, device=DEV)
+    x_out = xo_buf[pad:pad + M * D].view(M, D)
+    y = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    L.call("vaw_ln_fwd_res", x.data_ptr(), branch.data_ptr(), gate.data_ptr(), 6 * D, x_out.data_ptr(), shift.data_ptr(),
+           scale.data_ptr(), 6 * D, T, y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), M, D, 1e-6, L.stream_ptr())
+    g = gate.repeat_interleave(T, 0)
+    want = torch.addcmul(x.double(), g.double(), branch.double()).float()     # correctly rounded fma
+    assert torch.equal(x_out, want)
+    assert bool((xo_buf[:pad] == 7.0).all()) and bool((xo_buf[-pad:] == 7.0).all())
+    y2 = torch.empty_like(y); mean2, rstd2 = torch.empty_like(mean), torch.empty_like(rstd)
+    L.call("vaw_ln_fwd", x_out.data_ptr(), shift.data_ptr(), scale.data_ptr(), 6 * D, T, None, None, y2.data_ptr(),
+           mean2.data_ptr(), rstd2.data_ptr(), M, D, 1e-6, L.stream_ptr())
+    assert torch.equal(y, y2) and torch.equal(mean, mean2) and torch.equal(rstd, rstd2)
+    y_ref, _ = _ln_ref(want, (1 + scale).repeat_interleave(T, 0), shift.repeat_interleave(T, 0))
+    assert relerr(y, y_ref) < 4e-3
+
+
+def test_layernorm_fwd_res_rejects_bad_arguments():
+    x = torch.zeros(4, 128, device=DEV)
+    b = torch.zeros(4, 128, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(L.VawError):
+        L.call("vaw_ln_fwd_res", x.data_ptr(), None, x.data_ptr(), 128, x.data_ptr(), x.data_ptr(), x.data_ptr(), 128, 4,
+               b.data_ptr(), x.data_ptr(), x.data_ptr(), 4, 128, 1e-6, L.stream_ptr())
+
+
 def _ln_ref(x, A, Bv, eps=1e-6):
     xh = torch.nn.functional.layer_norm(x, x.shape[-1:], eps=eps)
     return xh * A + Bv, xh

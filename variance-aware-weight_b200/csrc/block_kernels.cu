@@ -23,12 +23,22 @@ constexpr int kMaxD = 2048;  // ln_fwd keeps a row in registers: KV = ceil(D / 1
 // ---------------------------------------------------------------------------------------------------
 constexpr int kLnRowsPerWarp = 4;
 
-template <int KV>
+// RES: the row that is normalised is the residual update of the PREVIOUS branch, x_out = x + gate[n, :] * branch, which
+// is formed here (and written out for the backward pass / the next residual) instead of in the epilogue of the GEMM
+// that produced `branch`: that GEMM becomes a plain bf16-output GEMM and the fp32 residual stream is read once.
+struct LnRes {
+  const bf16* branch;   // [M, D] output of the previous branch (attention projection / MLP), bias included
+  const float* gate;    // [n, :] adaLN-Zero gate of that branch, row stride ld_gate
+  long long ld_gate;
+  float* x_out;         // [M, D] updated residual stream
+};
+
+template <int KV, bool RES>
 __global__ void __launch_bounds__(256, KV <= 9 ? 4 : 2)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
               long long ld_mod, int rows_per_sample, const float* __restrict__ weight,
               const float* __restrict__ bias, bf16* __restrict__ y, float* __restrict__ mean_out,
-              float* __restrict__ rstd_out, int M, int D, float eps) {
+              float* __restrict__ rstd_out, int M, int D, float eps, LnRes res) {
   const int lane = threadIdx.x & 31;
   const int nv = D >> 2;  // float4 per row
   const int row_base = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kLnRowsPerWarp;
@@ -44,6 +54,16 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ shift, cons
       const int idx = i * 32 + lane;
       if (idx < nv) {
         v[i] = ldg_stream_f4(xr + idx);
+        if constexpr (RES) {
+          const uint2 br = ldg_stream_u2(reinterpret_cast<const uint2*>(res.branch + (long long)row * D) + idx);
+          const float4 g = __ldg(reinterpret_cast<const float4*>(res.gate + (long long)(row / rows_per_sample) * res.ld_gate) + idx);
+          const float2 b01 = unpack_bf16(br.x), b23 = unpack_bf16(br.y);
+          v[i].x = fmaf(g.x, b01.x, v[i].x);
+          v[i].y = fmaf(g.y, b01.y, v[i].y);
+          v[i].z = fmaf(g.z, b23.x, v[i].z);
+          v[i].w = fmaf(g.w, b23.y, v[i].w);
+          stg_stream_f4(reinterpret_cast<float4*>(res.x_out + (long long)row * D) + idx, v[i]);
+        }
         s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
       }
     }
@@ -719,9 +739,37 @@ extern "C" int vaw_ln_fwd(const float* x, const float* shift, const float* scale
   VAW_CHECK_ARG(!scale || rows_per_sample > 0, "vaw_ln_fwd: rows_per_sample");
   const int rows_per_cta = 8 * kLnRowsPerWarp;
   const unsigned grid = (unsigned)((M + rows_per_cta - 1) / rows_per_cta);
-#define VAW_LN_FWD(KV)                                                                                        \
-  ln_fwd_kernel<KV><<<grid, 256, 0, stream>>>(x, shift, scale, ld_mod, rows_per_sample > 0 ? rows_per_sample : 1, \
-                                              weight, bias, (bf16*)y, mean, rstd, M, D, eps)
+#define VAW_LN_FWD(KV)                                                                                               \
+  ln_fwd_kernel<KV, false><<<grid, 256, 0, stream>>>(x, shift, scale, ld_mod, rows_per_sample > 0 ? rows_per_sample : 1, \
+                                                     weight, bias, (bf16*)y, mean, rstd, M, D, eps, LnRes{})
+  if (D <= 384) VAW_LN_FWD(3);
+  else if (D <= 768) VAW_LN_FWD(6);
+  else if (D <= 1152) VAW_LN_FWD(9);
+  else VAW_LN_FWD(16);
+#undef VAW_LN_FWD
+  VAW_LAUNCH_CHECK();
+  return VAW_OK;
+}
+
+// Residual update of the previous branch + LayerNorm + adaLN modulate of the next one in ONE pass over the row
+// (models/dit.py:133-137: x = x + gate.unsqueeze(1) * branch(...), then modulate(norm(x), shift, scale)):
+//   x_out[r, :] = x[r, :] + gate[n, :] * branch[r, :];   y[r, :] = LN(x_out[r, :]) * (1 + scale[n, :]) + shift[n, :]
+extern "C" int vaw_ln_fwd_res(const float* x, const void* branch, const float* gate, long long ld_gate, float* x_out,
+                              const float* shift, const float* scale, long long ld_mod, int rows_per_sample, void* y,
+                              float* mean, float* rstd, int M, int D, float eps, cudaStream_t stream) {
+  VAW_CHECK_ARG(x && branch && gate && x_out && shift && scale && y && mean && rstd && M > 0, "vaw_ln_fwd_res: bad arguments");
+  VAW_CHECK_ARG(D % 4 == 0 && D <= kMaxD, "vaw_ln_fwd_res: D=%d must be a multiple of 4 and <= %d", D, kMaxD);
+  VAW_CHECK_ARG(rows_per_sample > 0 && ld_gate % 4 == 0 && ld_mod % 4 == 0, "vaw_ln_fwd_res: rows_per_sample / strides");
+  VAW_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_out) | reinterpret_cast<uintptr_t>(gate) |
+                  reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(scale)) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(branch) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0,
+                "vaw_ln_fwd_res: operands must be 16-byte aligned (bf16 tensors 8-byte)");
+  const int rows_per_cta = 8 * kLnRowsPerWarp;
+  const unsigned grid = (unsigned)((M + rows_per_cta - 1) / rows_per_cta);
+  const LnRes res{(const bf16*)branch, gate, ld_gate, x_out};
+#define VAW_LN_FWD(KV)                                                                                              \
+  ln_fwd_kernel<KV, true><<<grid, 256, 0, stream>>>(x, shift, scale, ld_mod, rows_per_sample, nullptr, nullptr, (bf16*)y, \
+                                                    mean, rstd, M, D, eps, res)
   if (D <= 384) VAW_LN_FWD(3);
   else if (D <= 768) VAW_LN_FWD(6);
   else if (D <= 1152) VAW_LN_FWD(9);

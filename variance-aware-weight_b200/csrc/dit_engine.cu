@@ -201,7 +201,9 @@ void carve_infer(const vaw_dit_cfg& c, void* base, Ws& w) {
   b.xn1 = k.take<bf16>(M * D); b.qkv = k.take<bf16>(M * 3 * D); b.attn_o = k.take<bf16>(M * D);
   b.xn2 = b.xn1;
   b.h_act = k.take<bf16>(M * Hd);
-  for (int i = 0; i < c.depth; ++i) w.blk[i] = b;   // y_attn / y_mlp / h_pre stay null: not stored
+  b.y_attn = k.take<bf16>(M * D);   // branch output on its way to the next LayerNorm pass (vaw_ln_fwd_res); one buffer:
+  b.y_mlp = b.y_attn;               // each is consumed before the other branch's GEMM writes
+  for (int i = 0; i < c.depth; ++i) w.blk[i] = b;   // h_pre stays null: not stored
   w.meanf = b.mean1; w.rstdf = b.rstd1;
   w.xnf = b.xn1;
   w.out_tok = k.take<bf16>(M * PPC);
@@ -308,6 +310,9 @@ static int dit_forward_impl(const vaw_dit_cfg* cfg, const float* P, const void* 
   TRY(G(w.c_silu, D, 0, Pb + L.off[P_FADA_W], D, 0, B, 2 * D, D, VAW_EPI_F32)
           .out(w.mod_final).bias(P + L.off[P_FADA_B]).run(s));
 
+  // VAW_DIT_GATE_EPI=1 (A/B measurement): the residual updates run in the proj / fc2 GEMM epilogues (VAW_EPI_GATE_RES)
+  static const bool gate_epi = getenv("VAW_DIT_GATE_EPI") && atoi(getenv("VAW_DIT_GATE_EPI")) != 0;
+  bool pending = false;
   for (int i = 0; i < c.depth; ++i) {
     BlockWs& b = w.blk[i];
     const int pb = P_BLOCK0 + i * B_COUNT;
@@ -316,17 +321,42 @@ static int dit_forward_impl(const vaw_dit_cfg* cfg, const float* P, const void* 
     float* x_mid = w.x[2 * i + 1];
     float* x_out = w.x[2 * i + 2];
     TRY(wait_for(1 + i));
-    TRY(vaw_ln_fwd(x_in, mod, mod + D, ldm, T, nullptr, nullptr, b.xn1, b.mean1, b.rstd1, M, D, kLnEps, s));
+    // The residual update  x += gate * branch  of each branch is formed by the LayerNorm pass that FOLLOWS it
+    // (vaw_ln_fwd_res): proj / fc2 are plain bf16-output GEMMs, and the fp32 residual stream is read once instead of by
+    // a GEMM epilogue and again by the LayerNorm.  `pending` = the previous block's MLP branch is not yet folded into
+    // x_in (its x_out buffer is written here).
+    if (pending) {
+      const float* pmod = w.mod_all + (long long)(i - 1) * 6 * D;
+      TRY(vaw_ln_fwd_res(w.x[2 * i - 1], w.blk[i - 1].y_mlp, pmod + 5 * D, ldm, x_in, mod, mod + D, ldm, T, b.xn1, b.mean1,
+                         b.rstd1, M, D, kLnEps, s));
+    } else {
+      TRY(vaw_ln_fwd(x_in, mod, mod + D, ldm, T, nullptr, nullptr, b.xn1, b.mean1, b.rstd1, M, D, kLnEps, s));
+    }
     TRY(G(b.xn1, D, 0, Pb + L.off[pb + B_QKV_W], D, 0, M, 3 * D, D, VAW_EPI_BF16)
             .out(b.qkv).bias(P + L.off[pb + B_QKV_B]).run(s));
     TRY(vaw_attn_fwd(b.qkv, b.attn_o, b.lse, B, T, c.H, hd, s));
-    TRY(G(b.attn_o, D, 0, Pb + L.off[pb + B_PROJ_W], D, 0, M, D, D, VAW_EPI_GATE_RES)
-            .out(b.y_attn, x_mid).bias(P + L.off[pb + B_PROJ_B]).resid(x_in).gate(mod + 2 * D, ldm, T).run(s));
-    TRY(vaw_ln_fwd(x_mid, mod + 3 * D, mod + 4 * D, ldm, T, nullptr, nullptr, b.xn2, b.mean2, b.rstd2, M, D, kLnEps, s));
+    if (gate_epi) {
+      TRY(G(b.attn_o, D, 0, Pb + L.off[pb + B_PROJ_W], D, 0, M, D, D, VAW_EPI_GATE_RES)
+              .out(b.y_attn, x_mid).bias(P + L.off[pb + B_PROJ_B]).resid(x_in).gate(mod + 2 * D, ldm, T).run(s));
+      TRY(vaw_ln_fwd(x_mid, mod + 3 * D, mod + 4 * D, ldm, T, nullptr, nullptr, b.xn2, b.mean2, b.rstd2, M, D, kLnEps, s));
+    } else {
+      TRY(G(b.attn_o, D, 0, Pb + L.off[pb + B_PROJ_W], D, 0, M, D, D, VAW_EPI_BF16)
+              .out(b.y_attn).bias(P + L.off[pb + B_PROJ_B]).run(s));
+      TRY(vaw_ln_fwd_res(x_in, b.y_attn, mod + 2 * D, ldm, x_mid, mod + 3 * D, mod + 4 * D, ldm, T, b.xn2, b.mean2,
+                         b.rstd2, M, D, kLnEps, s));
+    }
     TRY(G(b.xn2, D, 0, Pb + L.off[pb + B_FC1_W], D, 0, M, Hd, D, VAW_EPI_GELU_TANH)
             .out(b.h_pre, b.h_act).bias(P + L.off[pb + B_FC1_B]).run(s));
-    TRY(G(b.h_act, Hd, 0, Pb + L.off[pb + B_FC2_W], Hd, 0, M, D, Hd, VAW_EPI_GATE_RES)
-            .out(b.y_mlp, x_out).bias(P + L.off[pb + B_FC2_B]).resid(x_mid).gate(mod + 5 * D, ldm, T).run(s));
+    // the block whose output feeds the REPA projectors needs x_out right away: it keeps the gated-residual epilogue
+    const bool tap = gate_epi || (c.learn_align && i + 1 == c.encoder_depth);
+    if (tap) {
+      TRY(G(b.h_act, Hd, 0, Pb + L.off[pb + B_FC2_W], Hd, 0, M, D, Hd, VAW_EPI_GATE_RES)
+              .out(b.y_mlp, x_out).bias(P + L.off[pb + B_FC2_B]).resid(x_mid).gate(mod + 5 * D, ldm, T).run(s));
+    } else {
+      TRY(G(b.h_act, Hd, 0, Pb + L.off[pb + B_FC2_W], Hd, 0, M, D, Hd, VAW_EPI_BF16)
+              .out(b.y_mlp).bias(P + L.off[pb + B_FC2_B]).run(s));
+    }
+    pending = !tap;
     if (c.learn_align && i + 1 == c.encoder_depth) {
       const int pd = c.proj_dim, zd = c.z_dim;
       TRY(vaw_cast_f32_bf16(x_out, w.xa, (long long)M * D, s));
@@ -347,8 +377,14 @@ static int dit_forward_impl(const vaw_dit_cfg* cfg, const float* P, const void* 
   }
   // final layer: LN -> modulate -> linear -> unpatchify
   float* x_last = w.x[2 * c.depth];
-  TRY(vaw_ln_fwd(x_last, w.mod_final, w.mod_final + D, 2LL * D, T, nullptr, nullptr, w.xnf, w.meanf, w.rstdf, M, D,
-                 kLnEps, s));
+  if (pending) {
+    const float* pmod = w.mod_all + (long long)(c.depth - 1) * 6 * D;
+    TRY(vaw_ln_fwd_res(w.x[2 * c.depth - 1], w.blk[c.depth - 1].y_mlp, pmod + 5 * D, ldm, x_last, w.mod_final,
+                       w.mod_final + D, 2LL * D, T, w.xnf, w.meanf, w.rstdf, M, D, kLnEps, s));
+  } else {
+    TRY(vaw_ln_fwd(x_last, w.mod_final, w.mod_final + D, 2LL * D, T, nullptr, nullptr, w.xnf, w.meanf, w.rstdf, M, D,
+                   kLnEps, s));
+  }
   TRY(G(w.xnf, D, 0, Pb + L.off[P_FLIN_W], D, 0, M, PPC, D, VAW_EPI_BF16).out(w.out_tok).bias(P + L.off[P_FLIN_B]).run(s));
   TRY(vaw_unpatchify(w.out_tok, out, 1, B, c.C_out, c.img_h, c.img_w, c.P, 1, s));
   return VAW_OK;

@@ -74,6 +74,7 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 }
 
 // streaming 128-bit global accesses (inputs read once / outputs written once)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"

@@ -73,6 +73,9 @@ int vaw_attn_bwd_ws(const void* qkv, const void* o, const void* d_o, const float
 int vaw_ln_fwd(const float* x, const float* shift, const float* scale, long long ld_mod, int rows_per_sample,
                const float* weight, const float* bias, void* y, float* mean, float* rstd, int M, int D, float eps,
                cudaStream_t stream);
+int vaw_ln_fwd_res(const float* x, const void* branch, const float* gate, long long ld_gate, float* x_out,
+                   const float* shift, const float* scale, long long ld_mod, int rows_per_sample, void* y, float* mean,
+                   float* rstd, int M, int D, float eps, cudaStream_t stream);
 int vaw_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
                long long ld_mod, const float* weight, float* dx_io, int add_into, float* part, int rows_per_group,
                int groups, int chunks, int M, int D, cudaStream_t stream);
