@@ -511,7 +511,11 @@ def block_gemm_calls(batch, D, dev, tokens=256, family="dit"):
     EPI_DACT = L.EPI_DGELU_TANH if dit else L.EPI_DGELU_ERF
     bf = lambda *s: torch.randn(*s, device=dev).bfloat16()
     f32 = lambda *s: torch.randn(*s, device=dev)
-    xn, attn_o, h_act, h_pre = bf(M, D), bf(M, D), bf(M, Hd), bf(M, Hd)
+    # DiT: the LayerNorm outputs carry a [1, 0 x 31] block behind every row; the qkv / fc1 weight-gradient GEMMs read them
+    # as [M, D + 32] and return the bias gradient as an extra output column (VAW_EPI_F32 row-sum form)
+    ldx = D + 32 if dit else D
+    xn, attn_o, h_act, h_pre = bf(M, ldx), bf(M, D), bf(M, Hd), bf(M, Hd)
+    gb_fc1, gb_qkv = f32(Hd), f32(3 * D)
     qkv, dqkv, dh, dy = bf(M, 3 * D), bf(M, 3 * D), bf(M, Hd), bf(M, D)
     Wqkv, Wproj, Wfc1, Wfc2 = bf(3 * D, D), bf(D, D), bf(Hd, D), bf(D, Hd)
     x_res, gate = f32(M, D), f32(batch, D)
@@ -525,27 +529,30 @@ def block_gemm_calls(batch, D, dev, tokens=256, family="dit"):
         g = L.GemmArgs()
         g.A, g.B, g.lda, g.ldb, g.a_mn, g.b_mn = A.data_ptr(), Bm.data_ptr(), lda, ldb, a_mn, b_mn
         g.M, g.N, g.K, g.epilogue = m, n, k, epi
+        n_alg = n - 32 if (epi == L.EPI_F32 and out2 is not None) else n     # the ones block is not algorithmic work
         g.out, g.out2, g.bias, g.resid = L.ptr(out), L.ptr(out2), L.ptr(bias_), L.ptr(resid)
         g.gate, g.aux, g.rows_per_sample, g.ldg = L.ptr(gate_), L.ptr(aux), T, D
         if split:
             g.k_splits, g.split_ws, g.split_ws_elems = -1, ws.data_ptr(), ws.numel()
-        return (lambda: L.call("vaw_gemm_bf16", C.byref(g), L.stream_ptr())), 2.0 * m * n * k
+        return (lambda: L.call("vaw_gemm_bf16", C.byref(g), L.stream_ptr())), 2.0 * m * n_alg * k
 
     calls = [
-        mk(xn, D, 0, Wqkv, D, 0, M, 3 * D, D, L.EPI_BF16, qkv, bias_=bias[3 * D]),                       # qkv
+        mk(xn, ldx, 0, Wqkv, D, 0, M, 3 * D, D, L.EPI_BF16, qkv, bias_=bias[3 * D]),                     # qkv
         # DiT: proj / fc2 are plain bf16-output GEMMs, the gated residual update runs in the next LayerNorm pass
         (mk(attn_o, D, 0, Wproj, D, 0, M, D, D, L.EPI_BF16, y_bf, bias_=bias[D]) if dit else
          mk(attn_o, D, 0, Wproj, D, 0, M, D, D, EPI_RESID, None, x_out, bias[D], x_res, None)),          # proj
-        mk(xn, D, 0, Wfc1, D, 0, M, Hd, D, EPI_ACT, h_pre, h_act, bias[Hd]),                              # fc1
+        mk(xn, ldx, 0, Wfc1, D, 0, M, Hd, D, EPI_ACT, h_pre, h_act, bias[Hd]),                            # fc1
         (mk(h_act, Hd, 0, Wfc2, Hd, 0, M, D, Hd, L.EPI_BF16, y_bf, bias_=bias[D]) if dit else
          mk(h_act, Hd, 0, Wfc2, Hd, 0, M, D, Hd, EPI_RESID, None, x_out, bias[D], x_res, None)),         # fc2
         mk(dy, D, 1, h_act, Hd, 1, D, Hd, M, L.EPI_F32, gWfc2, split=True),                               # wgrad fc2
         mk(dy, D, 0, Wfc2, Hd, 1, M, Hd, D, EPI_DACT, dh, aux=h_pre),                                     # dgrad fc2
-        mk(dh, Hd, 1, xn, D, 1, Hd, D, M, L.EPI_F32, gWfc1, split=True),                                  # wgrad fc1
+        (mk(dh, Hd, 1, xn, ldx, 1, Hd, ldx, M, L.EPI_F32, gWfc1, gb_fc1, split=True) if dit else
+         mk(dh, Hd, 1, xn, D, 1, Hd, D, M, L.EPI_F32, gWfc1, split=True)),                                # wgrad fc1 (+ bias)
         mk(dh, Hd, 0, Wfc1, D, 1, M, D, Hd, L.EPI_BF16, o_bf),                                            # dgrad fc1
         mk(dy, D, 1, attn_o, D, 1, D, D, M, L.EPI_F32, gWproj, split=True),                               # wgrad proj
         mk(dy, D, 0, Wproj, D, 1, M, D, D, L.EPI_BF16, o_bf),                                             # dgrad proj
-        mk(dqkv, 3 * D, 1, xn, D, 1, 3 * D, D, M, L.EPI_F32, gWqkv, split=True),                          # wgrad qkv
+        (mk(dqkv, 3 * D, 1, xn, ldx, 1, 3 * D, ldx, M, L.EPI_F32, gWqkv, gb_qkv, split=True) if dit else
+         mk(dqkv, 3 * D, 1, xn, D, 1, 3 * D, D, M, L.EPI_F32, gWqkv, split=True)),                        # wgrad qkv (+ bias)
         mk(dqkv, 3 * D, 0, Wqkv, D, 1, M, D, 3 * D, L.EPI_BF16, o_bf),                                    # dgrad qkv
     ]
     return [c for c, _ in calls], [f for _, f in calls]

@@ -218,7 +218,11 @@ int vaw_pack_tloss(const long long* t, const float* loss, int* t32, float* l32, 
  * D[M,N] = A[M,K] B[N,K]^T, bf16 operands, fp32 accumulation in TMEM.  Replaces the nn.Linear GEMMs of the DiT /
  * U-ViT blocks (models/dit.py:118-137 via timm Attention/Mlp; models/uvit.py:55-121) in forward, dgrad and wgrad. */
 #define VAW_EPI_BF16 0       /* out(bf16) = acc + bias */
-#define VAW_EPI_F32 1        /* out(f32)  = acc + bias (+= when accumulate) */
+#define VAW_EPI_F32 1        /* out(f32)  = acc + bias (+= when accumulate).  With out2 != NULL ("row-sum form", no bias): the
+                                last 32 columns of B are not part of the output - out is [M, N - 32] (ldo, default N - 32) and
+                                column N - 32 of the product goes to out2[M] (fp32, += when accumulate); with
+                                B = [X | 1 0 ... 0] (vaw_ln_fwd_ex ones_block) one GEMM yields a Linear's weight AND bias
+                                gradient (models/dit.py:126-128 qkv / fc1 under autograd) */
 #define VAW_EPI_GELU_TANH 2  /* out(bf16) = pre ; out2(bf16) = gelu_tanh(pre) */
 #define VAW_EPI_GELU_ERF 3   /* out(bf16) = pre ; out2(bf16) = gelu_erf(pre) */
 #define VAW_EPI_GATE_RES 4   /* out(bf16) = y   ; out2(f32) = resid + gate[row/rows_per_sample] * y */
@@ -288,6 +292,13 @@ int vaw_ln_fwd(const float* x, const float* shift, const float* scale, long long
 int vaw_ln_fwd_res(const float* x, const void* branch, const float* gate, long long ld_gate, float* x_out,
                    const float* shift, const float* scale, long long ld_mod, int rows_per_sample, void* y, float* mean,
                    float* rstd, int M, int D, float eps, vaw_stream_t stream);
+/* General form of the two above.  branch == NULL: no folded-in residual update (gate / x_out unused).  ldy: row stride of
+ * y (0 = D).  ones_block != 0: the 32 bf16 after the D outputs of each row are set to [1, 0, ..., 0] (ldy >= D + 32), so
+ * that a weight-gradient GEMM reading y as [M, D + 32] also returns the bias gradient (VAW_EPI_F32 with out2). */
+int vaw_ln_fwd_ex(const float* x, const void* branch, const float* gate, long long ld_gate, float* x_out,
+                  const float* shift, const float* scale, long long ld_mod, int rows_per_sample, const float* weight,
+                  const float* bias, void* y, long long ldy, int ones_block, float* mean, float* rstd, int M, int D,
+                  float eps, vaw_stream_t stream);
 int vaw_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
                long long ld_mod, const float* weight, float* dx_io, int add_into, float* part, int rows_per_group,
                int groups, int chunks, int M, int D, vaw_stream_t stream);

@@ -105,6 +105,44 @@ def test_tail_split_wgrad_shapes():
         assert torch.equal(out2, out3) and relerr(out2, ref) < 1e-5
 
 
+@pytest.mark.parametrize("Mo,D,Kt", [(4608, 1152, 4096), (3456, 1152, 2048), (1536, 384, 1024), (3072, 768, 2304), (136, 72, 256)])
+def test_weight_and_bias_gradient_in_one_gemm(Mo, D, Kt):
+    """Row-sum form of VAW_EPI_F32 (out2 != NULL): B = [X | 1 0 ... 0] is read as [K, D + 32]; out[Mo, D] = A^T X lands in
+    a dense [Mo, D] buffer (ldo = D), column D of the product - the column sums of A, i.e. a Linear's bias gradient - goes
+    to out2[Mo].  Every tile shape, with and without tail split-K, with accumulate, and nothing written out of bounds."""
+    torch.manual_seed(Mo + D)
+    A = torch.randn(Kt, Mo, device=DEV).bfloat16()
+    X = torch.empty(Kt, D + 32, device=DEV, dtype=torch.bfloat16)
+    X[:, :D] = (torch.randn(Kt, D, device=DEV) * 0.05).bfloat16()
+    X[:, D:] = 0
+    X[:, D] = 1
+    ref_w = A.float().t() @ X[:, :D].float()
+    ref_b = A.float().sum(0)
+    ws = torch.empty(148 * 128 * 256, device=DEV)
+    pad = 4096
+
+    def guarded(n):
+        buf = torch.full((n + 2 * pad,), 7.0, device=DEV)
+        return buf, buf[pad:pad + n]
+
+    for kw in (dict(), dict(k_splits=-1, split_ws=ws), dict(cta_group=1, tile_n=192, k_splits=-1, split_ws=ws),
+               dict(cta_group=2, tile_n=256, k_splits=-1, split_ws=ws), dict(cta_group=1, tile_n=128),
+               dict(cta_group=2, tile_n=128, k_splits=-1, split_ws=ws), dict(cta_group=1, tile_n=256, k_splits=3, split_ws=ws)):
+        if kw.get("cta_group") == 2 and Mo < 256:
+            continue
+        bw, w = guarded(Mo * D)
+        bb, b = guarded(Mo)
+        run_gemm(A, X, 1, 1, Mo, D + 32, Kt, L.EPI_F32, out=w, out2=b, **kw)
+        assert relerr(w.view(Mo, D), ref_w) < 1e-5, kw
+        assert relerr(b, ref_b) < 1e-5, kw
+        run_gemm(A, X, 1, 1, Mo, D + 32, Kt, L.EPI_F32, out=w, out2=b, accumulate=1, **kw)
+        assert relerr(w.view(Mo, D), 2 * ref_w) < 1e-5 and relerr(b, 2 * ref_b) < 1e-5, kw
+        for buf in (bw, bb):
+            assert bool((buf[:pad] == 7.0).all()) and bool((buf[-pad:] == 7.0).all()), kw
+    with pytest.raises(L.VawError):   # the row-sum form takes no bias
+        run_gemm(A, X, 1, 1, Mo, D + 32, Kt, L.EPI_F32, out=w, out2=b, bias=torch.zeros(D + 32, device=DEV))
+
+
 @pytest.mark.parametrize("splits", [2, 7, 24])
 def test_split_k_deterministic_and_correct(splits):
     torch.manual_seed(3)

@@ -52,6 +52,42 @@ def test_layernorm_fwd_with_the_previous_branch_folded_in(B, T, D):
     assert relerr(y, y_ref) < 4e-3
 
 
+L.register("vaw_ln_fwd_ex", [P] * 3 + [C.c_longlong] + [P] * 3 + [C.c_longlong, C.c_int] + [P] * 3 +
+           [C.c_longlong, C.c_int] + [P] * 2 + [C.c_int, C.c_int, C.c_float, P])
+
+
+@pytest.mark.parametrize("B,T,D,fold", [(4, 256, 1152, True), (3, 64, 384, False), (2, 258, 768, True), (2, 33, 136, False)])
+def test_layernorm_fwd_with_row_stride_and_ones_block(B, T, D, fold):
+    """vaw_ln_fwd_ex: the same values as vaw_ln_fwd / vaw_ln_fwd_res in a [M, D + 32] buffer whose 32 trailing columns are
+    [1, 0, ..., 0] in every row (the B operand of the weight + bias gradient GEMM)."""
+    torch.manual_seed(B + D)
+    M = B * T
+    x = torch.randn(M, D, device=DEV) * 1.5 + 0.3
+    branch = torch.randn(M, D, device=DEV).bfloat16()
+    mod = torch.randn(B, 6 * D, device=DEV) * 0.3
+    gate, shift, scale = mod[:, 2 * D:3 * D], mod[:, 3 * D:4 * D], mod[:, 4 * D:5 * D]
+    y = torch.full((M + 2, D + 32), 5.0, device=DEV, dtype=torch.bfloat16)     # one guard row on each side
+    yv = y[1:M + 1]
+    x_out = torch.empty(M, D, device=DEV)
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    L.call("vaw_ln_fwd_ex", x.data_ptr(), branch.data_ptr() if fold else None, gate.data_ptr(), 6 * D, x_out.data_ptr(),
+           shift.data_ptr(), scale.data_ptr(), 6 * D, T, None, None, yv.data_ptr(), D + 32, 1, mean.data_ptr(), rstd.data_ptr(),
+           M, D, 1e-6, L.stream_ptr())
+    y2 = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    m2, r2 = torch.empty_like(mean), torch.empty_like(rstd)
+    if fold:
+        xo2 = torch.empty_like(x_out)
+        L.call("vaw_ln_fwd_res", x.data_ptr(), branch.data_ptr(), gate.data_ptr(), 6 * D, xo2.data_ptr(), shift.data_ptr(),
+               scale.data_ptr(), 6 * D, T, y2.data_ptr(), m2.data_ptr(), r2.data_ptr(), M, D, 1e-6, L.stream_ptr())
+        assert torch.equal(x_out, xo2)
+    else:
+        L.call("vaw_ln_fwd", x.data_ptr(), shift.data_ptr(), scale.data_ptr(), 6 * D, T, None, None, y2.data_ptr(),
+               m2.data_ptr(), r2.data_ptr(), M, D, 1e-6, L.stream_ptr())
+    assert torch.equal(yv[:, :D], y2) and torch.equal(mean, m2) and torch.equal(rstd, r2)
+    assert bool((yv[:, D] == 1).all()) and bool((yv[:, D + 1:] == 0).all())
+    assert bool((y[0] == 5).all()) and bool((y[M + 1] == 5).all())
+
+
 def test_layernorm_fwd_res_rejects_bad_arguments():
     x = torch.zeros(4, 128, device=DEV)
     b = torch.zeros(4, 128, device=DEV, dtype=torch.bfloat16)

@@ -32,13 +32,20 @@ struct LnRes {
   long long ld_gate;
   float* x_out;         // [M, D] updated residual stream
 };
+// Output row layout: row stride ldy >= D; ones_block: the 32 bf16 after the D outputs of every row are set to
+// [1, 0, ..., 0] (ldy >= D + 32).  A weight-gradient GEMM that reads y as [M, D + 32] then delivers the bias gradient
+// (the row sums of the other operand) as output column D - no separate column-sum pass over that operand.
+struct LnOut {
+  long long ldy;
+  int ones_block;
+};
 
 template <int KV, bool RES>
 __global__ void __launch_bounds__(256, KV <= 9 ? 4 : 2)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
               long long ld_mod, int rows_per_sample, const float* __restrict__ weight,
               const float* __restrict__ bias, bf16* __restrict__ y, float* __restrict__ mean_out,
-              float* __restrict__ rstd_out, int M, int D, float eps, LnRes res) {
+              float* __restrict__ rstd_out, int M, int D, float eps, LnRes res, LnOut lo) {
   const int lane = threadIdx.x & 31;
   const int nv = D >> 2;  // float4 per row
   const int row_base = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kLnRowsPerWarp;
@@ -83,7 +90,9 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ shift, cons
       rstd_out[row] = rstd;
     }
     const long long mo = scale ? (long long)(row / rows_per_sample) * ld_mod : 0;
-    uint2* yr = reinterpret_cast<uint2*>(y + (long long)row * D);
+    uint2* yr = reinterpret_cast<uint2*>(y + (long long)row * lo.ldy);
+    if (lo.ones_block && lane < 4)   // bf16 1.0 = 0x3F80 in the first of 32 elements
+      reinterpret_cast<uint4*>(y + (long long)row * lo.ldy + D)[lane] = make_uint4(lane == 0 ? 0x00003F80u : 0u, 0u, 0u, 0u);
 #pragma unroll
     for (int i = 0; i < KV; ++i) {
       const int idx = i * 32 + lane;
@@ -729,19 +738,39 @@ inline int threads_for_columns(int D) {
 // ---------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------
-extern "C" int vaw_ln_fwd(const float* x, const float* shift, const float* scale, long long ld_mod,
-                          int rows_per_sample, const float* weight, const float* bias, void* y, float* mean,
-                          float* rstd, int M, int D, float eps, cudaStream_t stream) {
+namespace {
+int launch_ln_fwd(const float* x, const LnRes& res, const float* shift, const float* scale, long long ld_mod,
+                  int rows_per_sample, const float* weight, const float* bias, void* y, const LnOut& lo, float* mean,
+                  float* rstd, int M, int D, float eps, cudaStream_t stream) {
   VAW_CHECK_ARG(x && y && mean && rstd && M > 0, "vaw_ln_fwd: bad arguments");
   VAW_CHECK_ARG(D % 4 == 0 && D <= kMaxD, "vaw_ln_fwd: D=%d must be a multiple of 4 and <= %d", D, kMaxD);
   VAW_CHECK_ARG((scale == nullptr) == (shift == nullptr), "vaw_ln_fwd: shift and scale go together");
   VAW_CHECK_ARG((weight == nullptr) == (bias == nullptr), "vaw_ln_fwd: weight and bias go together");
   VAW_CHECK_ARG(!scale || rows_per_sample > 0, "vaw_ln_fwd: rows_per_sample");
+  VAW_CHECK_ARG(lo.ldy >= D + (lo.ones_block ? 32 : 0) && lo.ldy % 4 == 0 && (!lo.ones_block || (lo.ldy % 8 == 0 && D % 8 == 0)),
+                "vaw_ln_fwd: ldy=%lld too small or misaligned for D=%d", lo.ldy, D);
+  const int rps = rows_per_sample > 0 ? rows_per_sample : 1;
+  if (res.branch) {
+    VAW_CHECK_ARG(res.gate && res.x_out && scale && rows_per_sample > 0 && res.ld_gate % 4 == 0 && ld_mod % 4 == 0,
+                  "vaw_ln_fwd_res: bad arguments");
+    VAW_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(res.x_out) |
+                    reinterpret_cast<uintptr_t>(res.gate) | reinterpret_cast<uintptr_t>(shift) |
+                    reinterpret_cast<uintptr_t>(scale)) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(res.branch) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0,
+                  "vaw_ln_fwd_res: operands must be 16-byte aligned (bf16 tensors 8-byte)");
+  }
+  VAW_CHECK_ARG(!lo.ones_block || (reinterpret_cast<uintptr_t>(y) & 15) == 0, "vaw_ln_fwd: y must be 16-byte aligned");
   const int rows_per_cta = 8 * kLnRowsPerWarp;
   const unsigned grid = (unsigned)((M + rows_per_cta - 1) / rows_per_cta);
-#define VAW_LN_FWD(KV)                                                                                               \
-  ln_fwd_kernel<KV, false><<<grid, 256, 0, stream>>>(x, shift, scale, ld_mod, rows_per_sample > 0 ? rows_per_sample : 1, \
-                                                     weight, bias, (bf16*)y, mean, rstd, M, D, eps, LnRes{})
+#define VAW_LN_FWD(KV)                                                                                                 \
+  do {                                                                                                                 \
+    if (res.branch)                                                                                                    \
+      ln_fwd_kernel<KV, true><<<grid, 256, 0, stream>>>(x, shift, scale, ld_mod, rps, weight, bias, (bf16*)y, mean, rstd, \
+                                                        M, D, eps, res, lo);                                           \
+    else                                                                                                               \
+      ln_fwd_kernel<KV, false><<<grid, 256, 0, stream>>>(x, shift, scale, ld_mod, rps, weight, bias, (bf16*)y, mean,    \
+                                                         rstd, M, D, eps, res, lo);                                    \
+  } while (0)
   if (D <= 384) VAW_LN_FWD(3);
   else if (D <= 768) VAW_LN_FWD(6);
   else if (D <= 1152) VAW_LN_FWD(9);
@@ -750,6 +779,14 @@ extern "C" int vaw_ln_fwd(const float* x, const float* shift, const float* scale
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }
+}  // namespace
+
+extern "C" int vaw_ln_fwd(const float* x, const float* shift, const float* scale, long long ld_mod,
+                          int rows_per_sample, const float* weight, const float* bias, void* y, float* mean,
+                          float* rstd, int M, int D, float eps, cudaStream_t stream) {
+  return launch_ln_fwd(x, LnRes{}, shift, scale, ld_mod, rows_per_sample, weight, bias, y, LnOut{D, 0}, mean, rstd, M, D,
+                       eps, stream);
+}
 
 // Residual update of the previous branch + LayerNorm + adaLN modulate of the next one in ONE pass over the row
 // (models/dit.py:133-137: x = x + gate.unsqueeze(1) * branch(...), then modulate(norm(x), shift, scale)):
@@ -757,26 +794,19 @@ extern "C" int vaw_ln_fwd(const float* x, const float* shift, const float* scale
 extern "C" int vaw_ln_fwd_res(const float* x, const void* branch, const float* gate, long long ld_gate, float* x_out,
                               const float* shift, const float* scale, long long ld_mod, int rows_per_sample, void* y,
                               float* mean, float* rstd, int M, int D, float eps, cudaStream_t stream) {
-  VAW_CHECK_ARG(x && branch && gate && x_out && shift && scale && y && mean && rstd && M > 0, "vaw_ln_fwd_res: bad arguments");
-  VAW_CHECK_ARG(D % 4 == 0 && D <= kMaxD, "vaw_ln_fwd_res: D=%d must be a multiple of 4 and <= %d", D, kMaxD);
-  VAW_CHECK_ARG(rows_per_sample > 0 && ld_gate % 4 == 0 && ld_mod % 4 == 0, "vaw_ln_fwd_res: rows_per_sample / strides");
-  VAW_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_out) | reinterpret_cast<uintptr_t>(gate) |
-                  reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(scale)) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(branch) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0,
-                "vaw_ln_fwd_res: operands must be 16-byte aligned (bf16 tensors 8-byte)");
-  const int rows_per_cta = 8 * kLnRowsPerWarp;
-  const unsigned grid = (unsigned)((M + rows_per_cta - 1) / rows_per_cta);
-  const LnRes res{(const bf16*)branch, gate, ld_gate, x_out};
-#define VAW_LN_FWD(KV)                                                                                              \
-  ln_fwd_kernel<KV, true><<<grid, 256, 0, stream>>>(x, shift, scale, ld_mod, rows_per_sample, nullptr, nullptr, (bf16*)y, \
-                                                    mean, rstd, M, D, eps, res)
-  if (D <= 384) VAW_LN_FWD(3);
-  else if (D <= 768) VAW_LN_FWD(6);
-  else if (D <= 1152) VAW_LN_FWD(9);
-  else VAW_LN_FWD(16);
-#undef VAW_LN_FWD
-  VAW_LAUNCH_CHECK();
-  return VAW_OK;
+  VAW_CHECK_ARG(branch, "vaw_ln_fwd_res: bad arguments");
+  return launch_ln_fwd(x, LnRes{(const bf16*)branch, gate, ld_gate, x_out}, shift, scale, ld_mod, rows_per_sample,
+                       nullptr, nullptr, y, LnOut{D, 0}, mean, rstd, M, D, eps, stream);
+}
+
+// The general form: optional folded-in branch (branch == NULL: none), modulate or affine, output row stride ldy and the
+// optional ones block after each row (see LnOut).
+extern "C" int vaw_ln_fwd_ex(const float* x, const void* branch, const float* gate, long long ld_gate, float* x_out,
+                             const float* shift, const float* scale, long long ld_mod, int rows_per_sample,
+                             const float* weight, const float* bias, void* y, long long ldy, int ones_block, float* mean,
+                             float* rstd, int M, int D, float eps, cudaStream_t stream) {
+  return launch_ln_fwd(x, LnRes{(const bf16*)branch, gate, ld_gate, x_out}, shift, scale, ld_mod, rows_per_sample, weight,
+                       bias, y, LnOut{ldy ? ldy : D, ones_block}, mean, rstd, M, D, eps, stream);
 }
 
 // chunks: number of partial rows per group (ceil(rows_per_group / chunks) must be <= 64); part must hold

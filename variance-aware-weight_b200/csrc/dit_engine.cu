@@ -17,6 +17,7 @@ namespace {
 
 constexpr int kMaxDepth = 64;
 constexpr float kLnEps = 1e-6f;  // dit.py:122,124,147
+constexpr int kOnes = 32;        // width of the ones block behind the rows of xn1 / xn2 (training workspace)
 
 // ---- parameter layout -------------------------------------------------------------------------------------
 enum ParamId : int {
@@ -130,8 +131,10 @@ void carve(const vaw_dit_cfg& c, void* base, Ws& w) {
     BlockWs& b = w.blk[i];
     b.mean1 = k.take<float>(M); b.rstd1 = k.take<float>(M); b.mean2 = k.take<float>(M); b.rstd2 = k.take<float>(M);
     b.lse = k.take<float>(B * c.H * c.T);
-    b.xn1 = k.take<bf16>(M * D); b.qkv = k.take<bf16>(M * 3 * D); b.attn_o = k.take<bf16>(M * D);
-    b.y_attn = k.take<bf16>(M * D); b.xn2 = k.take<bf16>(M * D); b.h_pre = k.take<bf16>(M * Hd);
+    // xn1 / xn2 rows carry a [1, 0 x 31] block after their D values (kOnes): the qkv / fc1 weight-gradient GEMMs read
+    // them as [M, D + 32] and return the bias gradients as output column D
+    b.xn1 = k.take<bf16>(M * (D + kOnes)); b.qkv = k.take<bf16>(M * 3 * D); b.attn_o = k.take<bf16>(M * D);
+    b.y_attn = k.take<bf16>(M * D); b.xn2 = k.take<bf16>(M * (D + kOnes)); b.h_pre = k.take<bf16>(M * Hd);
     b.h_act = k.take<bf16>(M * Hd); b.y_mlp = k.take<bf16>(M * D);
   }
   w.meanf = k.take<float>(M); w.rstdf = k.take<float>(M);
@@ -313,6 +316,8 @@ static int dit_forward_impl(const vaw_dit_cfg* cfg, const float* P, const void* 
   // VAW_DIT_GATE_EPI=1 (A/B measurement): the residual updates run in the proj / fc2 GEMM epilogues (VAW_EPI_GATE_RES)
   static const bool gate_epi = getenv("VAW_DIT_GATE_EPI") && atoi(getenv("VAW_DIT_GATE_EPI")) != 0;
   bool pending = false;
+  const long long ldx = infer ? D : D + kOnes;   // row stride of xn1 / xn2
+  const int ones = infer ? 0 : 1;
   for (int i = 0; i < c.depth; ++i) {
     BlockWs& b = w.blk[i];
     const int pb = P_BLOCK0 + i * B_COUNT;
@@ -327,25 +332,27 @@ static int dit_forward_impl(const vaw_dit_cfg* cfg, const float* P, const void* 
     // x_in (its x_out buffer is written here).
     if (pending) {
       const float* pmod = w.mod_all + (long long)(i - 1) * 6 * D;
-      TRY(vaw_ln_fwd_res(w.x[2 * i - 1], w.blk[i - 1].y_mlp, pmod + 5 * D, ldm, x_in, mod, mod + D, ldm, T, b.xn1, b.mean1,
-                         b.rstd1, M, D, kLnEps, s));
+      TRY(vaw_ln_fwd_ex(w.x[2 * i - 1], w.blk[i - 1].y_mlp, pmod + 5 * D, ldm, x_in, mod, mod + D, ldm, T, nullptr, nullptr,
+                        b.xn1, ldx, ones, b.mean1, b.rstd1, M, D, kLnEps, s));
     } else {
-      TRY(vaw_ln_fwd(x_in, mod, mod + D, ldm, T, nullptr, nullptr, b.xn1, b.mean1, b.rstd1, M, D, kLnEps, s));
+      TRY(vaw_ln_fwd_ex(x_in, nullptr, nullptr, 0, nullptr, mod, mod + D, ldm, T, nullptr, nullptr, b.xn1, ldx, ones,
+                        b.mean1, b.rstd1, M, D, kLnEps, s));
     }
-    TRY(G(b.xn1, D, 0, Pb + L.off[pb + B_QKV_W], D, 0, M, 3 * D, D, VAW_EPI_BF16)
+    TRY(G(b.xn1, ldx, 0, Pb + L.off[pb + B_QKV_W], D, 0, M, 3 * D, D, VAW_EPI_BF16)
             .out(b.qkv).bias(P + L.off[pb + B_QKV_B]).run(s));
     TRY(vaw_attn_fwd(b.qkv, b.attn_o, b.lse, B, T, c.H, hd, s));
     if (gate_epi) {
       TRY(G(b.attn_o, D, 0, Pb + L.off[pb + B_PROJ_W], D, 0, M, D, D, VAW_EPI_GATE_RES)
               .out(b.y_attn, x_mid).bias(P + L.off[pb + B_PROJ_B]).resid(x_in).gate(mod + 2 * D, ldm, T).run(s));
-      TRY(vaw_ln_fwd(x_mid, mod + 3 * D, mod + 4 * D, ldm, T, nullptr, nullptr, b.xn2, b.mean2, b.rstd2, M, D, kLnEps, s));
+      TRY(vaw_ln_fwd_ex(x_mid, nullptr, nullptr, 0, nullptr, mod + 3 * D, mod + 4 * D, ldm, T, nullptr, nullptr, b.xn2, ldx,
+                        ones, b.mean2, b.rstd2, M, D, kLnEps, s));
     } else {
       TRY(G(b.attn_o, D, 0, Pb + L.off[pb + B_PROJ_W], D, 0, M, D, D, VAW_EPI_BF16)
               .out(b.y_attn).bias(P + L.off[pb + B_PROJ_B]).run(s));
-      TRY(vaw_ln_fwd_res(x_in, b.y_attn, mod + 2 * D, ldm, x_mid, mod + 3 * D, mod + 4 * D, ldm, T, b.xn2, b.mean2,
-                         b.rstd2, M, D, kLnEps, s));
+      TRY(vaw_ln_fwd_ex(x_in, b.y_attn, mod + 2 * D, ldm, x_mid, mod + 3 * D, mod + 4 * D, ldm, T, nullptr, nullptr, b.xn2,
+                        ldx, ones, b.mean2, b.rstd2, M, D, kLnEps, s));
     }
-    TRY(G(b.xn2, D, 0, Pb + L.off[pb + B_FC1_W], D, 0, M, Hd, D, VAW_EPI_GELU_TANH)
+    TRY(G(b.xn2, ldx, 0, Pb + L.off[pb + B_FC1_W], D, 0, M, Hd, D, VAW_EPI_GELU_TANH)
             .out(b.h_pre, b.h_act).bias(P + L.off[pb + B_FC1_B]).run(s));
     // the block whose output feeds the REPA projectors needs x_out right away: it keeps the gated-residual epilogue
     const bool tap = gate_epi || (c.learn_align && i + 1 == c.encoder_depth);
@@ -479,6 +486,8 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
   TRY(vaw_finish_group(w.part_d, 0, B, ch, D, w.dmod_final, 2LL * D, 0, s));      // d shift
   TRY(vaw_finish_group(w.part_d, 1, B, ch, D, w.dmod_final + D, 2LL * D, 0, s));  // d scale
 
+  // VAW_DIT_COLSUM_BIAS=1 (A/B measurement): qkv / fc1 bias gradients from separate column-sum passes
+  static const bool colsum_bias = getenv("VAW_DIT_COLSUM_BIAS") && atoi(getenv("VAW_DIT_COLSUM_BIAS")) != 0;
   for (int i = c.depth - 1; i >= 0; --i) {
     BlockWs& b = w.blk[i];
     const int pb = P_BLOCK0 + i * B_COUNT;
@@ -510,9 +519,15 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
     TRY(G(w.dy, D, 1, b.h_act, Hd, 1, D, Hd, M, VAW_EPI_F32).out(Gd + L.off[pb + B_FC2_W]).acc(acc)
             .autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dy, D, 0, Pb + L.off[pb + B_FC2_W], Hd, 1, M, Hd, D, VAW_EPI_DGELU_TANH).out(w.dh).aux(b.h_pre).run(s));
-    TRY(vaw_colsum_bf16(w.dh, Hd, M, Hd, w.cpart, colsum_rows(M, Hd), Gd + L.off[pb + B_FC1_B], acc, s));
-    TRY(G(w.dh, Hd, 1, b.xn2, D, 1, Hd, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_FC1_W]).acc(acc)
-            .autosplit(w.split_ws, w.split_elems).run(s));
+    if (colsum_bias) {   // A/B knob: separate column-sum pass for the bias gradient
+      TRY(vaw_colsum_bf16(w.dh, Hd, M, Hd, w.cpart, colsum_rows(M, Hd), Gd + L.off[pb + B_FC1_B], acc, s));
+      TRY(G(w.dh, Hd, 1, b.xn2, D + kOnes, 1, Hd, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_FC1_W]).acc(acc)
+              .autosplit(w.split_ws, w.split_elems).run(s));
+    } else {
+      // weight and bias gradient of fc1 in one GEMM: xn2 carries the ones block, output column D is sum_rows(dh)
+      TRY(G(w.dh, Hd, 1, b.xn2, D + kOnes, 1, Hd, D + kOnes, M, VAW_EPI_F32)
+              .out(Gd + L.off[pb + B_FC1_W], Gd + L.off[pb + B_FC1_B]).acc(acc).autosplit(w.split_ws, w.split_elems).run(s));
+    }
     TRY(G(w.dh, Hd, 0, Pb + L.off[pb + B_FC1_W], D, 1, M, D, Hd, VAW_EPI_BF16).out(w.dxn).run(s));
     // ---- attention branch: x_mid = x_in + gate_msa * proj(attn(qkv(modulate(LN(x_in))))) ----
     // (its gate backward is fused into the MLP LayerNorm backward)
@@ -522,9 +537,14 @@ extern "C" int vaw_dit_backward(const vaw_dit_cfg* cfg, const float* P, const vo
             .autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dy, D, 0, Pb + L.off[pb + B_PROJ_W], D, 1, M, D, D, VAW_EPI_BF16).out(w.d_o).run(s));
     TRY(vaw_attn_bwd_ws(b.qkv, b.attn_o, w.d_o, b.lse, w.dqkv, w.attn_delta, B, T, c.H, hd, s));
-    TRY(vaw_colsum_bf16(w.dqkv, 3LL * D, M, 3 * D, w.cpart, colsum_rows(M, 3 * D), Gd + L.off[pb + B_QKV_B], acc, s));
-    TRY(G(w.dqkv, 3LL * D, 1, b.xn1, D, 1, 3 * D, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_QKV_W]).acc(acc)
-            .autosplit(w.split_ws, w.split_elems).run(s));
+    if (colsum_bias) {
+      TRY(vaw_colsum_bf16(w.dqkv, 3LL * D, M, 3 * D, w.cpart, colsum_rows(M, 3 * D), Gd + L.off[pb + B_QKV_B], acc, s));
+      TRY(G(w.dqkv, 3LL * D, 1, b.xn1, D + kOnes, 1, 3 * D, D, M, VAW_EPI_F32).out(Gd + L.off[pb + B_QKV_W]).acc(acc)
+              .autosplit(w.split_ws, w.split_elems).run(s));
+    } else {
+      TRY(G(w.dqkv, 3LL * D, 1, b.xn1, D + kOnes, 1, 3 * D, D + kOnes, M, VAW_EPI_F32)   // qkv weight + bias gradient
+              .out(Gd + L.off[pb + B_QKV_W], Gd + L.off[pb + B_QKV_B]).acc(acc).autosplit(w.split_ws, w.split_elems).run(s));
+    }
     TRY(G(w.dqkv, 3LL * D, 0, Pb + L.off[pb + B_QKV_W], D, 1, M, D, 3 * D, VAW_EPI_BF16).out(w.dxn).run(s));
     if (i > 0 && !injects(i - 1)) {   // + the MLP-branch gate backward of block i-1
       TRY(vaw_ln_bwd_gate(w.dxn, w.x[2 * i], b.mean1, b.rstd1, mod + D, ldm, nullptr, w.dx, 1, w.part_d,

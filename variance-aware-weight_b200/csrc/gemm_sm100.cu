@@ -67,6 +67,8 @@ struct EpiParams {
   int resid_mod;    // > 0: the residual is a [resid_mod, N] table indexed by row % resid_mod (pos_embed)
   int accumulate;
   int M, N, K;
+  int n_out;        // EPI_F32: columns [0, n_out) go to out; column n_out (if < N) is a row sum that goes to out2[row]
+                    // (B = [X | 1 0 ... 0]: weight gradient and bias gradient from one GEMM), columns above are dropped
   int a_mn, b_mn;   // operand majorness: 0 = K-major, 1 = MN-major
   // work decomposition (see decode_work): full tiles, then the remaining tiles split along K
   int num_work, full_tiles, tail_splits, kb_per_split;
@@ -218,6 +220,10 @@ __device__ __forceinline__ void epilogue_load(const EpiParams& p, int row, int c
   if (!interior && (row >= p.M || col >= p.N)) return;
   const long long o = (long long)row * p.ldo + col;
   if constexpr (EPI == EPI_F32) {
+    if (col >= p.n_out) {   // the row-sum column (and the padding after it)
+      if (p.accumulate && col == p.n_out && row < p.M) pre.r.x = reinterpret_cast<const float*>(p.out2)[row];
+      return;
+    }
     if (p.accumulate) pre.r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + o);
   }
   if constexpr (EPI == EPI_RES || EPI == EPI_GATE_RES) {
@@ -236,6 +242,10 @@ __device__ __forceinline__ void epilogue_vec4(const EpiParams& p, int row, int c
   if (!interior && (row >= p.M || col >= p.N)) return;
   const long long o = (long long)row * p.ldo + col;
   if constexpr (EPI == EPI_F32) {
+    if (col >= p.n_out) {
+      if (col == p.n_out && row < p.M) reinterpret_cast<float*>(p.out2)[row] = p.accumulate ? pre.r.x + v.x : v.x;
+      return;
+    }
     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
     if (p.accumulate) {
       const float4 d = pre.r;
@@ -855,7 +865,8 @@ constexpr int kFixupSlices = 8;
 template <int TM, int BN>
 __global__ void __launch_bounds__(256)
 splitk_fixup_kernel(const float* __restrict__ ws, int first_tile, int splits, int n_tiles, float* __restrict__ out,
-                    const float* __restrict__ bias, int M, int N, long long ldo, int accumulate) {
+                    const float* __restrict__ bias, int M, int N, long long ldo, int accumulate, int n_out,
+                    float* __restrict__ out2) {
   const int tile = first_tile + blockIdx.x;
   const int m0 = (tile / n_tiles) * TM, n0 = (tile % n_tiles) * BN;
   const float* base = ws + (long long)blockIdx.x * splits * (TM * BN);
@@ -867,6 +878,10 @@ splitk_fixup_kernel(const float* __restrict__ ws, int first_tile, int splits, in
     for (int s = 0; s < splits; ++s) {
       const float4 v = *reinterpret_cast<const float4*>(base + (long long)s * (TM * BN) + r * BN + c);
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    if (n0 + c >= n_out) {   // the row-sum column of EPI_F32 (see EpiParams::n_out)
+      if (n0 + c == n_out) out2[m0 + r] = accumulate ? out2[m0 + r] + a.x : a.x;
+      continue;
     }
     if (bias) {
       const float4 b = *reinterpret_cast<const float4*>(bias + n0 + c);
@@ -1038,7 +1053,12 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
   VAW_CHECK_ARG((((uintptr_t)a->A | (uintptr_t)a->B) & 15) == 0, "vaw_gemm_bf16: operands must be 16-byte aligned");
   VAW_CHECK_ARG(a->epilogue >= 0 && a->epilogue < EPI_COUNT, "vaw_gemm_bf16: unknown epilogue %d", a->epilogue);
   const int epi = a->epilogue;
-  const long long ldo = a->ldo ? a->ldo : a->N;
+  // VAW_EPI_F32 with out2: the last 32 columns of B are not part of the [M, N - 32] output; column N - 32 of the product
+  // (a row sum when B = [X | 1 0 ... 0]) goes to out2[M]
+  const int n_out = (epi == EPI_F32 && a->out2) ? a->N - 32 : a->N;
+  VAW_CHECK_ARG(n_out > 0 && (n_out == a->N || (n_out % 4 == 0 && !a->bias)),
+                "vaw_gemm_bf16: the row-sum form of VAW_EPI_F32 needs N - 32 > 0, a multiple of 4, and no bias");
+  const long long ldo = a->ldo ? a->ldo : n_out;
   VAW_CHECK_ARG(ldo % 8 == 0, "vaw_gemm_bf16: ldo must be a multiple of 8");
   // the epilogues with a second output may drop the first (the saved pre-activation / branch output only the backward
   // pass reads): forward-only callers pass out = NULL and save its HBM writes
@@ -1124,6 +1144,7 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
   p.M = a->M;
   p.N = a->N;
   p.K = a->K;
+  p.n_out = n_out;
   p.a_mn = a->a_mn ? 1 : 0;
   p.b_mn = a->b_mn ? 1 : 0;
 
@@ -1205,7 +1226,7 @@ extern "C" int vaw_gemm_bf16(const vaw_gemm_args* a, cudaStream_t stream) {
     float* o = reinterpret_cast<float*>(a->out);
 #define VAW_FIXUP(TM_, BN_)                                                                                          \
   splitk_fixup_kernel<TM_, BN_><<<dim3(rem, kFixupSlices), 256, 0, stream>>>(a->split_ws, full, splits, n_tiles, o, a->bias, a->M, a->N, \
-                                                         ldo, a->accumulate)
+                                                         ldo, a->accumulate, p.n_out, reinterpret_cast<float*>(a->out2))
     if (pair) {
       if (bn == 128) VAW_FIXUP(256, 128); else if (bn == 192) VAW_FIXUP(256, 192); else VAW_FIXUP(256, 256);
     } else {

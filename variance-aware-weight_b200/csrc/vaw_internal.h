@@ -76,6 +76,10 @@ int vaw_ln_fwd(const float* x, const float* shift, const float* scale, long long
 int vaw_ln_fwd_res(const float* x, const void* branch, const float* gate, long long ld_gate, float* x_out,
                    const float* shift, const float* scale, long long ld_mod, int rows_per_sample, void* y, float* mean,
                    float* rstd, int M, int D, float eps, cudaStream_t stream);
+int vaw_ln_fwd_ex(const float* x, const void* branch, const float* gate, long long ld_gate, float* x_out,
+                  const float* shift, const float* scale, long long ld_mod, int rows_per_sample, const float* weight,
+                  const float* bias, void* y, long long ldy, int ones_block, float* mean, float* rstd, int M, int D,
+                  float eps, cudaStream_t stream);
 int vaw_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* scale,
                long long ld_mod, const float* weight, float* dx_io, int add_into, float* part, int rows_per_group,
                int groups, int chunks, int M, int D, cudaStream_t stream);
