@@ -247,14 +247,17 @@ class PortCpuStep:
 def cpu_step_rate(cfg, batch, steps, warmup):
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
+    import contextlib
     kind = "reference" if _reference_available() else "port"
-    runner = (ReferenceCpuStep if kind == "reference" else PortCpuStep)(cfg, batch)
-    for _ in range(warmup):
-        runner.step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        runner.step()
-    dt = (time.perf_counter() - t0) / max(1, steps)
+    # the reference prints at import time ("attention mode is ..."): stdout carries the JSON line and nothing else
+    with contextlib.redirect_stdout(sys.stderr):
+        runner = (ReferenceCpuStep if kind == "reference" else PortCpuStep)(cfg, batch)
+        for _ in range(warmup):
+            runner.step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            runner.step()
+        dt = (time.perf_counter() - t0) / max(1, steps)
     return batch / dt, dt, torch.get_num_threads(), kind
 
 
