@@ -514,10 +514,12 @@ def block_gemm_calls(batch, D, dev, tokens=256, family="dit"):
     EPI_DACT = L.EPI_DGELU_TANH if dit else L.EPI_DGELU_ERF
     bf = lambda *s: torch.randn(*s, device=dev).bfloat16()
     f32 = lambda *s: torch.randn(*s, device=dev)
-    # DiT: the LayerNorm outputs carry a [1, 0 x 31] block behind every row; the qkv / fc1 weight-gradient GEMMs read them
-    # as [M, D + 32] and return the bias gradient as an extra output column (VAW_EPI_F32 row-sum form)
+    # The LayerNorm outputs carry a [1, 0 x 31] block behind every row; the fc1 (and, in DiT, where qkv has a bias, the
+    # qkv) weight-gradient GEMM reads them as [M, D + 32] and returns the bias gradient as an extra output column
+    # (VAW_EPI_F32 row-sum form)
     ldx = D + 32 if dit else D
-    xn, attn_o, h_act, h_pre = bf(M, ldx), bf(M, D), bf(M, Hd), bf(M, Hd)
+    ldf = D + 32
+    xn, xn2, attn_o, h_act, h_pre = bf(M, ldx), bf(M, ldf), bf(M, D), bf(M, Hd), bf(M, Hd)
     gb_fc1, gb_qkv = f32(Hd), f32(3 * D)
     qkv, dqkv, dh, dy = bf(M, 3 * D), bf(M, 3 * D), bf(M, Hd), bf(M, D)
     Wqkv, Wproj, Wfc1, Wfc2 = bf(3 * D, D), bf(D, D), bf(Hd, D), bf(D, Hd)
@@ -544,13 +546,12 @@ def block_gemm_calls(batch, D, dev, tokens=256, family="dit"):
         # DiT: proj / fc2 are plain bf16-output GEMMs, the gated residual update runs in the next LayerNorm pass
         (mk(attn_o, D, 0, Wproj, D, 0, M, D, D, L.EPI_BF16, y_bf, bias_=bias[D]) if dit else
          mk(attn_o, D, 0, Wproj, D, 0, M, D, D, EPI_RESID, None, x_out, bias[D], x_res, None)),          # proj
-        mk(xn, ldx, 0, Wfc1, D, 0, M, Hd, D, EPI_ACT, h_pre, h_act, bias[Hd]),                            # fc1
+        mk(xn2, ldf, 0, Wfc1, D, 0, M, Hd, D, EPI_ACT, h_pre, h_act, bias[Hd]),                           # fc1
         (mk(h_act, Hd, 0, Wfc2, Hd, 0, M, D, Hd, L.EPI_BF16, y_bf, bias_=bias[D]) if dit else
          mk(h_act, Hd, 0, Wfc2, Hd, 0, M, D, Hd, EPI_RESID, None, x_out, bias[D], x_res, None)),         # fc2
         mk(dy, D, 1, h_act, Hd, 1, D, Hd, M, L.EPI_F32, gWfc2, split=True),                               # wgrad fc2
         mk(dy, D, 0, Wfc2, Hd, 1, M, Hd, D, EPI_DACT, dh, aux=h_pre),                                     # dgrad fc2
-        (mk(dh, Hd, 1, xn, ldx, 1, Hd, ldx, M, L.EPI_F32, gWfc1, gb_fc1, split=True) if dit else
-         mk(dh, Hd, 1, xn, D, 1, Hd, D, M, L.EPI_F32, gWfc1, split=True)),                                # wgrad fc1 (+ bias)
+        mk(dh, Hd, 1, xn2, ldf, 1, Hd, ldf, M, L.EPI_F32, gWfc1, gb_fc1, split=True),                     # wgrad fc1 + bias
         mk(dh, Hd, 0, Wfc1, D, 1, M, D, Hd, L.EPI_BF16, o_bf),                                            # dgrad fc1
         mk(dy, D, 1, attn_o, D, 1, D, D, M, L.EPI_F32, gWproj, split=True),                               # wgrad proj
         mk(dy, D, 0, Wproj, D, 1, M, D, D, L.EPI_BF16, o_bf),                                             # dgrad proj

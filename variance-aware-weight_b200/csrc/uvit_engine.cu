@@ -97,7 +97,9 @@ void u_carve(const vaw_uvit_cfg& c, void* base, UWs& w) {
     b.mean1 = k.take<float>(M); b.rstd1 = k.take<float>(M); b.mean2 = k.take<float>(M); b.rstd2 = k.take<float>(M);
     b.lse = k.take<float>(B * c.H * c.T);
     b.xn1 = k.take<bf16>(M * D); b.qkv = k.take<bf16>(M * 3 * D); b.attn_o = k.take<bf16>(M * D);
-    b.xn2 = k.take<bf16>(M * D); b.h_pre = k.take<bf16>(M * Hd); b.h_act = k.take<bf16>(M * Hd);
+    // xn2 rows carry a [1, 0 x 31] block after their D values: the fc1 weight-gradient GEMM reads them as [M, D + 32] and
+    // returns the bias gradient as output column D (row-sum form of VAW_EPI_F32)
+    b.xn2 = k.take<bf16>(M * (D + 32)); b.h_pre = k.take<bf16>(M * Hd); b.h_act = k.take<bf16>(M * Hd);
     b.cat = sk ? k.take<bf16>(M * 2 * D) : nullptr;
     b.dcat = sk ? k.take<bf16>(M * 2 * D) : nullptr;
   }
@@ -221,9 +223,9 @@ extern "C" int vaw_uvit_forward(const vaw_uvit_cfg* cfg, const float* P, const v
     TRY(vaw_attn_fwd(b.qkv, b.attn_o, b.lse, B, T, c.H, hd, s));
     TRY(G(b.attn_o, D, 0, Pb + L.off[pb + UB_PROJ_W], D, 0, M, D, D, VAW_EPI_RES)
             .out(nullptr, b.x_mid).bias(P + L.off[pb + UB_PROJ_B]).resid(x).run(s));
-    TRY(vaw_ln_fwd(b.x_mid, nullptr, nullptr, 0, 1, P + L.off[pb + UB_N2_W], P + L.off[pb + UB_N2_B], b.xn2, b.mean2,
-                   b.rstd2, M, D, kLnEps, s));
-    TRY(G(b.xn2, D, 0, Pb + L.off[pb + UB_FC1_W], D, 0, M, Hd, D, VAW_EPI_GELU_ERF)
+    TRY(vaw_ln_fwd_ex(b.x_mid, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 1, P + L.off[pb + UB_N2_W],
+                      P + L.off[pb + UB_N2_B], b.xn2, D + 32, 1, b.mean2, b.rstd2, M, D, kLnEps, s));
+    TRY(G(b.xn2, D + 32, 0, Pb + L.off[pb + UB_FC1_W], D, 0, M, Hd, D, VAW_EPI_GELU_ERF)
             .out(b.h_pre, b.h_act).bias(P + L.off[pb + UB_FC1_B]).run(s));
     TRY(G(b.h_act, Hd, 0, Pb + L.off[pb + UB_FC2_W], Hd, 0, M, D, Hd, VAW_EPI_RES)
             .out(nullptr, X.xs[i]).bias(P + L.off[pb + UB_FC2_B]).resid(b.x_mid).run(s));
@@ -294,9 +296,8 @@ extern "C" int vaw_uvit_backward_ev(const vaw_uvit_cfg* cfg, const float* P, con
     TRY(G(w.dy, D, 1, b.h_act, Hd, 1, D, Hd, M, VAW_EPI_F32).out(Gd + L.off[pb + UB_FC2_W]).acc(acc)
             .autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dy, D, 0, Pb + L.off[pb + UB_FC2_W], Hd, 1, M, Hd, D, VAW_EPI_DGELU_ERF).out(w.dh).aux(b.h_pre).run(s));
-    TRY(vaw_colsum_bf16(w.dh, Hd, M, Hd, w.cpart, colsum_rows(M, Hd), Gd + L.off[pb + UB_FC1_B], acc, s));
-    TRY(G(w.dh, Hd, 1, b.xn2, D, 1, Hd, D, M, VAW_EPI_F32).out(Gd + L.off[pb + UB_FC1_W]).acc(acc)
-            .autosplit(w.split_ws, w.split_elems).run(s));
+    TRY(G(w.dh, Hd, 1, b.xn2, D + 32, 1, Hd, D + 32, M, VAW_EPI_F32)   // fc1 weight + bias gradient in one GEMM
+            .out(Gd + L.off[pb + UB_FC1_W], Gd + L.off[pb + UB_FC1_B]).acc(acc).autosplit(w.split_ws, w.split_elems).run(s));
     TRY(G(w.dh, Hd, 0, Pb + L.off[pb + UB_FC1_W], D, 1, M, D, Hd, VAW_EPI_BF16).out(w.dxn).run(s));
     TRY(vaw_ln_bwd(w.dxn, b.x_mid, b.mean2, b.rstd2, nullptr, 0, P + L.off[pb + UB_N2_W], w.dx, 1, w.part, T, B, ch, M, D, s));
     TRY(vaw_finish_all(w.part, 0, B, ch, D, nullptr, 0, Gd + L.off[pb + UB_N2_B], acc, s));
