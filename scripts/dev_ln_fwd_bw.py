@@ -7,8 +7,8 @@ from vaw_b200 import _lib as L
 P = C.c_void_p
 L.register("vaw_ln_fwd", [P] * 3 + [C.c_longlong, C.c_int] + [P] * 5 + [C.c_int, C.c_int, C.c_float, P])
 L.register("vaw_ln_fwd_res", [P] * 3 + [C.c_longlong] + [P] * 3 + [C.c_longlong, C.c_int] + [P] * 3 + [C.c_int, C.c_int, C.c_float, P])
-B, T, D = 64, 256, int(os.environ.get("D", 1152)); M = B * T
-n_buf = 6   # rotate buffers: 6 x 340 MB > L2
+B, T, D = int(os.environ.get("B", 64)), 256, int(os.environ.get("D", 1152)); M = B * T
+n_buf = 4   # rotate buffers: 6 x 340 MB > L2
 xs = [torch.randn(M, D, device="cuda") for _ in range(n_buf)]
 brs = [torch.randn(M, D, device="cuda").bfloat16() for _ in range(n_buf)]
 xo = [torch.empty(M, D, device="cuda") for _ in range(n_buf)]
@@ -29,4 +29,4 @@ for name, f, bytes_ in (("ln_fwd", plain, M * D * 6), ("ln_fwd_res", res, M * D 
     for it in range(60): f(it % n_buf)
     b.record(); torch.cuda.synchronize()
     us = a.elapsed_time(b) / 60 * 1e3
-    print(f"VAW_LN_PREFETCH={os.environ.get('VAW_LN_PREFETCH', '1')} {name} M={M} D={D}: {us:.1f} us  {bytes_ / us / 1e3:.0f} GB/s")
+    print(f"{name} M={M} D={D}: {us:.1f} us  {bytes_ / us / 1e3:.0f} GB/s")

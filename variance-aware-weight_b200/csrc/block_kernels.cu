@@ -40,79 +40,124 @@ struct LnOut {
   int ones_block;
 };
 
-template <int KV, bool RES>
-__global__ void __launch_bounds__(256, KV <= 9 ? 4 : 2)
+// EXACT: D == KV * 128, every lane owns KV float4 of the row - no bounds predicates.
+// RPW rows of a warp are in flight together (their loads are issued before anything is reduced, their reductions
+// interleave): a row of D = 384 is 12 registers per lane, and with one such row at a time the kernel ran at 1.3 TB/s -
+// one DRAM round trip, two shuffle reductions and the modulation loads per row, back to back, 26 us for ANY D.
+// The kernel is issue-limited at D = 1152 (ncu: 578 warp instructions per row, issue slots 43 % busy with 26 warps per SM),
+// so the arithmetic is packed two floats per instruction (FADD2 / FMUL2 / FFMA2) and xhat is one fma:
+// (v - mean) * rstd = fma(v, rstd, -mean * rstd).
+template <int KV, bool RES, bool EXACT, int RPW>
+__global__ void __launch_bounds__(256, RPW > 1 ? 2 : (KV <= 9 ? 4 : 2))   // RPW rows per warp in registers: fewer, fatter CTAs
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
               long long ld_mod, int rows_per_sample, const float* __restrict__ weight,
               const float* __restrict__ bias, bf16* __restrict__ y, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, int M, int D, float eps, LnRes res, LnOut lo) {
+  static_assert(kLnRowsPerWarp % RPW == 0, "rows per warp");
   const int lane = threadIdx.x & 31;
   const int nv = D >> 2;  // float4 per row
   const int row_base = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kLnRowsPerWarp;
+  const float2 one2 = make_float2(1.f, 1.f);
 #pragma unroll 1
-  for (int rr = 0; rr < kLnRowsPerWarp; ++rr) {
-    const int row = row_base + rr;
-    if (row >= M) return;
-    const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
-    float4 v[KV];
-    float s = 0.f;
+  for (int rr = 0; rr < kLnRowsPerWarp; rr += RPW) {
+    const int row0 = row_base + rr;
+    if (row0 >= M) return;
+    float4 v[RPW][KV];
+    float2 s2[RPW];
 #pragma unroll
-    for (int i = 0; i < KV; ++i) {
-      const int idx = i * 32 + lane;
-      if (idx < nv) {
-        v[i] = ldg_stream_f4(xr + idx);
-        if constexpr (RES) {
-          const uint2 br = ldg_stream_u2(reinterpret_cast<const uint2*>(res.branch + (long long)row * D) + idx);
-          const float4 g = __ldg(reinterpret_cast<const float4*>(res.gate + (long long)(row / rows_per_sample) * res.ld_gate) + idx);
-          const float2 b01 = unpack_bf16(br.x), b23 = unpack_bf16(br.y);
-          v[i].x = fmaf(g.x, b01.x, v[i].x);
-          v[i].y = fmaf(g.y, b01.y, v[i].y);
-          v[i].z = fmaf(g.z, b23.x, v[i].z);
-          v[i].w = fmaf(g.w, b23.y, v[i].w);
-          stg_stream_f4(reinterpret_cast<float4*>(res.x_out + (long long)row * D) + idx, v[i]);
+    for (int u = 0; u < RPW; ++u) {
+      const int row = row0 + u;
+      s2[u] = make_float2(0.f, 0.f);
+      if (row < M) {
+        const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
+#pragma unroll
+        for (int i = 0; i < KV; ++i) {
+          const int idx = i * 32 + lane;
+          if (EXACT || idx < nv) v[u][i] = ldg_stream_f4(xr + idx);
         }
-        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
       }
     }
-    const float mean = warp_sum(s) / (float)D;
-    float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < KV; ++i) {
-      const int idx = i * 32 + lane;
-      if (idx < nv) {
-        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-        q += (a * a + b * b) + (c * c + d * d);
+    for (int u = 0; u < RPW; ++u) {
+      const int row = row0 + u;
+      if (row < M) {
+#pragma unroll
+        for (int i = 0; i < KV; ++i) {
+          const int idx = i * 32 + lane;
+          if (EXACT || idx < nv) {
+            if constexpr (RES) {
+              const uint2 br = ldg_stream_u2(reinterpret_cast<const uint2*>(res.branch + (long long)row * D) + idx);
+              const float4 g = __ldg(reinterpret_cast<const float4*>(res.gate + (long long)(row / rows_per_sample) * res.ld_gate) + idx);
+              const float2 lo2 = __ffma2_rn(make_float2(g.x, g.y), unpack_bf16(br.x), make_float2(v[u][i].x, v[u][i].y));
+              const float2 hi2 = __ffma2_rn(make_float2(g.z, g.w), unpack_bf16(br.y), make_float2(v[u][i].z, v[u][i].w));
+              v[u][i] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+              stg_stream_f4(reinterpret_cast<float4*>(res.x_out + (long long)row * D) + idx, v[u][i]);
+            }
+            s2[u] = __fadd2_rn(s2[u], __fadd2_rn(make_float2(v[u][i].x, v[u][i].y), make_float2(v[u][i].z, v[u][i].w)));
+          }
+        }
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
-    if (lane == 0) {
-      mean_out[row] = mean;
-      rstd_out[row] = rstd;
-    }
-    const long long mo = scale ? (long long)(row / rows_per_sample) * ld_mod : 0;
-    uint2* yr = reinterpret_cast<uint2*>(y + (long long)row * lo.ldy);
-    if (lo.ones_block && lane < 4)   // bf16 1.0 = 0x3F80 in the first of 32 elements
-      reinterpret_cast<uint4*>(y + (long long)row * lo.ldy + D)[lane] = make_uint4(lane == 0 ? 0x00003F80u : 0u, 0u, 0u, 0u);
+    float mean[RPW], rstd[RPW];
 #pragma unroll
-    for (int i = 0; i < KV; ++i) {
-      const int idx = i * 32 + lane;
-      if (idx < nv) {
-        float4 A = make_float4(1.f, 1.f, 1.f, 1.f), Bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (scale) {
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + mo) + idx);
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + mo) + idx);
-          A = make_float4(1.f + sc.x, 1.f + sc.y, 1.f + sc.z, 1.f + sc.w);
-          Bv = sh;
-        } else if (weight) {
-          A = __ldg(reinterpret_cast<const float4*>(weight) + idx);
-          Bv = __ldg(reinterpret_cast<const float4*>(bias) + idx);
+    for (int u = 0; u < RPW; ++u) mean[u] = warp_sum(s2[u].x + s2[u].y) / (float)D;
+#pragma unroll
+    for (int u = 0; u < RPW; ++u) {
+      const float2 nm = make_float2(-mean[u], -mean[u]);
+      float2 q2 = make_float2(0.f, 0.f);
+      if (row0 + u < M) {
+#pragma unroll
+        for (int i = 0; i < KV; ++i) {
+          const int idx = i * 32 + lane;
+          if (EXACT || idx < nv) {
+            const float2 a = __fadd2_rn(make_float2(v[u][i].x, v[u][i].y), nm), b = __fadd2_rn(make_float2(v[u][i].z, v[u][i].w), nm);
+            q2 = __ffma2_rn(a, a, q2);
+            q2 = __ffma2_rn(b, b, q2);
+          }
         }
-        const float a = (v[i].x - mean) * rstd, b = (v[i].y - mean) * rstd, c = (v[i].z - mean) * rstd,
-                    d = (v[i].w - mean) * rstd;
-        uint2 o;
-        o.x = pack_bf16(fmaf(a, A.x, Bv.x), fmaf(b, A.y, Bv.y));
-        o.y = pack_bf16(fmaf(c, A.z, Bv.z), fmaf(d, A.w, Bv.w));
-        yr[idx] = o;
+      }
+      s2[u] = q2;
+    }
+#pragma unroll
+    for (int u = 0; u < RPW; ++u) rstd[u] = rsqrtf(warp_sum(s2[u].x + s2[u].y) / (float)D + eps);
+#pragma unroll
+    for (int u = 0; u < RPW; ++u) {
+      const int row = row0 + u;
+      if (row >= M) continue;
+      if (lane == 0) {
+        mean_out[row] = mean[u];
+        rstd_out[row] = rstd[u];
+      }
+      const long long mo = scale ? (long long)(row / rows_per_sample) * ld_mod : 0;
+      uint2* yr = reinterpret_cast<uint2*>(y + (long long)row * lo.ldy);
+      if (lo.ones_block && lane < 4)   // bf16 1.0 = 0x3F80 in the first of 32 elements
+        reinterpret_cast<uint4*>(y + (long long)row * lo.ldy + D)[lane] = make_uint4(lane == 0 ? 0x00003F80u : 0u, 0u, 0u, 0u);
+      const float2 r2 = make_float2(rstd[u], rstd[u]), nmr = make_float2(-mean[u] * rstd[u], -mean[u] * rstd[u]);
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        const int idx = i * 32 + lane;
+        if (EXACT || idx < nv) {
+          float2 A0 = one2, A1 = one2, B0 = make_float2(0.f, 0.f), B1 = B0;
+          if (scale) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + mo) + idx);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + mo) + idx);
+            A0 = __fadd2_rn(make_float2(sc.x, sc.y), one2);
+            A1 = __fadd2_rn(make_float2(sc.z, sc.w), one2);
+            B0 = make_float2(sh.x, sh.y);
+            B1 = make_float2(sh.z, sh.w);
+          } else if (weight) {
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(weight) + idx);
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + idx);
+            A0 = make_float2(wv.x, wv.y); A1 = make_float2(wv.z, wv.w);
+            B0 = make_float2(bv.x, bv.y); B1 = make_float2(bv.z, bv.w);
+          }
+          const float2 o0 = __ffma2_rn(__ffma2_rn(make_float2(v[u][i].x, v[u][i].y), r2, nmr), A0, B0);
+          const float2 o1 = __ffma2_rn(__ffma2_rn(make_float2(v[u][i].z, v[u][i].w), r2, nmr), A1, B1);
+          uint2 o;
+          o.x = pack_bf16(o0.x, o0.y);
+          o.y = pack_bf16(o1.x, o1.y);
+          yr[idx] = o;
+        }
       }
     }
   }
@@ -762,20 +807,24 @@ int launch_ln_fwd(const float* x, const LnRes& res, const float* shift, const fl
   VAW_CHECK_ARG(!lo.ones_block || (reinterpret_cast<uintptr_t>(y) & 15) == 0, "vaw_ln_fwd: y must be 16-byte aligned");
   const int rows_per_cta = 8 * kLnRowsPerWarp;
   const unsigned grid = (unsigned)((M + rows_per_cta - 1) / rows_per_cta);
-#define VAW_LN_FWD(KV)                                                                                                 \
-  do {                                                                                                                 \
-    if (res.branch)                                                                                                    \
-      ln_fwd_kernel<KV, true><<<grid, 256, 0, stream>>>(x, shift, scale, ld_mod, rps, weight, bias, (bf16*)y, mean, rstd, \
-                                                        M, D, eps, res, lo);                                           \
-    else                                                                                                               \
-      ln_fwd_kernel<KV, false><<<grid, 256, 0, stream>>>(x, shift, scale, ld_mod, rps, weight, bias, (bf16*)y, mean,    \
-                                                         rstd, M, D, eps, res, lo);                                    \
+#define VAW_LN_FWD_K(KV, RES_, EX_)                                                                                \
+  ln_fwd_kernel<KV, RES_, EX_, (KV <= 3 ? 4 : KV <= 6 ? 2 : 1)><<<grid, 256, 0, stream>>>(                              \
+      x, shift, scale, ld_mod, rps, weight, bias, (bf16*)y, mean, rstd, M, D, eps, res, lo)
+#define VAW_LN_FWD(KV)                                                     \
+  do {                                                                     \
+    const bool exact = D == KV * 128;                                      \
+    if (res.branch) {                                                      \
+      if (exact) VAW_LN_FWD_K(KV, true, true); else VAW_LN_FWD_K(KV, true, false);   \
+    } else {                                                               \
+      if (exact) VAW_LN_FWD_K(KV, false, true); else VAW_LN_FWD_K(KV, false, false); \
+    }                                                                      \
   } while (0)
   if (D <= 384) VAW_LN_FWD(3);
   else if (D <= 768) VAW_LN_FWD(6);
   else if (D <= 1152) VAW_LN_FWD(9);
   else VAW_LN_FWD(16);
 #undef VAW_LN_FWD
+#undef VAW_LN_FWD_K
   VAW_LAUNCH_CHECK();
   return VAW_OK;
 }
