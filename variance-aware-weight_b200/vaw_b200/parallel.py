@@ -98,6 +98,18 @@ class FlatGradSync:
         finally:
             self.enabled = old
 
+    @contextmanager
+    def _one_launch(self):
+        """Collectives of ONE kind issued inside become a single NCCL group (one kernel launch): c10d's coalescing
+        manager; plain back-to-back calls if this torch does not have it."""
+        try:
+            from torch.distributed.distributed_c10d import _coalescing_manager
+        except ImportError:  # pragma: no cover
+            yield
+            return
+        with _coalescing_manager(group=self.group):
+            yield
+
     def _reduce(self, view):
         if self._native_avg:
             dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group)
@@ -121,8 +133,13 @@ class FlatGradSync:
                     self.stream.wait_event(events[i])
                 else:
                     self.stream.wait_stream(torch.cuda.default_stream())
-                for b, e in ranges:
-                    self._reduce(self.gflat[b:e])
+                if self._native_avg and len(ranges) > 1:
+                    with self._one_launch():     # a bucket's ranges (weights, biases, adaLN slice) as ONE NCCL launch
+                        for b, e in ranges:
+                            dist.all_reduce(self.gflat[b:e], op=dist.ReduceOp.AVG, group=self.group)
+                else:
+                    for b, e in ranges:
+                        self._reduce(self.gflat[b:e])
 
     def wait(self):
         if self.stream is not None and self.enabled and self.world > 1:
@@ -166,18 +183,6 @@ class ShardedGradSync(FlatGradSync):
             for k, b, e in bk:
                 (owned if k == "rs" else replicated).append(self._slice(b, e) if k == "rs" else (b, e))
         return owned, replicated
-
-    @contextmanager
-    def _one_launch(self):
-        """Collectives of ONE kind issued inside become a single NCCL group (one kernel launch): c10d's coalescing
-        manager; plain back-to-back calls if this torch does not have it."""
-        try:
-            from torch.distributed.distributed_c10d import _coalescing_manager
-        except ImportError:  # pragma: no cover
-            yield
-            return
-        with _coalescing_manager(group=self.group):
-            yield
 
     def launch(self, events=None):
         """Per bucket (gated by its event): the reduce-scatters of its large tensors as one launch.  The small
