@@ -157,6 +157,12 @@ class FusedAdamW(torch.optim.Optimizer):
             found_inf = found_inf.to(device=flat.device, dtype=torch.float32).reshape(1)
         else:
             found_inf = None
+        shard = getattr(self.model, "_shard_sync", None)
+        if (found_inf is not None or inv_scale is not None) and shard is not None:
+            # sharded mode: a rank sees the averaged gradient only on the slices it owns (elsewhere its own local values),
+            # so GradScaler's per-rank overflow check - and with it the loss scale - could differ between ranks
+            raise L.VawError("FusedAdamW: an enabled GradScaler is not supported with DataParallel(shard_optimizer=True) "
+                             "(bf16 autocast needs no loss scaling: GradScaler(enabled=False))")
         self.step_count += 1   # host-side bias-correction counter; a skipped (inf) step is undone below
         if found_inf is not None:
             # torch's own fused AdamW does `step -= found_inf` on the device; the counter here lives on the host because
@@ -166,6 +172,9 @@ class FusedAdamW(torch.optim.Optimizer):
                 self.step_count -= 1
                 return loss
         clip = None
+        if max_grad_norm and shard is not None:
+            raise L.VawError("FusedAdamW: gradient clipping needs the full gradient on every rank; it is not "
+                             "available with DataParallel(shard_optimizer=True)")
         if max_grad_norm:
             if self.grad_norm is None or self.grad_norm.device != flat.device:
                 self.grad_norm = torch.zeros(2, device=flat.device)
@@ -174,11 +183,7 @@ class FusedAdamW(torch.optim.Optimizer):
                    self._norm_ws.data_ptr(), self.grad_norm.data_ptr(), L.stream_ptr())
             clip = self.grad_norm.data_ptr() + 4
         ema_decay = float(self.ema_decay if self.ema_decay is not None else 0.0)
-        shard = getattr(self.model, "_shard_sync", None)
         if shard is not None:
-            if max_grad_norm:
-                raise L.VawError("FusedAdamW: gradient clipping needs the full gradient on every rank; it is not "
-                                 "available with DataParallel(shard_optimizer=True)")
             self._step_sharded(shard, flat, gflat, shadow, grad_scale, ema_decay, inv_scale, found_inf)
             return loss
         for g, ranges in zip(self.param_groups, self._group_ranges):
